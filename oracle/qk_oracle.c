@@ -1,0 +1,328 @@
+/*
+ * qk_oracle.c -- CPU restatement of QuicK-mer2's `count` path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This file is the checker the CUDA path is compared
+ * against.  Nothing under quick-mer2_b200/ may include, link, or execute it; only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs use it.
+ *
+ * Parity pin: the reference ships no golden vectors for `count`, so
+ * this restatement is pinned against outputs of the reference itself, compiled
+ * unmodified from /root/reference/QuicKmer.c into oracle/_ref/quicKmer2 by
+ * oracle/Makefile.  tests/golden/ holds .bin/.txt fixtures produced by that binary
+ * (tests/golden/make_golden.py); tests/test_oracle.py checks this file against them
+ * and, when oracle/_ref/quicKmer2 is present, against live runs of it.
+ *
+ * Every function cites the lines of QuicKmer.c ("Q.c") it restates.  It is a
+ * restatement, not a copy: serial, single-threaded (the reference's result does not
+ * depend on -t, Q.c:291 vs Q.c:443), with explicit handling of the two inputs on which
+ * the reference has undefined behaviour (flagged in qko_stats.undefined_lines).
+ */
+#define _FILE_OFFSET_BITS 64
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define QKO_LINE_CAP 100000 /* Q.c:388 `char line[100000]`; fgets reads <= 99,999 bytes */
+#define QKO_GC_BINS 401     /* Q.c:495-497 */
+
+typedef struct {
+    uint8_t k;        /* Q.c:346  byte 4 of the .qm header */
+    uint64_t n_slots; /* Q.c:349  Hash_size, bytes 8..15   */
+    uint64_t first;   /* Q.c:351  first_idx, bytes 16..23  */
+    uint64_t *keys;   /* Q.c:359  Hash_size x u64          */
+    uint32_t *next;   /* Q.c:483  Hash_size x u32 chain    */
+} qko_dict;
+
+typedef struct {
+    uint64_t total_kmers;     /* Q.c:445 process_kmers                      */
+    uint64_t hits;            /* emitted keys found in the dictionary        */
+    uint64_t lines;           /* sequence lines processed                    */
+    uint64_t bases;           /* bytes of sequence lines excluding '\n'      */
+    uint64_t undefined_lines; /* lines the reference would run off (T8, T9)  */
+    int fastq;                /* Q.c:395                                     */
+} qko_stats;
+
+/* ---- a-3: Q.c:66-76 --------------------------------------------------------------- */
+uint64_t qko_djb(uint64_t key)
+{
+    uint64_t h = 5381;
+    for (int b = 0; b < 8; ++b) {
+        h = h * 33u + (key & 0xFFu);
+        key >>= 8;
+    }
+    return h;
+}
+
+/* ---- a-4: Q.c:90-99.  Returns 1 and the slot when `key` sits on its probe path. ----
+ * Home slot = djb & (H-1); walk +1 from the lower half, -1 from the upper half, until an
+ * empty slot or the key.  Note that key 0 "matches" the first empty slot (Q.c:98). */
+int qko_find(const qko_dict *d, uint64_t key, uint64_t *slot_out)
+{
+    uint64_t s = qko_djb(key) & (d->n_slots - 1);
+    int64_t step = (s & (d->n_slots >> 1)) ? -1 : 1;
+    while (d->keys[s] != 0 && d->keys[s] != key)
+        s = (uint64_t)((int64_t)s + step);
+    *slot_out = s;
+    return d->keys[s] == key;
+}
+
+/* ---- a-7: Q.c:345-359, 483 --------------------------------------------------------- */
+int qko_dict_load(const char *qm_path, qko_dict *d)
+{
+    memset(d, 0, sizeof *d);
+    FILE *f = fopen(qm_path, "rb");
+    if (!f) return 1;
+    uint8_t hdr[24];
+    if (fread(hdr, 1, 24, f) != 24) { fclose(f); return 2; }
+    d->k = hdr[4];
+    memcpy(&d->n_slots, hdr + 8, 8);
+    memcpy(&d->first, hdr + 16, 8);
+    if (d->n_slots == 0 || (d->n_slots & (d->n_slots - 1))) { fclose(f); return 3; }
+    d->keys = malloc(d->n_slots * sizeof(uint64_t));
+    d->next = malloc(d->n_slots * sizeof(uint32_t));
+    if (!d->keys || !d->next) { fclose(f); return 4; }
+    if (fread(d->keys, 8, d->n_slots, f) != d->n_slots) { fclose(f); return 5; }
+    if (fread(d->next, 4, d->n_slots, f) != d->n_slots) { fclose(f); return 6; }
+    fclose(f);
+    return 0;
+}
+
+void qko_dict_free(qko_dict *d)
+{
+    free(d->keys);
+    free(d->next);
+    memset(d, 0, sizeof *d);
+}
+
+/* Chain length = number of .bin entries (Q.c:498-516: do { } while (c != first)). */
+uint64_t qko_chain_length(const qko_dict *d)
+{
+    uint64_t n = 0;
+    uint32_t c = (uint32_t)d->first;
+    do { ++n; c = d->next[c]; } while (c != (uint32_t)d->first);
+    return n;
+}
+
+/* ---- a-2: Q.c:399-420, one sequence line ------------------------------------------
+ * `line` holds `len` bytes, none of which is '\n' (the terminator is implied at len).
+ * If keys_out != NULL every emitted canonical key is appended (up to cap) -- used by the
+ * codec unit tests; if depth != NULL hits are tallied by hash slot as Q.c:443 does. */
+uint64_t qko_count_line(const qko_dict *d, uint8_t k, const uint8_t *line, size_t len,
+                        uint16_t *depth, uint64_t *keys_out, size_t cap, uint64_t *hits)
+{
+    /* Q.c:419: ((uint64_t)1 << (k<<1)) - 1; x86-64 masks the shift count to 6 bits, so
+     * k=32 gives (1<<0)-1 = 0. */
+    const uint64_t mask = ((uint64_t)1 << ((2u * k) & 63u)) - 1;
+    uint64_t fwd = 0, rc = 0, emitted = 0;
+    uint16_t run = 0; /* Q.c:402 uint16_t cur_chars: wraps at 65,536 (T7) */
+    for (size_t i = 0; i < len; ++i) {
+        uint8_t c = line[i];
+        if (c == 'N') { /* Q.c:404-408: only upper-case N resets (T5) */
+            fwd = 0; rc = 0; run = 0;
+            continue;
+        }
+        ++run;
+        uint64_t code = (c >> 1) & 3u;                 /* Q.c:411 */
+        fwd = (fwd << 2) | code;                       /* Q.c:412-413 */
+        rc |= (uint64_t)((code - 2u) & 3u) << 60;      /* Q.c:414-415 */
+        rc >>= 2;                                      /* Q.c:416: 60-bit register */
+        if (run >= k) {                                /* Q.c:418 */
+            uint64_t key = fwd & mask;                 /* Q.c:419 */
+            if (key > rc) key = rc;                    /* Q.c:420 */
+            if (keys_out && emitted < cap) keys_out[emitted] = key;
+            ++emitted;
+            if (depth) {
+                uint64_t slot;
+                if (qko_find(d, key, &slot)) {         /* Q.c:442-443 */
+                    depth[slot]++;
+                    if (hits && key != 0) ++*hits;
+                }
+            }
+        }
+    }
+    return emitted;
+}
+
+/* Keys of a packed chunk: sequence lines separated by '\n' (the layout the device
+ * consumes).  Returns the number of emitted keys; fills keys_out up to cap. */
+uint64_t qko_chunk_keys(uint8_t k, const uint8_t *bytes, size_t n, uint64_t *keys_out, size_t cap)
+{
+    uint64_t total = 0;
+    size_t start = 0;
+    for (size_t i = 0; i <= n; ++i) {
+        if (i == n || bytes[i] == '\n') {
+            if (i > start || i < n) {
+                size_t room = total < cap ? cap - (size_t)total : 0;
+                total += qko_count_line(NULL, k, bytes + start, i - start, NULL,
+                                        keys_out ? keys_out + (total < cap ? total : cap) : NULL,
+                                        room, NULL);
+            }
+            start = i + 1;
+        }
+    }
+    return total;
+}
+
+/* ---- a-1: Q.c:393-398, 451-455.  fgets(line, 100000, f) semantics ------------------
+ * Reads up to 99,999 bytes, stopping after a '\n'.  Returns the number of bytes stored
+ * (0 at EOF).  *has_nl says whether the stored bytes end in '\n'.  NUL bytes are kept:
+ * the reference's scan loop (Q.c:403) only stops at '\n'. */
+static size_t qko_getline(FILE *f, uint8_t *line, int *has_nl)
+{
+    size_t n = 0;
+    int c;
+    *has_nl = 0;
+    while (n < QKO_LINE_CAP - 1 && (c = getc_unlocked(f)) != EOF) {
+        line[n++] = (uint8_t)c;
+        if (c == '\n') { *has_nl = 1; break; }
+    }
+    return n;
+}
+
+/* Stream a FASTA/FASTQ file; tally depth by hash slot.  Q.c:393-456. */
+int qko_count_stream(const qko_dict *d, FILE *f, uint16_t *depth, qko_stats *st)
+{
+    static uint8_t line[QKO_LINE_CAP];
+    int nl;
+    memset(st, 0, sizeof *st);
+    size_t n = qko_getline(f, line, &nl);       /* Q.c:393 */
+    if (n && line[0] == '@') st->fastq = 1;     /* Q.c:395 */
+    else if (fseeko(f, 0, SEEK_SET) != 0) { /* Q.c:396: on a pipe the first line is lost */ }
+    while ((n = qko_getline(f, line, &nl)) > 0) {   /* Q.c:397 */
+        if (line[0] == '>') continue;               /* Q.c:398 */
+        size_t len = nl ? n - 1 : n;
+        if (!nl) st->undefined_lines++;  /* T8/T9: reference scans past the buffer here */
+        st->total_kmers += qko_count_line(d, d->k, line, len, depth, NULL, 0, &st->hits);
+        st->lines++;
+        st->bases += len;
+        if (st->fastq) {                            /* Q.c:451-455 */
+            qko_getline(f, line, &nl);
+            qko_getline(f, line, &nl);
+            qko_getline(f, line, &nl);
+        }
+    }
+    return 0;
+}
+
+/* ---- a-8: Q.c:490-518.  Depth by hash slot -> depth in chain (reference) order ---- */
+uint64_t qko_chain_gather(const qko_dict *d, const uint16_t *depth, uint16_t *out, uint64_t cap)
+{
+    uint64_t n = 0;
+    uint32_t c = (uint32_t)d->first;            /* Q.c:494: first_idx truncated to u32 */
+    do {
+        if (n < cap) out[n] = depth[c];
+        ++n;
+        c = d->next[c];
+    } while (c != (uint32_t)d->first);
+    return n;
+}
+
+/* ---- a-9: Q.c:495-509, 522-542.  GC control curve from ordered depths + .qgc ------ */
+typedef struct {
+    double curve[QKO_GC_BINS];   /* sum of depth, later mean  */
+    double sq[QKO_GC_BINS];      /* sum of depth^2, later var */
+    uint32_t count[QKO_GC_BINS];
+    double mean_depth;           /* Q.c:539-540 */
+} qko_gc;
+
+void qko_gc_accumulate(const uint16_t *ordered, const uint16_t *qgc, uint64_t n, qko_gc *g)
+{
+    memset(g, 0, sizeof *g);
+    for (uint64_t i = 0; i < n; ++i) {
+        if (qgc[i] & 0x8000u) {                               /* Q.c:504 */
+            unsigned bin = qgc[i] & 0x1FFu;
+            if (bin >= QKO_GC_BINS) continue; /* reference would write out of bounds */
+            int dd = (int)((uint32_t)ordered[i] * (uint32_t)ordered[i]); /* Q.c:507 int product */
+            g->curve[bin] += ordered[i];                      /* Q.c:505 */
+            g->count[bin] += 1;                               /* Q.c:506 */
+            g->sq[bin] += dd;
+        }
+    }
+}
+
+/* Finalise and print the 401 lines of <out>.txt exactly as Q.c:529-538 formats them. */
+int qko_gc_write(qko_gc *g, const char *txt_path)
+{
+    FILE *f = fopen(txt_path, "w");
+    if (!f) return 1;
+    double total_depth = 0;
+    uint64_t total_count = 0;
+    for (int i = 0; i < QKO_GC_BINS; ++i) {
+        total_count += g->count[i];
+        total_depth += g->curve[i];
+        if (g->count[i]) {
+            g->curve[i] /= g->count[i];
+            volatile double m2 = g->curve[i] * g->curve[i]; /* no FMA contraction */
+            g->sq[i] = g->sq[i] / g->count[i] - m2;
+        }
+        fprintf(f, "%.2f\t%f\t%i\t%f\n", i / 4.0, g->curve[i], g->count[i], g->sq[i]);
+    }
+    g->mean_depth = total_depth / total_count;
+    fclose(f);
+    return 0;
+}
+
+/* ---- whole command: Q.c:304-545 ---------------------------------------------------- */
+int qko_count(const char *ref_prefix, const char *reads_path, const char *out_prefix, qko_stats *st)
+{
+    char path[4096];
+    qko_dict d;
+    snprintf(path, sizeof path, "%s.qm", ref_prefix);
+    int rc = qko_dict_load(path, &d);
+    if (rc) return 10 + rc;
+    FILE *reads = fopen(reads_path, "rb");
+    if (!reads) { qko_dict_free(&d); return 2; }
+    uint16_t *depth = calloc(d.n_slots, sizeof(uint16_t));
+    if (!depth) return 3;
+    qko_count_stream(&d, reads, depth, st);
+    fclose(reads);
+
+    uint64_t n = qko_chain_length(&d);
+    uint16_t *ordered = malloc(n * sizeof(uint16_t));
+    if (!ordered) return 3;
+    qko_chain_gather(&d, depth, ordered, n);
+    snprintf(path, sizeof path, "%s.bin", out_prefix);
+    FILE *bin = fopen(path, "wb");
+    if (!bin) return 4;
+    fwrite(ordered, 2, n, bin);
+    fclose(bin);
+
+    snprintf(path, sizeof path, "%s.qgc", ref_prefix);
+    FILE *qgc = fopen(path, "rb");
+    if (qgc) {                                              /* Q.c:486-488, 522 */
+        uint16_t *g = calloc(n, sizeof(uint16_t));
+        size_t got = fread(g, 2, n, qgc);
+        (void)got; /* short .qgc: the reference keeps stale buffer contents; we use zeros */
+        fclose(qgc);
+        qko_gc gc;
+        qko_gc_accumulate(ordered, g, n, &gc);
+        snprintf(path, sizeof path, "%s.txt", out_prefix);
+        qko_gc_write(&gc, path);
+        free(g);
+    }
+    free(ordered);
+    free(depth);
+    qko_dict_free(&d);
+    return 0;
+}
+
+#ifdef QKO_MAIN
+int main(int argc, char **argv)
+{
+    if (argc < 5 || strcmp(argv[1], "count")) {
+        fprintf(stderr, "usage: qk_oracle count ref_prefix reads out_prefix\n");
+        return 1;
+    }
+    qko_stats st;
+    int rc = qko_count(argv[argc - 3], argv[argc - 2], argv[argc - 1], &st);
+    if (rc) { fprintf(stderr, "qk_oracle: error %d\n", rc); return 1; }
+    printf("{\"total_kmers\": %llu, \"hits\": %llu, \"lines\": %llu, \"bases\": %llu, "
+           "\"undefined_lines\": %llu, \"fastq\": %d}\n",
+           (unsigned long long)st.total_kmers, (unsigned long long)st.hits,
+           (unsigned long long)st.lines, (unsigned long long)st.bases,
+           (unsigned long long)st.undefined_lines, st.fastq);
+    return 0;
+}
+#endif
