@@ -1,0 +1,92 @@
+/*
+ * qk_host.h -- host side of the `count` path, in C like the reference: the QM11 reader,
+ * the FASTA/FASTQ record framer, the .bin/.txt writers and the `count` command itself.
+ * Everything here runs on the CPU and feeds / drains the device through
+ * quickmer2_b200.h; none of it computes k-mers, hashes or counts.
+ */
+#ifndef QK_HOST_H
+#define QK_HOST_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "quickmer2_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QK_ERR_IO 6 /* file cannot be opened / short read */
+
+/* ---- QM11 dictionary file: written at Q.c:1284-1299, read at Q.c:345-359 and 483 ---- */
+typedef struct qk_qm_header {
+    uint8_t k;          /* byte 4 */
+    uint64_t hash_size; /* bytes 8..15, power of two */
+    uint64_t first_idx; /* bytes 16..23 */
+} qk_qm_header;
+
+int qk_qm_read_header(const char *qm_path, qk_qm_header *hdr);
+/* Stream <qm_path> to the device in pinned pieces and build the table.  Unlike the
+ * reference (NULL dereference at Q.c:345) a missing file is an error, not a crash. */
+int qk_qm_load(qk_ctx *ctx, const char *qm_path, qk_qm_header *hdr_out, uint64_t *n_kmers_out);
+
+/* ---- record framer: Q.c:393-398 and 451-455 -------------------------------------------
+ * Splits a FASTA / 4-line FASTQ byte stream into sequence lines exactly as the
+ * reference's fgets loop does:
+ *   - the first line decides the format: '@' => FASTQ (that line is consumed); otherwise
+ *     FASTA and the stream is rewound -- which silently fails on a pipe, so on a
+ *     non-seekable input the first line is lost (Q.c:396);
+ *   - a line starting with '>' is skipped, in either format (Q.c:398);
+ *   - every other line is one read, '\n' included; multi-line FASTA records are
+ *     independent reads;
+ *   - in FASTQ mode the three lines after a read are skipped (Q.c:451-455).
+ * Outside the reference's defined behaviour, handled deterministically and counted in the
+ * stats: a last line without '\n' gets one appended (T9), a line longer than 99,999
+ * bytes is passed through whole (T8).
+ */
+typedef struct qk_framer qk_framer;
+typedef struct qk_framer_stats {
+    uint64_t lines;         /* sequence lines emitted            */
+    uint64_t bases;         /* their bytes, excluding the '\n'   */
+    uint64_t raw_bytes;     /* bytes consumed from the input     */
+    uint64_t long_lines;    /* > QK_MAX_LINE_BYTES (T8)          */
+    uint64_t unterminated;  /* final line without '\n' (T9)      */
+    int fastq;
+} qk_framer_stats;
+
+qk_framer *qk_framer_open(const char *path);        /* NULL if the file cannot be opened */
+qk_framer *qk_framer_open_fd(int fd, int seekable); /* takes ownership of fd             */
+/* In-memory input (tests, benchmarks): frames `n` bytes at `data`; seekable says which
+ * first-line rule applies. The memory must outlive the framer. */
+qk_framer *qk_framer_open_mem(const uint8_t *data, size_t n, int seekable);
+/* Fill `dst` (capacity `cap` >= 100000) with whole sequence lines.  If line_off != NULL
+ * it receives the start offset of every line plus the end offset (at most off_cap
+ * entries; filling stops before it would overflow).  Returns 1 if *n_bytes > 0 was
+ * produced, 0 at end of input, negative QK_ERR_* on error. */
+int qk_framer_next(qk_framer *f, uint8_t *dst, size_t cap, size_t *n_bytes, uint32_t *line_off, uint32_t off_cap,
+                   uint32_t *n_lines);
+void qk_framer_get_stats(const qk_framer *f, qk_framer_stats *st);
+void qk_framer_close(qk_framer *f);
+
+/* ---- writers: Q.c:498-518 (.bin) and Q.c:522-542 (.txt) -------------------------------- */
+int qk_write_bin(const char *path, const uint16_t *counts, uint64_t n);
+/* 401 lines "%.2f\t%f\t%i\t%f\n" of bin/4, mean, count, variance; *mean_depth receives the
+ * figure printed as "Mean sequencing depth" (Q.c:539-540). */
+int qk_write_gc_txt(const char *path, const uint64_t sum[QK_GC_BINS], const int64_t sumsq[QK_GC_BINS],
+                    const uint64_t count[QK_GC_BINS], double *mean_depth);
+
+/* ---- streaming driver: file -> framer -> pinned slots -> device -------------------------
+ * Counts every read of `reads_path` into the context's counters (does not reset them).
+ * Returns the framer statistics. */
+int qk_count_file(qk_ctx *ctx, const char *reads_path, qk_framer_stats *st);
+int qk_count_framer(qk_ctx *ctx, qk_framer *f, qk_framer_stats *st);
+
+/* ---- the command: main_count, Q.c:304-545 -----------------------------------------------
+ * quicKmer2 count [-h] [-t N] [-g device] ref_prefix reads out_prefix
+ * Same positional-from-the-end convention, same stdout lines, same files. */
+int qk_count_main(int argc, char **argv);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QK_HOST_H */

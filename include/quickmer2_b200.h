@@ -1,0 +1,161 @@
+/*
+ * quickmer2_b200.h -- C ABI of the B200 device side of `quicKmer2 count`.
+ *
+ * The reference (QuicKmer.c, "Q.c") is a monolith with no FFI; the seams it does have are
+ * listed in SURVEY.md 8(b).  This header is the boundary a maintainer of the reference
+ * would bind to: each entry point names the reference lines it replaces.  Plain C types
+ * only.  All functions return 0 on success or a QK_ERR_* code; qk_last_error() returns a
+ * human-readable message for the most recent failure on that context.
+ *
+ * There is NO CPU fallback behind any of these calls: without a CUDA device
+ * qk_ctx_create() fails with QK_ERR_CUDA.
+ *
+ * Threading: one caller thread per context (the reference has exactly one producer,
+ * Q.c:397-456).  One context drives one GPU.
+ */
+#ifndef QUICKMER2_B200_H
+#define QUICKMER2_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QK_OK 0
+#define QK_ERR_CUDA 1   /* CUDA runtime failure (incl. no device)                  */
+#define QK_ERR_ARG 2    /* bad argument                                            */
+#define QK_ERR_NOMEM 3  /* host or device allocation failed (Q.c:354-366 return 1) */
+#define QK_ERR_STATE 4  /* call out of order                                       */
+#define QK_ERR_FORMAT 5 /* dictionary is not a valid QM11 chain                    */
+
+#define QK_GC_BINS 401          /* Q.c:495-497 */
+#define QK_MAX_LINE_BYTES 99999 /* Q.c:388,397: fgets(line, 100000) incl. the '\n' */
+
+typedef struct qk_ctx qk_ctx;
+
+/* Version / build string of the library (static storage). */
+const char *qk_version(void);
+
+/* Number of CUDA devices visible, or a negative QK_ERR_* code. */
+int qk_device_count(void);
+
+/*
+ * Create a context on CUDA device `device` with `n_slots` (1..8) chunk slots of
+ * `chunk_capacity` bytes each.  Every slot owns a pinned host buffer, a device buffer, a
+ * stream and two events -- the replacement for the reference's per-worker double FIFO
+ * (struct FIFO_arg_struc, Q.c:34-41; thread pool set-up Q.c:368-384).
+ * chunk_capacity must be >= 2 * 100000 and < 2^31.
+ */
+int qk_ctx_create(qk_ctx **out, int device, uint32_t n_slots, size_t chunk_capacity);
+void qk_ctx_destroy(qk_ctx *ctx);
+const char *qk_last_error(const qk_ctx *ctx);
+/* Slot count and (tile-rounded) slot capacity of a context. */
+int qk_ctx_info(const qk_ctx *ctx, uint32_t *n_slots, size_t *chunk_capacity);
+
+/* ------------------------------------------------------------------ dictionary ------
+ * Replaces the .qm load (Q.c:345-359 keys, Q.c:483 chain) and, at build time, the
+ * reference's serial chain walk (Q.c:490-516): the chain is list-ranked on the device so
+ * that every dictionary k-mer gets its ordinal (its index in the .bin file), and a new
+ * bucketised table key -> ordinal is built.  Observable semantics kept: membership in the
+ * set of non-zero keys, and for duplicate keys (written by `index`, Q.c:209-216) only the
+ * slot Find_hash (Q.c:90-99) reaches first ever receives counts.
+ */
+int qk_dict_begin(qk_ctx *ctx, uint8_t k, uint64_t hash_size, uint64_t first_idx);
+/* Copy `count` keys / chain entries starting at hash slot `slot_offset`.  `keys`/`next`
+ * are host pointers (pinned or pageable); the call returns when they may be reused. */
+int qk_dict_upload_keys(qk_ctx *ctx, uint64_t slot_offset, const uint64_t *keys, uint64_t count);
+int qk_dict_upload_chain(qk_ctx *ctx, uint64_t slot_offset, const uint32_t *next, uint64_t count);
+/* Rank the chain, build the table, release the raw arrays, zero the counters. */
+int qk_dict_build(qk_ctx *ctx, uint64_t *n_kmers_out);
+
+/* Geometry of a built table -- what a peer GPU needs to hold a replica. */
+typedef struct qk_table_desc {
+    uint64_t n_kmers;        /* chain length = number of .bin entries            */
+    uint64_t n_buckets;      /* power of two                                     */
+    uint64_t stash_slots;    /* power of two                                     */
+    uint64_t stash_used;
+    uint64_t table_bytes;    /* n_buckets * 32                                   */
+    uint64_t stash_bytes;    /* stash_slots * 16                                 */
+    uint32_t k;
+    uint32_t bucket_bits;    /* log2(n_buckets)                                  */
+    uint32_t ord_bits;       /* bits of the (ordinal + 1) field of an entry      */
+    uint32_t rem_bits;       /* 60 - bucket_bits                                 */
+    uint64_t skipped_keys;   /* dictionary keys no read can produce (>= 2^60) or
+                                shadowed duplicates; their ordinals stay 0       */
+} qk_table_desc;
+
+int qk_dict_describe(const qk_ctx *ctx, qk_table_desc *desc);
+/* Allocate an (uninitialised) replica with the geometry of `desc` on this context; the
+ * host then fills it, e.g. with an NCCL broadcast into the pointers below. */
+int qk_dict_adopt(qk_ctx *ctx, const qk_table_desc *desc);
+/* Device pointers of the table image (for NCCL broadcast / peer copies). */
+int qk_dict_device_ptrs(const qk_ctx *ctx, void **table, void **stash);
+
+/* ------------------------------------------------------------------ counting --------
+ * A chunk is a run of SEQUENCE LINES ONLY, each terminated by '\n', each at most
+ * QK_MAX_LINE_BYTES bytes including the '\n' (the framing of Q.c:393-398,451-455 is the
+ * host's job, see qk_host.h).  The device applies the codec of Q.c:399-420 to every line
+ * -- 'N' resets, (c>>1)&3 encoding of every other byte, 64-bit forward and 60-bit
+ * reverse-complement registers, 16-bit run counter with wrap -- looks every emitted key
+ * up and adds 1 to the counter of its ordinal (Q.c:256-296, 440-444).
+ */
+/* Pinned host buffer of slot `slot` (chunk_capacity bytes). */
+uint8_t *qk_slot_host_buffer(qk_ctx *ctx, uint32_t slot);
+/* Enqueue a chunk: async H2D of `n_bytes` from `bytes` (any host pointer; the slot's own
+ * pinned buffer gives a true async copy) followed by the count kernel, on the slot's
+ * stream.  `line_off` (n_lines + 1 offsets, may be NULL) is not needed by the device and
+ * only cross-checked in debug builds; n_lines feeds the statistics.  Returns at once. */
+int qk_submit(qk_ctx *ctx, uint32_t slot, const uint8_t *bytes, size_t n_bytes,
+              const uint32_t *line_off, uint32_t n_lines);
+/* Same, for a chunk already resident in device memory (16-byte aligned). */
+int qk_submit_device(qk_ctx *ctx, uint32_t slot, const uint8_t *dev_bytes, size_t n_bytes);
+/* Block until the host buffer last submitted on `slot` may be overwritten. */
+int qk_wait_slot(qk_ctx *ctx, uint32_t slot);
+/* Block until every enqueued chunk has been counted. */
+int qk_sync(qk_ctx *ctx);
+
+/* Running totals (call after qk_sync): emitted k-mers = the reference's process_kmers
+ * ("total %lu kmers", Q.c:445,481), dictionary hits, and sequence lines seen. */
+int qk_stats(qk_ctx *ctx, uint64_t *total_kmers, uint64_t *hits, uint64_t *lines);
+
+/* Device pointer of the per-ordinal uint32 counters (n_kmers entries), for an NCCL
+ * reduce across GPUs; the low 16 bits are the reference's uint16 depth (Q.c:23,291). */
+int qk_counters_device_ptr(const qk_ctx *ctx, uint32_t **counters, uint64_t *n_kmers);
+int qk_reset_counters(qk_ctx *ctx);
+/* Copy `count` raw uint32 counters starting at ordinal `offset` to host memory (syncs). */
+int qk_counters_download(qk_ctx *ctx, uint64_t offset, uint32_t *out, uint64_t count);
+
+/* ------------------------------------------------------------------ results ---------
+ * Replaces the dump loop Q.c:498-518: counts_out[i] = depth of the i-th k-mer of the
+ * chain, already in .bin order, wrapped to 16 bits exactly as uint16_t Kmer_depth does.
+ */
+int qk_finish(qk_ctx *ctx, uint16_t *counts_out, uint64_t n_kmers);
+/* GC control curve sums of Q.c:501-508 from the final depths and the .qgc flags
+ * (host array of n_kmers uint16): sum[b] = sum of depth, sumsq[b] = sum of the int
+ * product depth*depth, count[b] = entries, for control k-mers of GC bin b. */
+int qk_gc_curve(qk_ctx *ctx, const uint16_t *qgc, uint64_t n_kmers, uint64_t sum[QK_GC_BINS],
+                int64_t sumsq[QK_GC_BINS], uint64_t count[QK_GC_BINS]);
+
+/* ------------------------------------------------------------------ measurement -----
+ * Device time (ms) spent in count kernels / H2D copies on all slots since the last
+ * qk_reset_counters, from CUDA events recorded on the slots' streams, and the number of
+ * count-kernel launches. */
+int qk_timing(qk_ctx *ctx, double *kernel_ms, double *h2d_ms, uint64_t *launches);
+/* Device-clock span over ALL slot streams: qk_span_begin records a start event ordered after
+ * everything enqueued so far; qk_span_end records an end event ordered after everything
+ * enqueued on every slot stream since, waits for it and returns the elapsed device time. */
+int qk_span_begin(qk_ctx *ctx);
+int qk_span_end(qk_ctx *ctx, double *elapsed_ms);
+/* Micro-benchmarks for the roofline denominators: random `gran`-byte
+ * (32 or 64) gathers over a `table_bytes` region with `loads_in_flight` independent loads
+ * per thread; and pinned host -> device copy.  Both return GB/s. */
+int qk_bench_gather(qk_ctx *ctx, uint64_t table_bytes, uint32_t gran, uint32_t loads_in_flight,
+                    uint64_t n_gathers, double *gbs);
+int qk_bench_h2d(qk_ctx *ctx, size_t bytes, int repeats, double *gbs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUICKMER2_B200_H */

@@ -206,6 +206,56 @@ int qko_count_stream(const qko_dict *d, FILE *f, uint16_t *depth, qko_stats *st)
     return 0;
 }
 
+/* The sequence lines the loop of Q.c:397-456 would process, concatenated, each followed by
+ * '\n' -- the framing alone, for checking the host framer.  Returns bytes needed. */
+size_t qko_frame_stream(FILE *f, uint8_t *out, size_t cap, qko_stats *st)
+{
+    static uint8_t line[QKO_LINE_CAP];
+    int nl;
+    size_t total = 0;
+    memset(st, 0, sizeof *st);
+    size_t n = qko_getline(f, line, &nl);
+    if (n && line[0] == '@') st->fastq = 1;
+    else if (fseeko(f, 0, SEEK_SET) != 0) { /* pipe: first line lost (Q.c:396) */ }
+    while ((n = qko_getline(f, line, &nl)) > 0) {
+        if (line[0] == '>') continue;
+        size_t len = nl ? n - 1 : n;
+        if (!nl) st->undefined_lines++;
+        if (total + len + 1 <= cap) {
+            memcpy(out + total, line, len);
+            out[total + len] = '\n';
+        }
+        total += len + 1;
+        st->lines++;
+        st->bases += len;
+        if (st->fastq) {
+            qko_getline(f, line, &nl);
+            qko_getline(f, line, &nl);
+            qko_getline(f, line, &nl);
+        }
+    }
+    return total;
+}
+
+size_t qko_frame_file(const char *path, uint8_t *out, size_t cap, qko_stats *st)
+{
+    FILE *f = fopen(path, "rb");
+    if (!f) return (size_t)-1;
+    size_t n = qko_frame_stream(f, out, cap, st);
+    fclose(f);
+    return n;
+}
+
+/* Count a file against a loaded dictionary; depth is indexed by hash slot (Q.c:443). */
+int qko_count_file(const qko_dict *d, const char *path, uint16_t *depth, qko_stats *st)
+{
+    FILE *f = fopen(path, "rb");
+    if (!f) return 1;
+    qko_count_stream(d, f, depth, st);
+    fclose(f);
+    return 0;
+}
+
 /* ---- a-8: Q.c:490-518.  Depth by hash slot -> depth in chain (reference) order ---- */
 uint64_t qko_chain_gather(const qko_dict *d, const uint16_t *depth, uint16_t *out, uint64_t cap)
 {

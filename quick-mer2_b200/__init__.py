@@ -1,0 +1,415 @@
+"""quickmer2_b200 -- Python face of the B200 `quicKmer2 count` path.
+
+The product is the C-ABI shared library ``libquickmer2_b200.so`` (CUDA kernels for sm_100a
+plus the host C code) declared in ``include/quickmer2_b200.h`` and ``include/qk_host.h``;
+this module is a thin ctypes binding used by the tests, ``bench.py`` and
+``__graft_entry__.py``.  It mirrors the reference's only public interface, the command
+``quicKmer2 count [-t N] ref.fa sample.fast[a/q] Out_prefix`` (QuicKmer.c:298-302,
+main_count QuicKmer.c:304-545), as :func:`count`.
+
+There is no CPU fallback: if the library is missing, or no CUDA device is present,
+everything here raises.
+
+The directory name ``quick-mer2_b200`` is not an importable identifier; load the package
+with ``tests/conftest.py::load_package`` / ``bench.py`` (importlib, module name
+``quickmer2_b200``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+PKG_DIR = Path(__file__).resolve().parent
+REPO_ROOT = PKG_DIR.parent
+LIB_PATH = PKG_DIR / "libquickmer2_b200.so"
+CLI_PATH = PKG_DIR / "bin" / "quicKmer2_b200"
+SYNTH_PATH = PKG_DIR / "bin" / "qk_synth"
+
+GC_BINS = 401
+MAX_LINE_BYTES = 99999
+
+ERRORS = {1: "QK_ERR_CUDA", 2: "QK_ERR_ARG", 3: "QK_ERR_NOMEM", 4: "QK_ERR_STATE", 5: "QK_ERR_FORMAT", 6: "QK_ERR_IO"}
+
+
+class QkError(RuntimeError):
+    def __init__(self, code: int, message: str = ""):
+        self.code = code
+        super().__init__(f"{ERRORS.get(code, code)}: {message}" if message else str(ERRORS.get(code, code)))
+
+
+class TableDesc(C.Structure):
+    """struct qk_table_desc (include/quickmer2_b200.h)."""
+
+    _fields_ = [
+        ("n_kmers", C.c_uint64),
+        ("n_buckets", C.c_uint64),
+        ("stash_slots", C.c_uint64),
+        ("stash_used", C.c_uint64),
+        ("table_bytes", C.c_uint64),
+        ("stash_bytes", C.c_uint64),
+        ("k", C.c_uint32),
+        ("bucket_bits", C.c_uint32),
+        ("ord_bits", C.c_uint32),
+        ("rem_bits", C.c_uint32),
+        ("skipped_keys", C.c_uint64),
+    ]
+
+    def as_dict(self):
+        return {name: int(getattr(self, name)) for name, _ in self._fields_}
+
+
+class QmHeader(C.Structure):
+    _fields_ = [("k", C.c_uint8), ("hash_size", C.c_uint64), ("first_idx", C.c_uint64)]
+
+
+class FramerStats(C.Structure):
+    _fields_ = [
+        ("lines", C.c_uint64),
+        ("bases", C.c_uint64),
+        ("raw_bytes", C.c_uint64),
+        ("long_lines", C.c_uint64),
+        ("unterminated", C.c_uint64),
+        ("fastq", C.c_int),
+    ]
+
+    def as_dict(self):
+        return {name: int(getattr(self, name)) for name, _ in self._fields_}
+
+
+# name -> (restype, argtypes); every symbol include/*.h declares
+_P = C.c_void_p
+_U64P = C.POINTER(C.c_uint64)
+SIGNATURES = {
+    # quickmer2_b200.h
+    "qk_version": (C.c_char_p, []),
+    "qk_device_count": (C.c_int, []),
+    "qk_ctx_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_uint32, C.c_size_t]),
+    "qk_ctx_destroy": (None, [_P]),
+    "qk_last_error": (C.c_char_p, [_P]),
+    "qk_ctx_info": (C.c_int, [_P, C.POINTER(C.c_uint32), C.POINTER(C.c_size_t)]),
+    "qk_dict_begin": (C.c_int, [_P, C.c_uint8, C.c_uint64, C.c_uint64]),
+    "qk_dict_upload_keys": (C.c_int, [_P, C.c_uint64, _P, C.c_uint64]),
+    "qk_dict_upload_chain": (C.c_int, [_P, C.c_uint64, _P, C.c_uint64]),
+    "qk_dict_build": (C.c_int, [_P, _U64P]),
+    "qk_dict_describe": (C.c_int, [_P, C.POINTER(TableDesc)]),
+    "qk_dict_adopt": (C.c_int, [_P, C.POINTER(TableDesc)]),
+    "qk_dict_device_ptrs": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),
+    "qk_slot_host_buffer": (_P, [_P, C.c_uint32]),
+    "qk_submit": (C.c_int, [_P, C.c_uint32, _P, C.c_size_t, _P, C.c_uint32]),
+    "qk_submit_device": (C.c_int, [_P, C.c_uint32, _P, C.c_size_t]),
+    "qk_wait_slot": (C.c_int, [_P, C.c_uint32]),
+    "qk_sync": (C.c_int, [_P]),
+    "qk_stats": (C.c_int, [_P, _U64P, _U64P, _U64P]),
+    "qk_counters_device_ptr": (C.c_int, [_P, C.POINTER(_P), _U64P]),
+    "qk_reset_counters": (C.c_int, [_P]),
+    "qk_counters_download": (C.c_int, [_P, C.c_uint64, _P, C.c_uint64]),
+    "qk_finish": (C.c_int, [_P, _P, C.c_uint64]),
+    "qk_gc_curve": (C.c_int, [_P, _P, C.c_uint64, _P, _P, _P]),
+    "qk_timing": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), _U64P]),
+    "qk_span_begin": (C.c_int, [_P]),
+    "qk_span_end": (C.c_int, [_P, C.POINTER(C.c_double)]),
+    "qk_bench_gather": (C.c_int, [_P, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(C.c_double)]),
+    "qk_bench_h2d": (C.c_int, [_P, C.c_size_t, C.c_int, C.POINTER(C.c_double)]),
+    # qk_host.h
+    "qk_qm_read_header": (C.c_int, [C.c_char_p, C.POINTER(QmHeader)]),
+    "qk_qm_load": (C.c_int, [_P, C.c_char_p, C.POINTER(QmHeader), _U64P]),
+    "qk_framer_open": (_P, [C.c_char_p]),
+    "qk_framer_open_fd": (_P, [C.c_int, C.c_int]),
+    "qk_framer_open_mem": (_P, [_P, C.c_size_t, C.c_int]),
+    "qk_framer_next": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(C.c_size_t), _P, C.c_uint32, C.POINTER(C.c_uint32)]),
+    "qk_framer_get_stats": (None, [_P, C.POINTER(FramerStats)]),
+    "qk_framer_close": (None, [_P]),
+    "qk_write_bin": (C.c_int, [C.c_char_p, _P, C.c_uint64]),
+    "qk_write_gc_txt": (C.c_int, [C.c_char_p, _P, _P, _P, C.POINTER(C.c_double)]),
+    "qk_count_file": (C.c_int, [_P, C.c_char_p, C.POINTER(FramerStats)]),
+    "qk_count_framer": (C.c_int, [_P, _P, C.POINTER(FramerStats)]),
+    "qk_count_main": (C.c_int, [C.c_int, C.POINTER(C.c_char_p)]),
+}
+
+_lib = None
+
+
+def build(verbose: bool = False) -> None:
+    """Compile the library and the host binaries in-tree (nvcc, sm_100a)."""
+    res = subprocess.run(["make", "-C", str(PKG_DIR), "all"], capture_output=True, text=True)
+    if verbose or res.returncode:
+        print(res.stdout[-4000:], res.stderr[-4000:])
+    if res.returncode:
+        raise RuntimeError("building libquickmer2_b200.so failed")
+
+
+def lib() -> C.CDLL:
+    """The C-ABI library.  Fails loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise FileNotFoundError(
+                f"{LIB_PATH} is missing: run `make -C {PKG_DIR}` (or __graft_entry__.build()). "
+                "There is no Python/CPU fallback for the count path."
+            )
+        handle = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def _np_ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One GPU: struct qk_ctx.  Mirrors the life cycle of main_count (Q.c:304-545)."""
+
+    def __init__(self, device: int = 0, n_slots: int = 4, chunk_capacity: int = 32 << 20):
+        self._h = C.c_void_p()
+        self._lib = lib()
+        rc = self._lib.qk_ctx_create(C.byref(self._h), device, n_slots, chunk_capacity)
+        if rc:
+            msg = self._lib.qk_last_error(self._h).decode() if self._h else "no CUDA device (no CPU fallback)"
+            if self._h:
+                self._lib.qk_ctx_destroy(self._h)
+                self._h = C.c_void_p()
+            raise QkError(rc, msg)
+        self.device = device
+        self.n_slots = n_slots
+        cap = C.c_size_t()
+        self._lib.qk_ctx_info(self._h, None, C.byref(cap))
+        self.chunk_capacity = cap.value
+        self.n_kmers = 0
+
+    # -- plumbing -------------------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc:
+            raise QkError(rc, self._lib.qk_last_error(self._h).decode())
+
+    def close(self):
+        if self._h:
+            self._lib.qk_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- dictionary -----------------------------------------------------------------------
+    def load_dictionary(self, qm_path) -> int:
+        """Stream a QM11 file to the device and build the table (Q.c:345-359, 483)."""
+        n = C.c_uint64()
+        hdr = QmHeader()
+        self._check(self._lib.qk_qm_load(self._h, os.fsencode(str(qm_path)), C.byref(hdr), C.byref(n)))
+        self.n_kmers = n.value
+        self.header = {"k": hdr.k, "hash_size": hdr.hash_size, "first_idx": hdr.first_idx}
+        return self.n_kmers
+
+    def load_dictionary_arrays(self, k: int, keys: np.ndarray, nxt: np.ndarray, first_idx: int) -> int:
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        nxt = np.ascontiguousarray(nxt, dtype=np.uint32)
+        assert keys.shape == nxt.shape
+        self._check(self._lib.qk_dict_begin(self._h, k, keys.size, first_idx))
+        self._check(self._lib.qk_dict_upload_keys(self._h, 0, _np_ptr(keys), keys.size))
+        self._check(self._lib.qk_dict_upload_chain(self._h, 0, _np_ptr(nxt), nxt.size))
+        n = C.c_uint64()
+        self._check(self._lib.qk_dict_build(self._h, C.byref(n)))
+        self.n_kmers = n.value
+        return self.n_kmers
+
+    def table_desc(self) -> TableDesc:
+        d = TableDesc()
+        self._check(self._lib.qk_dict_describe(self._h, C.byref(d)))
+        return d
+
+    def adopt(self, desc: TableDesc):
+        self._check(self._lib.qk_dict_adopt(self._h, C.byref(desc)))
+        self.n_kmers = int(desc.n_kmers)
+
+    def table_device_ptrs(self):
+        t, s = C.c_void_p(), C.c_void_p()
+        self._check(self._lib.qk_dict_device_ptrs(self._h, C.byref(t), C.byref(s)))
+        return t.value, s.value
+
+    def counters_device_ptr(self):
+        p, n = C.c_void_p(), C.c_uint64()
+        self._check(self._lib.qk_counters_device_ptr(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def counters(self) -> np.ndarray:
+        """Raw uint32 counters by ordinal (before the 16-bit wrap of :meth:`finish`)."""
+        out = np.empty(self.n_kmers, dtype=np.uint32)
+        self._check(self._lib.qk_counters_download(self._h, 0, _np_ptr(out), out.size))
+        return out
+
+    # -- counting -------------------------------------------------------------------------
+    def count_file(self, reads_path) -> dict:
+        """Frame a FASTA/FASTQ file on the host and count it (Q.c:393-479)."""
+        st = FramerStats()
+        rc = self._lib.qk_count_file(self._h, os.fsencode(str(reads_path)), C.byref(st))
+        if rc == 6:
+            raise QkError(rc, f"cannot read {reads_path}")
+        self._check(rc)
+        return st.as_dict()
+
+    def count_raw(self, data: bytes, seekable: bool = True) -> dict:
+        """Frame an in-memory FASTA/FASTQ byte string and count it."""
+        buf = np.frombuffer(data, dtype=np.uint8)
+        fr = self._lib.qk_framer_open_mem(_np_ptr(buf), buf.size, int(seekable))
+        st = FramerStats()
+        try:
+            self._check(self._lib.qk_count_framer(self._h, fr, C.byref(st)))
+        finally:
+            self._lib.qk_framer_close(fr)
+        return st.as_dict()
+
+    def submit_chunk(self, chunk: bytes, slot: int = 0, n_lines: int = 0):
+        """Count an already framed chunk (sequence lines only, each ending in a newline)."""
+        assert len(chunk) <= self.chunk_capacity
+        self._check(self._lib.qk_wait_slot(self._h, slot))
+        host = self._lib.qk_slot_host_buffer(self._h, slot)
+        C.memmove(host, chunk, len(chunk))
+        self._check(self._lib.qk_submit(self._h, slot, host, len(chunk), None, n_lines))
+
+    def submit_device(self, dev_ptr: int, n_bytes: int, slot: int = 0):
+        self._check(self._lib.qk_submit_device(self._h, slot, dev_ptr, n_bytes))
+
+    def sync(self):
+        self._check(self._lib.qk_sync(self._h))
+
+    def reset(self):
+        self._check(self._lib.qk_reset_counters(self._h))
+
+    def stats(self) -> dict:
+        t, h, l = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(self._lib.qk_stats(self._h, C.byref(t), C.byref(h), C.byref(l)))
+        return {"total_kmers": t.value, "hits": h.value, "lines": l.value}
+
+    def timing(self) -> dict:
+        k, h, n = C.c_double(), C.c_double(), C.c_uint64()
+        self._check(self._lib.qk_timing(self._h, C.byref(k), C.byref(h), C.byref(n)))
+        return {"kernel_ms": k.value, "h2d_ms": h.value, "launches": n.value}
+
+    # -- results --------------------------------------------------------------------------
+    def finish(self) -> np.ndarray:
+        """Depths in .bin order, uint16 with the reference's wrap (Q.c:498-518)."""
+        out = np.empty(self.n_kmers, dtype=np.uint16)
+        self._check(self._lib.qk_finish(self._h, _np_ptr(out), self.n_kmers))
+        return out
+
+    def gc_curve(self, qgc: np.ndarray):
+        qgc = np.ascontiguousarray(qgc, dtype=np.uint16)
+        assert qgc.size == self.n_kmers
+        s = np.zeros(GC_BINS, dtype=np.uint64)
+        q = np.zeros(GC_BINS, dtype=np.int64)
+        c = np.zeros(GC_BINS, dtype=np.uint64)
+        self._check(self._lib.qk_gc_curve(self._h, _np_ptr(qgc), qgc.size, _np_ptr(s), _np_ptr(q), _np_ptr(c)))
+        return s, q, c
+
+    def span_begin(self):
+        self._check(self._lib.qk_span_begin(self._h))
+
+    def span_end(self) -> float:
+        ms = C.c_double()
+        self._check(self._lib.qk_span_end(self._h, C.byref(ms)))
+        return ms.value
+
+    def submit_host(self, host_ptr: int, n_bytes: int, slot: int = 0, n_lines: int = 0):
+        """Count a framed chunk straight from (ideally pinned) host memory: async H2D + kernel."""
+        self._check(self._lib.qk_submit(self._h, slot, host_ptr, n_bytes, None, n_lines))
+
+    def count_mem(self, host_ptr: int, n_bytes: int, seekable: bool = True) -> dict:
+        """Frame + count raw FASTA/FASTQ bytes at a host address (the whole reads stream)."""
+        fr = self._lib.qk_framer_open_mem(host_ptr, n_bytes, int(seekable))
+        st = FramerStats()
+        try:
+            self._check(self._lib.qk_count_framer(self._h, fr, C.byref(st)))
+        finally:
+            self._lib.qk_framer_close(fr)
+        return st.as_dict()
+
+    # -- measurement ----------------------------------------------------------------------
+    def bench_gather(self, table_bytes: int, gran: int = 32, loads_in_flight: int = 4, n_gathers: int = 1 << 30) -> float:
+        g = C.c_double()
+        self._check(self._lib.qk_bench_gather(self._h, table_bytes, gran, loads_in_flight, n_gathers, C.byref(g)))
+        return g.value
+
+    def bench_h2d(self, n_bytes: int, repeats: int = 8) -> float:
+        g = C.c_double()
+        self._check(self._lib.qk_bench_h2d(self._h, n_bytes, repeats, C.byref(g)))
+        return g.value
+
+
+def write_gc_txt(path, s: np.ndarray, q: np.ndarray, c: np.ndarray) -> float:
+    mean = C.c_double()
+    rc = lib().qk_write_gc_txt(os.fsencode(str(path)), _np_ptr(s), _np_ptr(q), _np_ptr(c), C.byref(mean))
+    if rc:
+        raise QkError(rc, f"cannot write {path}")
+    return mean.value
+
+
+def frame(data: bytes, seekable: bool = True, chunk_capacity: int = 1 << 20, with_offsets: bool = False):
+    """Host framer only (no GPU): FASTA/FASTQ bytes -> list of framed chunks, stats."""
+    L = lib()
+    buf = np.frombuffer(data, dtype=np.uint8) if len(data) else np.zeros(0, dtype=np.uint8)
+    fr = L.qk_framer_open_mem(_np_ptr(buf), buf.size, int(seekable))
+    chunks, offsets = [], []
+    dst = np.empty(chunk_capacity, dtype=np.uint8)
+    off = np.empty(chunk_capacity // 2 + 2, dtype=np.uint32)
+    n, nl = C.c_size_t(), C.c_uint32()
+    try:
+        while True:
+            r = L.qk_framer_next(fr, _np_ptr(dst), dst.size, C.byref(n), _np_ptr(off) if with_offsets else None,
+                                 off.size, C.byref(nl))
+            if r < 0:
+                raise QkError(-r, "framer")
+            if r == 0:
+                break
+            chunks.append(dst[: n.value].tobytes())
+            if with_offsets:
+                offsets.append(off[: nl.value + 1].copy())
+        st = FramerStats()
+        L.qk_framer_get_stats(fr, C.byref(st))
+    finally:
+        L.qk_framer_close(fr)
+    return (chunks, offsets, st.as_dict()) if with_offsets else (chunks, st.as_dict())
+
+
+def count(ref_prefix, reads_path, out_prefix, threads: int = 0, device: int = 0) -> dict:
+    """``quicKmer2 count [-t N] ref.fa reads Out_prefix`` on the GPU, in-process.
+
+    Same files as the reference: reads ``<ref_prefix>.qm`` (and ``.qgc`` if present), writes
+    ``<out_prefix>.bin`` (and ``.txt``).  Returns the counting statistics.
+    """
+    with Context(device=device) as ctx:
+        n = ctx.load_dictionary(f"{ref_prefix}.qm")
+        st = ctx.count_file(reads_path)
+        st.update(ctx.stats())
+        counts = ctx.finish()
+        counts.tofile(f"{out_prefix}.bin")
+        qgc_path = Path(f"{ref_prefix}.qgc")
+        if qgc_path.exists():
+            qgc = np.zeros(n, dtype=np.uint16)
+            raw = np.fromfile(qgc_path, dtype=np.uint16, count=n)
+            qgc[: raw.size] = raw
+            s, q, c = ctx.gc_curve(qgc)
+            st["mean_depth"] = write_gc_txt(f"{out_prefix}.txt", s, q, c)
+        st["n_kmers"] = n
+        st.update(ctx.timing())
+    return st
+
+
+def run_cli(args, **kw) -> subprocess.CompletedProcess:
+    """Run the C command ``quicKmer2_b200`` (the drop-in for ``quicKmer2``)."""
+    return subprocess.run([str(CLI_PATH), *map(str, args)], capture_output=True, text=True, **kw)

@@ -1,0 +1,123 @@
+// qk_common.cuh -- shared device/host definitions: context layout, key mixer, entry layout.
+//
+// Table layout in HBM (DESIGN.md "data layout"):
+//   bucket  = 4 x uint64 entries = one 32-byte sector, fetched with one LDG.E.256
+//   entry   = (remainder << ord_bits) | (ordinal + 1), 0 = empty
+//   key     -> h = mix60(key) (a bijection on [0, 2^60)); bucket = top bucket_bits of h,
+//              remainder = low rem_bits = 60 - bucket_bits of h (quotienting: the bucket
+//              index is implied, so remainder + ordinal fit one 64-bit word)
+//   stash   = open-addressed {key, ordinal+1} 16-byte entries for the keys whose home
+//              bucket was full at build time; consulted only when a bucket is full
+// Every key a read can produce is < 2^60 because the reference's reverse-complement
+// register is 60 bits wide for every k (Q.c:415-416,420), so 60-bit keys lose nothing.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/quickmer2_b200.h"
+
+#define QK_TILE 4096          // bytes (= positions) per tile
+#define QK_THREADS 256        // threads per CTA of the count kernel
+#define QK_MAX_SLOTS 8
+#define QK_TIMING_RING 64
+#define QK_KEY_BITS 60
+#define QK_BUCKET_ENTRIES 4
+
+struct __align__(32) qk_bucket { unsigned long long e[QK_BUCKET_ENTRIES]; };
+struct __align__(16) qk_stash_entry { unsigned long long key; uint32_t ord1; uint32_t pad; };
+
+// Everything the count kernel needs, passed by value.
+struct qk_table_view {
+    const qk_bucket *buckets;
+    const qk_stash_entry *stash;
+    uint64_t stash_mask;      // stash_slots - 1
+    uint64_t kmask;           // (1 << 2k) - 1, 0 for k = 32 (Q.c:419 on x86-64)
+    uint32_t k;
+    uint32_t rem_bits;        // 60 - bucket_bits
+    uint32_t ord_bits;
+    uint32_t has_stash;       // stash_used != 0
+};
+
+struct qk_timing_pair { cudaEvent_t a, b; int kind; /* 0 = h2d, 1 = kernel */ };
+
+struct qk_slot {
+    uint8_t *host;            // pinned
+    uint8_t *dev;
+    cudaStream_t stream;
+    cudaEvent_t h2d_done;
+    qk_timing_pair ring[QK_TIMING_RING];
+    uint32_t ring_head, ring_count;
+};
+
+struct qk_ctx {
+    int device;
+    int sm_count;
+    uint32_t n_slots;
+    size_t chunk_capacity;
+    qk_slot slots[QK_MAX_SLOTS];
+    char err[512];
+
+    // raw QM11 arrays, resident only between qk_dict_begin and qk_dict_build
+    uint64_t *raw_keys;
+    uint32_t *raw_next;
+    uint64_t hash_size, first_idx;
+    uint8_t k;
+    int dict_state;           // 0 none, 1 uploading, 2 built/adopted
+
+    qk_bucket *buckets;
+    qk_stash_entry *stash;
+    qk_table_desc desc;
+
+    uint32_t *counters;       // n_kmers x u32, indexed by ordinal
+    unsigned long long *stats; // device: [0] emitted k-mers, [1] hits
+    uint64_t lines;
+
+    double kernel_ms, h2d_ms;
+    uint64_t launches;
+    cudaEvent_t span_a, span_b, span_join;
+};
+
+int qk_fail(qk_ctx *ctx, int code, const char *fmt, ...);
+int qk_cuda_fail(qk_ctx *ctx, cudaError_t e, const char *what);
+#define QK_CUDA(ctx, call)                                            \
+    do {                                                              \
+        cudaError_t e__ = (call);                                     \
+        if (e__ != cudaSuccess) return qk_cuda_fail(ctx, e__, #call); \
+    } while (0)
+
+// ---- 60-bit bijective mixer ---------------------------------------------------------
+// xorshift and odd multiplication are both invertible mod 2^60, so distinct keys map to
+// distinct (bucket, remainder) pairs and the remainder identifies the key in its bucket.
+#define QK_M60 0x0FFFFFFFFFFFFFFFull
+__host__ __device__ __forceinline__ uint64_t qk_mix60(uint64_t x)
+{
+    x ^= x >> 31;
+    x = (x * 0x9E3779B97F4A7C15ull) & QK_M60;
+    x ^= x >> 29;
+    x = (x * 0xBF58476D1CE4E5B9ull) & QK_M60;
+    x ^= x >> 32;
+    return x;
+}
+// second, independent hash for the stash
+__host__ __device__ __forceinline__ uint64_t qk_mix_stash(uint64_t x)
+{
+    x ^= x >> 33;
+    x *= 0xFF51AFD7ED558CCDull;
+    x ^= x >> 29;
+    x *= 0xC4CEB9FE1A85EC53ull;
+    x ^= x >> 32;
+    return x;
+}
+
+// The reference's slot hash (Q.c:66-76), needed at build time only: which of several
+// duplicate keys Find_hash would reach first.
+__host__ __device__ __forceinline__ uint64_t qk_djb(uint64_t key)
+{
+    uint64_t h = 5381;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        h = h * 33u + (key & 0xFFu);
+        key >>= 8;
+    }
+    return h;
+}

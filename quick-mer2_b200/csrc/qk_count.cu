@@ -1,0 +1,480 @@
+// qk_count.cu -- the count kernel (codec + probe + depth increment, fused) and the result
+// kernels (16-bit narrowing, GC control curve).
+//
+// Replaces the reference's hot loops:
+//   loop A  Q.c:397-456  per-byte codec on the main thread
+//   loop B  Q.c:256-296  Find_hash + atomic depth increment in the worker threads
+//   loop C  Q.c:498-518  chain-order dump (here the counters are already in chain order)
+//
+// Position-parallel form of the codec.  A chunk is a run of
+// sequence lines, each ending in '\n'.  For byte position p let last(p) be the position of
+// the last reset byte ('N' or '\n') at or before p (-1 = chunk start) and r = p - last(p).
+// Position p emits iff r > 0 and (r mod 65536) >= k            (Q.c:402,410,418; T7)
+//   fwd = 2-bit codes of bytes p-31..p, newest in bits 1:0, masked to 2k bits  (Q.c:412,419)
+//   rc  = complemented codes of the last min(r,30) bytes, newest in bits 59:58 (Q.c:414-416)
+//   key = min(fwd, rc)                                                         (Q.c:420)
+// so one thread per position needs only a 31-byte left halo and r.
+//
+// Mapping: a CTA owns a contiguous span of 4 KiB tiles and walks it tile by tile, carrying
+// last() across tiles (long reads span many tiles); only the span's first tile needs a
+// backward search.  Per tile the 256 threads load 16 bytes each (coalesced 128-bit loads,
+// next tile prefetched into registers), pack them to 2 bits/base and a reset bitmask in
+// shared memory; then lane = position: 32 consecutive positions per warp, so the two code
+// words and the mask word a warp reads are shared-memory broadcasts and the depth
+// increments of a warp land on consecutive ordinals (one or two 128-byte lines per RED).
+// Four positions per thread are in flight at once: four independent 32-byte bucket loads
+// (LDG.E.256, no L1 allocation) are issued before any is consumed.
+#include <limits.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "qk_common.cuh"
+
+#define QK_WORDS (QK_TILE / 32)       // 32-base code words / 32-byte mask words per tile
+#define QK_POS_PER_THREAD (QK_TILE / QK_THREADS)
+#define QK_UNROLL 4
+#define QK_NONE INT_MIN
+
+int qk_ring_push(qk_ctx *ctx, qk_slot *sl, int kind, qk_timing_pair **out);
+
+struct qk_count_args {
+    const uint8_t *bytes;
+    uint32_t n_bytes;
+    uint32_t n_tiles;
+    uint32_t tiles_per_cta;
+    uint32_t *counters;
+    unsigned long long *stats;
+    qk_table_view tv;
+};
+
+// ---- byte -> 2-bit code / reset flag packing --------------------------------------------
+// four bytes -> 8 bits, first byte in the top pair: ((c>>1)&3 per byte, Q.c:411)
+__device__ __forceinline__ uint32_t qk_pack4(uint32_t w)
+{
+    return (((w >> 1) & 0x03030303u) * 0x40100401u) >> 24;
+}
+// four bytes -> 4 flags, bit j set iff byte j is 'N' (Q.c:404) or '\n' (Q.c:403)
+__device__ __forceinline__ uint32_t qk_reset4(uint32_t w)
+{
+    uint32_t m = __vcmpeq4(w, 0x4E4E4E4Eu) | __vcmpeq4(w, 0x0A0A0A0Au);
+    return ((m & 0x01010101u) * 0x01020408u) >> 24;
+}
+__device__ __forceinline__ uint32_t qk_codes16(const uint4 &v)
+{
+    return (qk_pack4(v.x) << 24) | (qk_pack4(v.y) << 16) | (qk_pack4(v.z) << 8) | qk_pack4(v.w);
+}
+__device__ __forceinline__ uint32_t qk_resets16(const uint4 &v)
+{
+    return qk_reset4(v.x) | (qk_reset4(v.y) << 4) | (qk_reset4(v.z) << 8) | (qk_reset4(v.w) << 12);
+}
+
+// 16 bytes at chunk offset pos (16-byte aligned); bytes at or beyond n read as '\n'.  The
+// 128-bit load may touch up to 15 bytes past n: chunk buffers are readable up to the next
+// 16-byte boundary (slot buffers are tile-padded; cudaMalloc granularity covers the rest).
+__device__ __forceinline__ uint4 qk_load16(const uint8_t *__restrict__ bytes, uint32_t pos, uint32_t n)
+{
+    uint4 v = make_uint4(0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au, 0x0A0A0A0Au);
+    if (pos < n) {
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                     : "l"(bytes + pos));
+        const uint32_t rem = n - pos;
+        if (rem < 16) { // chunk tail: force the bytes past n to '\n'
+            uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int keep = (int)rem - 4 * i;
+                const uint32_t m = keep >= 4 ? 0xFFFFFFFFu : keep <= 0 ? 0u : ((1u << (8 * keep)) - 1);
+                w[i] = (w[i] & m) | (0x0A0A0A0Au & ~m);
+            }
+            v = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+    return v;
+}
+
+__device__ __forceinline__ qk_bucket qk_ld_bucket(const qk_bucket *p)
+{
+    qk_bucket v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(v.e[0]), "=l"(v.e[1]), "=l"(v.e[2]), "=l"(v.e[3])
+                 : "l"(p));
+    return v;
+}
+
+// reverse the order of the 2-bit groups of a 64-bit word
+__device__ __forceinline__ uint64_t qk_rev_pairs(uint64_t x)
+{
+    uint64_t z = __brevll(x);
+    return ((z & 0x5555555555555555ull) << 1) | ((z >> 1) & 0x5555555555555555ull);
+}
+
+// stash probe: linear over 16-byte entries; returns ordinal + 1 or 0
+__device__ __noinline__ uint32_t qk_stash_find(const qk_table_view &tv, uint64_t key)
+{
+    uint64_t s = qk_mix_stash(key) & tv.stash_mask;
+    for (;;) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(tv.stash + s));
+        const uint64_t sk = ((uint64_t)v.y << 32) | v.x;
+        if (sk == key) return v.z;
+        if (sk == 0) return 0;
+        s = (s + 1) & tv.stash_mask;
+    }
+}
+
+__global__ void __launch_bounds__(QK_THREADS, 3) qk_count_kernel(const qk_count_args a)
+{
+    __shared__ uint64_t s_codes[2][QK_WORDS + 1]; // [0] = halo: the 32 bases before the tile
+    __shared__ uint32_t s_mask[2][QK_WORDS];      // reset flags, bit j of word w = byte 32w+j
+    __shared__ int s_last[2][QK_WORDS];           // last reset before word w (chunk position)
+    __shared__ int s_red[QK_THREADS / 32];
+    __shared__ int s_carry;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tile0 = blockIdx.x * a.tiles_per_cta;
+    if (tile0 >= a.n_tiles) return;
+    const uint32_t tile_end = min(tile0 + a.tiles_per_cta, a.n_tiles);
+    const uint8_t *__restrict__ bytes = a.bytes;
+    const uint32_t n = a.n_bytes;
+
+    // ---- span start: last reset before the span, and the 32-base halo -----------------------
+    {
+        int found = QK_NONE;
+        uint32_t pos = tile0 * QK_TILE;
+        while (pos > 0 && found == QK_NONE) {
+            pos -= QK_TILE;
+            const uint32_t at = pos + tid * 16;
+            const uint32_t m = qk_resets16(qk_load16(bytes, at, n));
+            int own = m ? (int)(at + 31 - __clz(m)) : QK_NONE;
+            for (int o = 16; o; o >>= 1) own = max(own, __shfl_xor_sync(0xffffffffu, own, o));
+            if (lane == 0) s_red[warp] = own;
+            __syncthreads();
+            found = s_red[0];
+#pragma unroll
+            for (int w = 1; w < QK_THREADS / 32; ++w) found = max(found, s_red[w]);
+            __syncthreads();
+        }
+        if (tid == 0) {
+            s_carry = (found == QK_NONE) ? -1 : found;
+            uint64_t halo = 0;
+            const uint32_t base = tile0 * QK_TILE;
+            if (base >= 32)
+                halo = ((uint64_t)qk_codes16(qk_load16(bytes, base - 32, n)) << 32) | qk_codes16(qk_load16(bytes, base - 16, n));
+            s_codes[(tile0 & 1) ^ 1][QK_WORDS] = halo; // where the "previous tile" leaves its last word
+        }
+    }
+
+    const qk_table_view tv = a.tv;
+    const uint32_t k = tv.k;
+    const uint64_t rem_mask = ((uint64_t)1 << tv.rem_bits) - 1;
+    const uint64_t ord_mask = ((uint64_t)1 << tv.ord_bits) - 1;
+    uint32_t n_emit = 0, n_hit = 0;
+
+    uint4 cur = qk_load16(bytes, tile0 * QK_TILE + tid * 16, n);
+    for (uint32_t tile = tile0; tile < tile_end; ++tile) {
+        const uint32_t buf = tile & 1;
+        const uint32_t base = tile * QK_TILE;
+        __syncthreads(); // previous tile's readers are done with buf; s_carry / halo visible
+        reinterpret_cast<uint32_t *>(s_codes[buf])[2 + (tid ^ 1)] = qk_codes16(cur);
+        reinterpret_cast<uint16_t *>(s_mask[buf])[tid] = (uint16_t)qk_resets16(cur);
+        if (tid == 0) s_codes[buf][0] = s_codes[buf ^ 1][QK_WORDS];
+        if (tile + 1 < tile_end) cur = qk_load16(bytes, base + QK_TILE + tid * 16, n); // prefetch
+        __syncthreads();
+        if (warp == 0) { // exclusive max-scan of the per-word last reset
+            int carry = s_carry;
+#pragma unroll
+            for (int i = 0; i < QK_WORDS / 32; ++i) {
+                const uint32_t w = i * 32 + lane;
+                const uint32_t m = s_mask[buf][w];
+                int incl = m ? (int)(base + w * 32 + 31 - __clz(m)) : QK_NONE;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    int up = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl = max(incl, up);
+                }
+                int excl = __shfl_up_sync(0xffffffffu, incl, 1);
+                if (lane == 0) excl = QK_NONE;
+                s_last[buf][w] = max(carry, excl);
+                carry = max(carry, __shfl_sync(0xffffffffu, incl, 31));
+            }
+            if (lane == 0) s_carry = carry;
+        }
+        __syncthreads();
+
+#pragma unroll 1
+        for (int it = 0; it < QK_POS_PER_THREAD / QK_UNROLL; ++it) {
+            uint64_t key[QK_UNROLL], q[QK_UNROLL];
+            const qk_bucket *bp[QK_UNROLL];
+            bool valid[QK_UNROLL];
+            qk_bucket bk[QK_UNROLL];
+#pragma unroll
+            for (int u = 0; u < QK_UNROLL; ++u) {
+                const uint32_t w = (it * QK_UNROLL + u) * (QK_THREADS / 32) + warp; // word holding p
+                const uint32_t p = base + w * 32 + lane;
+                const uint32_t m = s_mask[buf][w] & (0xFFFFFFFFu >> (31 - lane));
+                const int last = m ? (int)(base + w * 32 + 31 - __clz(m)) : s_last[buf][w];
+                const uint32_t r = (uint32_t)((int)p - last);
+                const uint64_t A = s_codes[buf][w], B = s_codes[buf][w + 1];
+                const uint32_t sh = 2 * (31 - lane);
+                const uint64_t x = (B >> sh) | ((A << 1) << (63 - sh)); // 32 bases ending at p
+                const uint64_t fwd = x & tv.kmask;
+                const uint32_t keep = min(r, 30u);
+                uint64_t rc = (qk_rev_pairs(x & QK_M60) >> 4) ^ 0x0AAAAAAAAAAAAAAAull;
+                rc &= QK_M60 & ~(((uint64_t)1 << (60 - 2 * keep)) - 1);
+                key[u] = min(fwd, rc);
+                valid[u] = p < n && r != 0 && (r & 0xFFFFu) >= k;
+                const uint64_t h = qk_mix60(key[u]);
+                bp[u] = tv.buckets + (h >> tv.rem_bits);
+                q[u] = (h & rem_mask) << tv.ord_bits;
+            }
+#pragma unroll
+            for (int u = 0; u < QK_UNROLL; ++u) {
+                bk[u].e[0] = bk[u].e[1] = bk[u].e[2] = bk[u].e[3] = 0;
+                if (valid[u]) bk[u] = qk_ld_bucket(bp[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < QK_UNROLL; ++u) {
+                if (!valid[u]) continue;
+                ++n_emit;
+                uint64_t ord1 = 0;
+                bool full = true;
+#pragma unroll
+                for (int e = 0; e < QK_BUCKET_ENTRIES; ++e) {
+                    const uint64_t d = bk[u].e[e] ^ q[u];
+                    if (d - 1 < ord_mask) ord1 = d;
+                    full = full && bk[u].e[e] != 0;
+                }
+                if (ord1 == 0 && full && tv.has_stash) ord1 = qk_stash_find(tv, key[u]);
+                if (ord1) {
+                    ++n_hit;
+                    atomicAdd(a.counters + (ord1 - 1), 1u);
+                }
+            }
+        }
+    }
+
+    for (int o = 16; o; o >>= 1) {
+        n_emit += __shfl_xor_sync(0xffffffffu, n_emit, o);
+        n_hit += __shfl_xor_sync(0xffffffffu, n_hit, o);
+    }
+    if (lane == 0) {
+        atomicAdd(a.stats + 0, (unsigned long long)n_emit);
+        atomicAdd(a.stats + 1, (unsigned long long)n_hit);
+    }
+}
+
+static int qk_table_view_of(qk_ctx *ctx, qk_table_view *tv)
+{
+    if (ctx->dict_state != 2) return qk_fail(ctx, QK_ERR_STATE, "no dictionary built on this context");
+    const qk_table_desc *d = &ctx->desc;
+    tv->buckets = ctx->buckets;
+    tv->stash = ctx->stash;
+    tv->stash_mask = d->stash_slots - 1;
+    tv->kmask = (d->k >= 32) ? 0 : (((uint64_t)1 << (2 * d->k)) - 1); // Q.c:419 on x86-64
+    tv->k = d->k;
+    tv->rem_bits = d->rem_bits;
+    tv->ord_bits = d->ord_bits;
+    tv->has_stash = d->stash_used != 0;
+    return QK_OK;
+}
+
+static int qk_launch_count(qk_ctx *ctx, qk_slot *sl, const uint8_t *dev_bytes, size_t n_bytes)
+{
+    qk_count_args a;
+    int rc = qk_table_view_of(ctx, &a.tv);
+    if (rc) return rc;
+    a.bytes = dev_bytes;
+    a.n_bytes = (uint32_t)n_bytes;
+    a.n_tiles = (uint32_t)((n_bytes + QK_TILE - 1) / QK_TILE);
+    static int tiles_env = -1;
+    if (tiles_env < 0) {
+        const char *e = getenv("QK_TILES_PER_CTA");
+        tiles_env = e ? atoi(e) : 0;
+    }
+    uint32_t target_ctas = (uint32_t)ctx->sm_count * 3 * 4;
+    uint32_t tpc = (a.n_tiles + target_ctas - 1) / target_ctas;
+    if (tpc < 4) tpc = 4;
+    if (tiles_env > 0) tpc = (uint32_t)tiles_env;
+    a.tiles_per_cta = tpc;
+    a.counters = ctx->counters;
+    a.stats = ctx->stats;
+    const uint32_t grid = (a.n_tiles + tpc - 1) / tpc;
+    qk_timing_pair *tp;
+    rc = qk_ring_push(ctx, sl, 1, &tp);
+    if (rc) return rc;
+    QK_CUDA(ctx, cudaEventRecord(tp->a, sl->stream));
+    qk_count_kernel<<<grid, QK_THREADS, 0, sl->stream>>>(a);
+    QK_CUDA(ctx, cudaGetLastError());
+    QK_CUDA(ctx, cudaEventRecord(tp->b, sl->stream));
+    ctx->launches++;
+    return QK_OK;
+}
+
+extern "C" int qk_submit(qk_ctx *ctx, uint32_t slot, const uint8_t *bytes, size_t n_bytes, const uint32_t *line_off,
+                         uint32_t n_lines)
+{
+    (void)line_off;
+    if (!ctx || slot >= ctx->n_slots || (!bytes && n_bytes)) return QK_ERR_ARG;
+    if (n_bytes > ctx->chunk_capacity) return qk_fail(ctx, QK_ERR_ARG, "chunk of %zu bytes exceeds the slot capacity", n_bytes);
+    if (ctx->dict_state != 2) return qk_fail(ctx, QK_ERR_STATE, "no dictionary built on this context");
+    ctx->lines += n_lines;
+    if (n_bytes == 0) return QK_OK;
+    QK_CUDA(ctx, cudaSetDevice(ctx->device));
+    qk_slot *sl = &ctx->slots[slot];
+    qk_timing_pair *tp;
+    int rc = qk_ring_push(ctx, sl, 0, &tp);
+    if (rc) return rc;
+    QK_CUDA(ctx, cudaEventRecord(tp->a, sl->stream));
+    QK_CUDA(ctx, cudaMemcpyAsync(sl->dev, bytes, n_bytes, cudaMemcpyHostToDevice, sl->stream));
+    QK_CUDA(ctx, cudaEventRecord(tp->b, sl->stream));
+    QK_CUDA(ctx, cudaEventRecord(sl->h2d_done, sl->stream));
+    return qk_launch_count(ctx, sl, sl->dev, n_bytes);
+}
+
+extern "C" int qk_submit_device(qk_ctx *ctx, uint32_t slot, const uint8_t *dev_bytes, size_t n_bytes)
+{
+    if (!ctx || slot >= ctx->n_slots || !dev_bytes) return QK_ERR_ARG;
+    if (((uintptr_t)dev_bytes & 15) != 0) return qk_fail(ctx, QK_ERR_ARG, "device chunk must be 16-byte aligned");
+    if (n_bytes >= ((size_t)1 << 31)) return qk_fail(ctx, QK_ERR_ARG, "device chunk must be < 2^31 bytes");
+    if (n_bytes == 0) return QK_OK;
+    QK_CUDA(ctx, cudaSetDevice(ctx->device));
+    return qk_launch_count(ctx, &ctx->slots[slot], dev_bytes, n_bytes);
+}
+
+extern "C" int qk_counters_device_ptr(const qk_ctx *ctx, uint32_t **counters, uint64_t *n_kmers)
+{
+    if (!ctx) return QK_ERR_ARG;
+    if (ctx->dict_state != 2) return QK_ERR_STATE;
+    if (counters) *counters = ctx->counters;
+    if (n_kmers) *n_kmers = ctx->desc.n_kmers;
+    return QK_OK;
+}
+
+extern "C" int qk_reset_counters(qk_ctx *ctx)
+{
+    if (!ctx) return QK_ERR_ARG;
+    if (ctx->dict_state != 2) return QK_ERR_STATE;
+    int rc = qk_sync(ctx);
+    if (rc) return rc;
+    QK_CUDA(ctx, cudaMemset(ctx->counters, 0, (ctx->desc.n_kmers + 1) * sizeof(uint32_t)));
+    QK_CUDA(ctx, cudaMemset(ctx->stats, 0, 4 * sizeof(unsigned long long)));
+    QK_CUDA(ctx, cudaDeviceSynchronize()); // the slot streams do not order against stream 0
+    ctx->lines = 0;
+    ctx->kernel_ms = ctx->h2d_ms = 0;
+    ctx->launches = 0;
+    return QK_OK;
+}
+
+extern "C" int qk_counters_download(qk_ctx *ctx, uint64_t offset, uint32_t *out, uint64_t count)
+{
+    if (!ctx || !out) return QK_ERR_ARG;
+    if (ctx->dict_state != 2) return qk_fail(ctx, QK_ERR_STATE, "no dictionary built on this context");
+    if (offset + count > ctx->desc.n_kmers) return qk_fail(ctx, QK_ERR_ARG, "counter range outside the dictionary");
+    int rc = qk_sync(ctx);
+    if (rc) return rc;
+    QK_CUDA(ctx, cudaSetDevice(ctx->device));
+    QK_CUDA(ctx, cudaMemcpy(out, ctx->counters + offset, count * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return QK_OK;
+}
+
+// ---- results ------------------------------------------------------------------------------
+// uint32 counter -> the reference's uint16 depth: wraps mod 65,536, never saturates (T12)
+__global__ void qk_narrow_kernel(const uint32_t *__restrict__ counters, uint16_t *__restrict__ out, uint64_t n)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        out[i] = (uint16_t)(counters[i] & 0xFFFFu);
+}
+
+extern "C" int qk_finish(qk_ctx *ctx, uint16_t *counts_out, uint64_t n_kmers)
+{
+    if (!ctx || !counts_out) return QK_ERR_ARG;
+    if (ctx->dict_state != 2) return qk_fail(ctx, QK_ERR_STATE, "no dictionary built on this context");
+    if (n_kmers != ctx->desc.n_kmers) return qk_fail(ctx, QK_ERR_ARG, "n_kmers does not match the dictionary");
+    int rc = qk_sync(ctx);
+    if (rc) return rc;
+    QK_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t piece = (uint64_t)64 << 20; // entries per pass
+    uint16_t *tmp = NULL;
+    QK_CUDA(ctx, cudaMalloc((void **)&tmp, (n_kmers < piece ? n_kmers : piece) * sizeof(uint16_t)));
+    for (uint64_t at = 0; at < n_kmers; at += piece) {
+        const uint64_t m = n_kmers - at < piece ? n_kmers - at : piece;
+        qk_narrow_kernel<<<ctx->sm_count * 8, 256>>>(ctx->counters + at, tmp, m);
+        cudaError_t e = cudaMemcpy(counts_out + at, tmp, m * sizeof(uint16_t), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { cudaFree(tmp); return qk_cuda_fail(ctx, e, "D2H of counts"); }
+    }
+    cudaFree(tmp);
+    return QK_OK;
+}
+
+// GC control curve (Q.c:501-508).  Per CTA: 32-bit shared histograms over <= 16384 entries
+// (depth <= 65535 so no partial sum overflows), flushed with 64-bit global atomics.  The
+// reference squares in `int` (Q.c:507), i.e. the product wraps to negative above 46,340:
+// sumsq = sum(u) - 2^32 * #(u >= 2^31) with u the unsigned product.
+#define QK_GC_PER_CTA 16384
+__global__ void __launch_bounds__(256) qk_gc_kernel(const uint32_t *__restrict__ counters, const uint16_t *__restrict__ qgc,
+                                                    uint64_t n, unsigned long long *sum, long long *sumsq,
+                                                    unsigned long long *count)
+{
+    __shared__ uint32_t h_cnt[QK_GC_BINS], h_sum[QK_GC_BINS], h_lo[QK_GC_BINS], h_hi[QK_GC_BINS], h_neg[QK_GC_BINS];
+    for (int i = threadIdx.x; i < QK_GC_BINS; i += blockDim.x) h_cnt[i] = h_sum[i] = h_lo[i] = h_hi[i] = h_neg[i] = 0;
+    __syncthreads();
+    const uint64_t begin = (uint64_t)blockIdx.x * QK_GC_PER_CTA;
+    const uint64_t end = begin + QK_GC_PER_CTA < n ? begin + QK_GC_PER_CTA : n;
+    for (uint64_t i = begin + threadIdx.x; i < end; i += blockDim.x) {
+        const uint32_t g = qgc[i];
+        if (!(g & 0x8000u)) continue;
+        const uint32_t bin = g & 0x1FFu;
+        if (bin >= QK_GC_BINS) continue;
+        const uint32_t d = counters[i] & 0xFFFFu;
+        const uint32_t u = d * d;
+        atomicAdd(&h_cnt[bin], 1u);
+        atomicAdd(&h_sum[bin], d);
+        atomicAdd(&h_lo[bin], u & 0xFFFFu);
+        atomicAdd(&h_hi[bin], u >> 16);
+        if (u >> 31) atomicAdd(&h_neg[bin], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < QK_GC_BINS; i += blockDim.x) {
+        if (!h_cnt[i]) continue;
+        atomicAdd(&count[i], (unsigned long long)h_cnt[i]);
+        atomicAdd(&sum[i], (unsigned long long)h_sum[i]);
+        long long sq = (long long)h_lo[i] + ((long long)h_hi[i] << 16) - ((long long)h_neg[i] << 32);
+        atomicAdd(reinterpret_cast<unsigned long long *>(&sumsq[i]), (unsigned long long)sq);
+    }
+}
+
+extern "C" int qk_gc_curve(qk_ctx *ctx, const uint16_t *qgc, uint64_t n_kmers, uint64_t sum[QK_GC_BINS],
+                           int64_t sumsq[QK_GC_BINS], uint64_t count[QK_GC_BINS])
+{
+    if (!ctx || !qgc || !sum || !sumsq || !count) return QK_ERR_ARG;
+    if (ctx->dict_state != 2) return qk_fail(ctx, QK_ERR_STATE, "no dictionary built on this context");
+    if (n_kmers != ctx->desc.n_kmers) return qk_fail(ctx, QK_ERR_ARG, "n_kmers does not match the dictionary");
+    int rc = qk_sync(ctx);
+    if (rc) return rc;
+    QK_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t piece = (uint64_t)64 << 20;
+    uint16_t *dq = NULL;
+    unsigned long long *acc = NULL;
+    QK_CUDA(ctx, cudaMalloc((void **)&dq, (n_kmers < piece ? n_kmers : piece) * sizeof(uint16_t)));
+    cudaError_t e = cudaMalloc((void **)&acc, 3 * QK_GC_BINS * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(acc, 0, 3 * QK_GC_BINS * sizeof(unsigned long long));
+    for (uint64_t at = 0; e == cudaSuccess && at < n_kmers; at += piece) {
+        const uint64_t m = n_kmers - at < piece ? n_kmers - at : piece;
+        e = cudaMemcpy(dq, qgc + at, m * sizeof(uint16_t), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) break;
+        qk_gc_kernel<<<(unsigned)((m + QK_GC_PER_CTA - 1) / QK_GC_PER_CTA), 256>>>(
+            ctx->counters + at, dq, m, acc, reinterpret_cast<long long *>(acc + QK_GC_BINS), acc + 2 * QK_GC_BINS);
+        e = cudaGetLastError();
+    }
+    unsigned long long host[3 * QK_GC_BINS];
+    if (e == cudaSuccess) e = cudaMemcpy(host, acc, sizeof host, cudaMemcpyDeviceToHost);
+    cudaFree(dq);
+    cudaFree(acc);
+    if (e != cudaSuccess) return qk_cuda_fail(ctx, e, "GC control curve");
+    for (int i = 0; i < QK_GC_BINS; ++i) {
+        sum[i] = host[i];
+        sumsq[i] = (int64_t)host[QK_GC_BINS + i];
+        count[i] = host[2 * QK_GC_BINS + i];
+    }
+    return QK_OK;
+}

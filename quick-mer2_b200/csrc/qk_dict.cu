@@ -1,0 +1,405 @@
+// qk_dict.cu -- device dictionary: QM11 arrays -> (ordinal per chain entry) -> bucketised
+// table key -> ordinal.
+//
+// Replaces, on the device:
+//   * the key load of Q.c:353-359 and the chain load of Q.c:483,490
+//   * the serial chain walk of Q.c:498-516 (c = next[c] once per k-mer): here the chain is
+//     LIST-RANKED in parallel so that counters can be indexed by ordinal (= .bin index)
+//   * Find_hash's table (Q.c:90-99) -- slot placement is not observable in the .bin, so
+//     the table is rebuilt with a strong mixer, 32-byte buckets and quotiented entries
+//
+// List ranking (DESIGN.md "dictionary build"):
+//   1. every occupied slot s with s % stride == 0, plus first_idx (the head), is a
+//      splitter; one thread per splitter walks next[] to the following splitter and
+//      records (successor, segment length)                                  [walk kernel]
+//   2. pointer jumping (Wyllie) over the short splitter list gives each splitter its
+//      distance to the end of the chain, hence its ordinal                  [jump kernel]
+//   3. every splitter re-walks its segment handing out consecutive ordinals and inserts
+//      (key -> ordinal) into the new table                                [insert kernel]
+// A valid QM11 chain is a simple cycle through exactly the occupied slots; anything else
+// (chain length != occupied slots, an empty slot on the chain, a walk that never ends) is
+// rejected with QK_ERR_FORMAT.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "qk_common.cuh"
+
+// A walk ends at the next occupied slot that is a multiple of the stride; chain order is
+// unrelated to slot order, so segment lengths are geometric with mean = stride (<= 512) and
+// 2^20 steps is unreachable for a valid dictionary placed by hashing.
+#define QK_WALK_CAP (1u << 20)
+
+enum { QK_FLAG_WALK_CAP = 1, QK_FLAG_EMPTY_ON_CHAIN = 2, QK_FLAG_STASH_FULL = 4 };
+
+struct qk_build_info {
+    unsigned long long occupied;
+    unsigned long long skipped;
+    unsigned long long stash_used;
+    unsigned int flags;
+    unsigned int pad;
+};
+
+extern "C" int qk_dict_begin(qk_ctx *ctx, uint8_t k, uint64_t hash_size, uint64_t first_idx)
+{
+    if (!ctx) return QK_ERR_ARG;
+    if (k < 1 || k > 32) return qk_fail(ctx, QK_ERR_ARG, "k=%u outside 1..32", (unsigned)k);
+    if (hash_size < 2 || (hash_size & (hash_size - 1)) || hash_size > ((uint64_t)1 << 32))
+        return qk_fail(ctx, QK_ERR_FORMAT, "hash size 0x%llx is not a power of two <= 2^32 (Q.c:20 chain is u32)",
+                       (unsigned long long)hash_size);
+    if (first_idx >= hash_size) return qk_fail(ctx, QK_ERR_FORMAT, "first index outside the table");
+    QK_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaFree(ctx->raw_keys);
+    cudaFree(ctx->raw_next);
+    cudaFree(ctx->buckets);
+    cudaFree(ctx->stash);
+    cudaFree(ctx->counters);
+    ctx->raw_keys = NULL; ctx->raw_next = NULL; ctx->buckets = NULL; ctx->stash = NULL; ctx->counters = NULL;
+    ctx->dict_state = 0;
+    QK_CUDA(ctx, cudaMalloc((void **)&ctx->raw_keys, hash_size * sizeof(uint64_t)));
+    QK_CUDA(ctx, cudaMalloc((void **)&ctx->raw_next, hash_size * sizeof(uint32_t)));
+    ctx->k = k;
+    ctx->hash_size = hash_size;
+    ctx->first_idx = first_idx;
+    ctx->dict_state = 1;
+    return QK_OK;
+}
+
+extern "C" int qk_dict_upload_keys(qk_ctx *ctx, uint64_t slot_offset, const uint64_t *keys, uint64_t count)
+{
+    if (!ctx || !keys) return QK_ERR_ARG;
+    if (ctx->dict_state != 1) return qk_fail(ctx, QK_ERR_STATE, "qk_dict_begin not called");
+    if (slot_offset + count > ctx->hash_size) return qk_fail(ctx, QK_ERR_ARG, "key range outside the table");
+    QK_CUDA(ctx, cudaMemcpy(ctx->raw_keys + slot_offset, keys, count * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    return QK_OK;
+}
+
+extern "C" int qk_dict_upload_chain(qk_ctx *ctx, uint64_t slot_offset, const uint32_t *next, uint64_t count)
+{
+    if (!ctx || !next) return QK_ERR_ARG;
+    if (ctx->dict_state != 1) return qk_fail(ctx, QK_ERR_STATE, "qk_dict_begin not called");
+    if (slot_offset + count > ctx->hash_size) return qk_fail(ctx, QK_ERR_ARG, "chain range outside the table");
+    QK_CUDA(ctx, cudaMemcpy(ctx->raw_next + slot_offset, next, count * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    return QK_OK;
+}
+
+// ---- kernels ---------------------------------------------------------------------------
+__global__ void qk_count_occupied(const uint64_t *__restrict__ keys, uint64_t n, qk_build_info *info)
+{
+    unsigned long long local = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        local += keys[i] != 0;
+    for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(&info->occupied, local);
+}
+
+// Node ids: 0..n_split-1 = slot id*stride, n_split = head (first_idx), n_split+1 = END.
+__device__ __forceinline__ bool qk_node_slot(uint64_t id, uint64_t n_split, uint32_t stride_log2, uint64_t first,
+                                             const uint64_t *keys, uint64_t *slot)
+{
+    if (id == n_split) { *slot = first; return true; }
+    uint64_t s = id << stride_log2;
+    *slot = s;
+    return s != first && keys[s] != 0;
+}
+
+__global__ void qk_walk_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ next, uint64_t n_split,
+                               uint32_t stride_log2, uint64_t first, uint32_t *succ, unsigned long long *dist,
+                               uint32_t *seg_len, qk_build_info *info)
+{
+    uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id > n_split + 1) return;
+    const uint32_t END = (uint32_t)(n_split + 1);
+    uint64_t slot;
+    if (id == n_split + 1 || !qk_node_slot(id, n_split, stride_log2, first, keys, &slot)) {
+        succ[id] = END; dist[id] = 0; seg_len[id] = 0;
+        return;
+    }
+    const uint64_t smask = ((uint64_t)1 << stride_log2) - 1;
+    uint64_t c = slot;
+    uint32_t len = 0;
+    do {
+        c = next[c];
+        ++len;
+    } while (c != first && (c & smask) != 0 && len < QK_WALK_CAP);
+    if (len >= QK_WALK_CAP) atomicOr(&info->flags, QK_FLAG_WALK_CAP);
+    succ[id] = (c == first) ? END : (uint32_t)(c >> stride_log2);
+    dist[id] = len;
+    seg_len[id] = len;
+}
+
+// One round of pointer jumping: dist = distance (in chain entries) to END.
+__global__ void qk_jump_kernel(const uint32_t *__restrict__ succ_in, const unsigned long long *__restrict__ dist_in,
+                               uint32_t *succ_out, unsigned long long *dist_out, uint64_t n_nodes)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    uint32_t s = succ_in[i];
+    dist_out[i] = dist_in[i] + dist_in[s];
+    succ_out[i] = succ_in[s];
+}
+
+// Does Find_hash (Q.c:90-99) reach `slot` when asked for its own key?  False only for the
+// later copies of a duplicated key (dictionaries written by `index`).
+__device__ __forceinline__ bool qk_is_primary(const uint64_t *__restrict__ keys, uint64_t hash_size, uint64_t slot,
+                                              uint64_t key)
+{
+    uint64_t s = qk_djb(key) & (hash_size - 1);
+    const long long step = (s & (hash_size >> 1)) ? -1 : 1;
+    for (;;) {
+        if (s == slot) return true;
+        uint64_t v = keys[s];
+        if (v == key) return false; // an earlier copy shadows this slot
+        if (v == 0) return false;   // unreachable from its home: never found by the reference
+        s = (uint64_t)((long long)s + step);
+        if (s >= hash_size) return false;
+    }
+}
+
+struct qk_build_params {
+    qk_bucket *buckets;
+    qk_stash_entry *stash;
+    uint64_t stash_mask;
+    uint64_t stash_limit;
+    uint32_t rem_bits, ord_bits;
+};
+
+__device__ __forceinline__ void qk_table_insert(const qk_build_params &bp, uint64_t key, uint64_t ord1,
+                                                qk_build_info *info)
+{
+    const uint64_t h = qk_mix60(key);
+    const uint64_t bucket = h >> bp.rem_bits;
+    const uint64_t rem = h & (((uint64_t)1 << bp.rem_bits) - 1);
+    const unsigned long long entry = (rem << bp.ord_bits) | ord1;
+    unsigned long long *e = bp.buckets[bucket].e;
+#pragma unroll
+    for (int i = 0; i < QK_BUCKET_ENTRIES; ++i) {
+        if (e[i] == 0 && atomicCAS(&e[i], 0ull, entry) == 0ull) return;
+    }
+    // home bucket full: stash
+    unsigned long long used = atomicAdd(&info->stash_used, 1ull);
+    if (used >= bp.stash_limit) { atomicOr(&info->flags, QK_FLAG_STASH_FULL); return; }
+    uint64_t s = qk_mix_stash(key) & bp.stash_mask;
+    for (;;) {
+        unsigned long long old = atomicCAS(&bp.stash[s].key, 0ull, (unsigned long long)key);
+        if (old == 0ull) { bp.stash[s].ord1 = (uint32_t)ord1; return; }
+        s = (s + 1) & bp.stash_mask;
+    }
+}
+
+__global__ void qk_insert_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ next, uint64_t hash_size,
+                                 uint64_t n_split, uint32_t stride_log2, uint64_t first,
+                                 const unsigned long long *__restrict__ dist, const uint32_t *__restrict__ seg_len,
+                                 unsigned long long total, qk_build_params bp, qk_build_info *info)
+{
+    uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id > n_split) return;
+    uint32_t len = seg_len[id];
+    if (len == 0) return;
+    uint64_t c = (id == n_split) ? first : (id << stride_log2);
+    uint64_t ord = total - dist[id];
+    for (uint32_t i = 0; i < len; ++i, ++ord) {
+        uint64_t key = keys[c];
+        uint64_t nx = next[c];
+        if (key == 0) atomicOr(&info->flags, QK_FLAG_EMPTY_ON_CHAIN);
+        else if ((key >> QK_KEY_BITS) != 0 || !qk_is_primary(keys, hash_size, c, key)) atomicAdd(&info->skipped, 1ull);
+        else qk_table_insert(bp, key, ord + 1, info);
+        c = nx;
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------
+static uint32_t qk_bits_for(uint64_t v) // smallest b with v < 2^b
+{
+    uint32_t b = 0;
+    while (b < 64 && (v >> b) != 0) ++b;
+    return b;
+}
+
+// Geometry for n chain entries: buckets = smallest power of two with <= 2.8 keys per
+// 4-entry bucket on average; the stash is sized from the Poisson overflow expectation.
+static void qk_geometry(uint64_t n, uint32_t k, uint64_t stash_slots_min, qk_table_desc *d)
+{
+    memset(d, 0, sizeof *d);
+    d->n_kmers = n;
+    d->k = k;
+    uint64_t nb = 1;
+    while ((double)n / (double)nb > 2.8) nb <<= 1;
+    if (nb < 64) nb = 64;
+    d->n_buckets = nb;
+    d->bucket_bits = qk_bits_for(nb - 1);
+    d->rem_bits = QK_KEY_BITS - d->bucket_bits;
+    d->ord_bits = qk_bits_for(n); // holds ordinal + 1 <= n
+    if (d->ord_bits == 0) d->ord_bits = 1;
+    // expected fraction of keys that find their 4-entry bucket full, keys/bucket ~ Poisson(lambda)
+    const double lambda = (double)n / (double)nb;
+    double p = exp(-lambda), over = 0;
+    for (int x = 1; x <= 64; ++x) {
+        p *= lambda / x;
+        if (x > QK_BUCKET_ENTRIES) over += (x - QK_BUCKET_ENTRIES) * p;
+    }
+    uint64_t want = (uint64_t)(over / lambda * (double)n * 1.25) + 1024;
+    if (want < stash_slots_min) want = stash_slots_min;
+    uint64_t ss = 1024;
+    while (ss < 2 * want) ss <<= 1;
+    d->stash_slots = ss;
+    d->table_bytes = nb * sizeof(qk_bucket);
+    d->stash_bytes = ss * sizeof(qk_stash_entry);
+}
+
+static int qk_alloc_table(qk_ctx *ctx, const qk_table_desc *d)
+{
+    cudaFree(ctx->buckets);
+    cudaFree(ctx->stash);
+    cudaFree(ctx->counters);
+    ctx->buckets = NULL; ctx->stash = NULL; ctx->counters = NULL;
+    QK_CUDA(ctx, cudaMalloc((void **)&ctx->buckets, d->table_bytes));
+    QK_CUDA(ctx, cudaMalloc((void **)&ctx->stash, d->stash_bytes));
+    QK_CUDA(ctx, cudaMalloc((void **)&ctx->counters, (d->n_kmers + 1) * sizeof(uint32_t)));
+    QK_CUDA(ctx, cudaMemset(ctx->counters, 0, (d->n_kmers + 1) * sizeof(uint32_t)));
+    QK_CUDA(ctx, cudaDeviceSynchronize()); // the slot streams do not order against stream 0
+    return QK_OK;
+}
+
+extern "C" int qk_dict_build(qk_ctx *ctx, uint64_t *n_kmers_out)
+{
+    if (!ctx) return QK_ERR_ARG;
+    if (ctx->dict_state != 1) return qk_fail(ctx, QK_ERR_STATE, "qk_dict_begin/upload not called");
+    QK_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t H = ctx->hash_size, first = ctx->first_idx;
+    // stride: about 2^19 walkers or more, segments of 16..512 slots
+    uint32_t stride_log2 = 4;
+    while (stride_log2 < 9 && (H >> (stride_log2 + 1)) >= ((uint64_t)1 << 19)) ++stride_log2;
+    if (((uint64_t)1 << stride_log2) > H) stride_log2 = qk_bits_for(H - 1);
+    const uint64_t n_split = H >> stride_log2;
+    const uint64_t n_nodes = n_split + 2;
+
+    qk_build_info *info = NULL;
+    uint32_t *succ[2] = {NULL, NULL}, *seg_len = NULL;
+    unsigned long long *dist[2] = {NULL, NULL};
+    int rc = QK_OK;
+#define QK_TRY(call)                                                               \
+    do {                                                                           \
+        cudaError_t e__ = (call);                                                  \
+        if (e__ != cudaSuccess) { rc = qk_cuda_fail(ctx, e__, #call); goto done; } \
+    } while (0)
+    qk_build_info hinfo;
+    qk_table_desc d;
+    unsigned long long total = 0;
+    int cur = 0;
+    uint64_t stash_min = 0;
+
+    QK_TRY(cudaMalloc((void **)&info, sizeof(qk_build_info)));
+    QK_TRY(cudaMemset(info, 0, sizeof(qk_build_info)));
+    for (int i = 0; i < 2; ++i) {
+        QK_TRY(cudaMalloc((void **)&succ[i], n_nodes * sizeof(uint32_t)));
+        QK_TRY(cudaMalloc((void **)&dist[i], n_nodes * sizeof(unsigned long long)));
+    }
+    QK_TRY(cudaMalloc((void **)&seg_len, n_nodes * sizeof(uint32_t)));
+
+    qk_count_occupied<<<ctx->sm_count * 8, 256>>>(ctx->raw_keys, H, info);
+    qk_walk_kernel<<<(unsigned)((n_nodes + 127) / 128), 128>>>(ctx->raw_keys, ctx->raw_next, n_split, stride_log2, first,
+                                                               succ[0], dist[0], seg_len, info);
+    QK_TRY(cudaGetLastError());
+    for (uint64_t span = 1; span < n_nodes; span <<= 1) {
+        qk_jump_kernel<<<(unsigned)((n_nodes + 255) / 256), 256>>>(succ[cur], dist[cur], succ[cur ^ 1], dist[cur ^ 1],
+                                                                   n_nodes);
+        cur ^= 1;
+    }
+    QK_TRY(cudaGetLastError());
+    QK_TRY(cudaMemcpy(&total, dist[cur] + n_split, sizeof total, cudaMemcpyDeviceToHost));
+    QK_TRY(cudaMemcpy(&hinfo, info, sizeof hinfo, cudaMemcpyDeviceToHost));
+    if (hinfo.flags & QK_FLAG_WALK_CAP) {
+        rc = qk_fail(ctx, QK_ERR_FORMAT, "chain walk did not reach a splitter within %u steps: corrupt chain", QK_WALK_CAP);
+        goto done;
+    }
+    if (total != hinfo.occupied || total == 0) {
+        rc = qk_fail(ctx, QK_ERR_FORMAT,
+                     "chain from first_idx has %llu entries but the table holds %llu keys: not a QM11 chain", total,
+                     hinfo.occupied);
+        goto done;
+    }
+
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        qk_geometry(total, ctx->k, stash_min, &d);
+        if (d.rem_bits + d.ord_bits > 64) {
+            rc = qk_fail(ctx, QK_ERR_FORMAT, "entry needs %u bits", d.rem_bits + d.ord_bits);
+            goto done;
+        }
+        rc = qk_alloc_table(ctx, &d);
+        if (rc) goto done;
+        QK_TRY(cudaMemset(ctx->buckets, 0, d.table_bytes));
+        QK_TRY(cudaMemset(ctx->stash, 0, d.stash_bytes));
+        QK_TRY(cudaMemset(info, 0, sizeof(qk_build_info)));
+        qk_build_params bp;
+        bp.buckets = ctx->buckets;
+        bp.stash = ctx->stash;
+        bp.stash_mask = d.stash_slots - 1;
+        bp.stash_limit = d.stash_slots / 2;
+        bp.rem_bits = d.rem_bits;
+        bp.ord_bits = d.ord_bits;
+        qk_insert_kernel<<<(unsigned)((n_split + 1 + 127) / 128), 128>>>(ctx->raw_keys, ctx->raw_next, H, n_split, stride_log2,
+                                                                         first, dist[cur], seg_len, total, bp, info);
+        QK_TRY(cudaGetLastError());
+        QK_TRY(cudaMemcpy(&hinfo, info, sizeof hinfo, cudaMemcpyDeviceToHost));
+        if (hinfo.flags & QK_FLAG_EMPTY_ON_CHAIN) {
+            rc = qk_fail(ctx, QK_ERR_FORMAT, "the chain passes through an empty slot: not a QM11 chain");
+            goto done;
+        }
+        if (!(hinfo.flags & QK_FLAG_STASH_FULL)) break;
+        stash_min = hinfo.stash_used + 1024; // retry with a stash that holds what was needed
+        if (attempt == 3) { rc = qk_fail(ctx, QK_ERR_NOMEM, "stash overflow after 4 attempts"); goto done; }
+    }
+    d.stash_used = hinfo.stash_used;
+    d.skipped_keys = hinfo.skipped;
+    ctx->desc = d;
+    ctx->dict_state = 2;
+    if (n_kmers_out) *n_kmers_out = total;
+
+done:
+    cudaFree(info);
+    cudaFree(succ[0]); cudaFree(succ[1]);
+    cudaFree(dist[0]); cudaFree(dist[1]);
+    cudaFree(seg_len);
+    cudaFree(ctx->raw_keys);
+    cudaFree(ctx->raw_next);
+    ctx->raw_keys = NULL;
+    ctx->raw_next = NULL;
+    if (rc) ctx->dict_state = 0;
+    return rc;
+#undef QK_TRY
+}
+
+extern "C" int qk_dict_describe(const qk_ctx *ctx, qk_table_desc *desc)
+{
+    if (!ctx || !desc) return QK_ERR_ARG;
+    if (ctx->dict_state != 2) return QK_ERR_STATE;
+    *desc = ctx->desc;
+    return QK_OK;
+}
+
+extern "C" int qk_dict_adopt(qk_ctx *ctx, const qk_table_desc *desc)
+{
+    if (!ctx || !desc) return QK_ERR_ARG;
+    if (desc->n_buckets == 0 || (desc->n_buckets & (desc->n_buckets - 1)) || desc->stash_slots == 0 ||
+        (desc->stash_slots & (desc->stash_slots - 1)) || desc->table_bytes != desc->n_buckets * sizeof(qk_bucket) ||
+        desc->stash_bytes != desc->stash_slots * sizeof(qk_stash_entry) || desc->rem_bits + desc->ord_bits > 64 ||
+        desc->rem_bits + desc->bucket_bits != QK_KEY_BITS || desc->k < 1 || desc->k > 32)
+        return qk_fail(ctx, QK_ERR_ARG, "inconsistent table descriptor");
+    QK_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = qk_alloc_table(ctx, desc);
+    if (rc) return rc;
+    ctx->desc = *desc;
+    ctx->k = (uint8_t)desc->k;
+    ctx->dict_state = 2;
+    return QK_OK;
+}
+
+extern "C" int qk_dict_device_ptrs(const qk_ctx *ctx, void **table, void **stash)
+{
+    if (!ctx) return QK_ERR_ARG;
+    if (ctx->dict_state != 2) return QK_ERR_STATE;
+    if (table) *table = ctx->buckets;
+    if (stash) *stash = ctx->stash;
+    return QK_OK;
+}

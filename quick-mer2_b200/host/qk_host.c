@@ -1,0 +1,415 @@
+/*
+ * qk_host.c -- host side of `count` in C: QM11 reader, FASTA/FASTQ framer, .bin/.txt
+ * writers, streaming driver and the command.  See include/qk_host.h for the contract and
+ * the reference lines each piece replaces.  No k-mer arithmetic happens here.
+ */
+#define _GNU_SOURCE
+#define _FILE_OFFSET_BITS 64
+#include <errno.h>
+#include <fcntl.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <time.h>
+#include <unistd.h>
+
+#include "../../include/qk_host.h"
+
+/* ------------------------------------------------------------------ QM11 reader ------ */
+int qk_qm_read_header(const char *qm_path, qk_qm_header *hdr)
+{
+    if (!qm_path || !hdr) return QK_ERR_ARG;
+    FILE *f = fopen(qm_path, "rb");
+    if (!f) return QK_ERR_IO;
+    uint8_t raw[24];
+    size_t got = fread(raw, 1, sizeof raw, f);
+    fclose(f);
+    if (got != sizeof raw) return QK_ERR_IO;
+    hdr->k = raw[4];                        /* Q.c:345-346 */
+    memcpy(&hdr->hash_size, raw + 8, 8);    /* Q.c:348-349 */
+    memcpy(&hdr->first_idx, raw + 16, 8);   /* Q.c:350-351 */
+    return QK_OK;
+}
+
+int qk_qm_load(qk_ctx *ctx, const char *qm_path, qk_qm_header *hdr_out, uint64_t *n_kmers_out)
+{
+    qk_qm_header hdr;
+    int rc = qk_qm_read_header(qm_path, &hdr);
+    if (rc) return rc;
+    if (hdr_out) *hdr_out = hdr;
+    rc = qk_dict_begin(ctx, hdr.k, hdr.hash_size, hdr.first_idx);
+    if (rc) return rc;
+    FILE *f = fopen(qm_path, "rb");
+    if (!f) return QK_ERR_IO;
+    const size_t piece = (size_t)64 << 20;
+    void *buf = malloc(piece);
+    if (!buf) { fclose(f); return QK_ERR_NOMEM; }
+    rc = QK_OK;
+    if (fseeko(f, 24, SEEK_SET) != 0) rc = QK_ERR_IO;
+    for (uint64_t at = 0; !rc && at < hdr.hash_size;) {       /* keys, Q.c:359 */
+        uint64_t m = hdr.hash_size - at;
+        if (m > piece / 8) m = piece / 8;
+        if (fread(buf, 8, m, f) != m) { rc = QK_ERR_IO; break; }
+        rc = qk_dict_upload_keys(ctx, at, (const uint64_t *)buf, m);
+        at += m;
+    }
+    for (uint64_t at = 0; !rc && at < hdr.hash_size;) {       /* chain, Q.c:483 */
+        uint64_t m = hdr.hash_size - at;
+        if (m > piece / 4) m = piece / 4;
+        if (fread(buf, 4, m, f) != m) { rc = QK_ERR_IO; break; }
+        rc = qk_dict_upload_chain(ctx, at, (const uint32_t *)buf, m);
+        at += m;
+    }
+    free(buf);
+    fclose(f);
+    if (rc) return rc;
+    return qk_dict_build(ctx, n_kmers_out);
+}
+
+/* ------------------------------------------------------------------ framer ----------- */
+struct qk_framer {
+    int fd;             /* -1 for in-memory input */
+    int seekable;
+    int own_buf;
+    uint8_t *buf;
+    size_t cap, pos, have;
+    int eof;
+    int started;        /* first line seen */
+    int skip;           /* FASTQ: lines still to discard after a read (Q.c:451-455) */
+    qk_framer_stats st;
+};
+
+static qk_framer *framer_new(void)
+{
+    qk_framer *f = calloc(1, sizeof *f);
+    if (f) f->fd = -1;
+    return f;
+}
+
+qk_framer *qk_framer_open_fd(int fd, int seekable)
+{
+    qk_framer *f = framer_new();
+    if (!f) return NULL;
+    f->fd = fd;
+    f->seekable = seekable;
+    f->cap = (size_t)8 << 20;
+    f->buf = malloc(f->cap);
+    f->own_buf = 1;
+    if (!f->buf) { free(f); return NULL; }
+    return f;
+}
+
+qk_framer *qk_framer_open(const char *path)
+{
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return NULL;
+    /* Q.c:396 fseek(0): works on regular files, fails silently on pipes */
+    int seekable = lseek(fd, 0, SEEK_CUR) != (off_t)-1;
+    qk_framer *f = qk_framer_open_fd(fd, seekable);
+    if (!f) close(fd);
+    return f;
+}
+
+qk_framer *qk_framer_open_mem(const uint8_t *data, size_t n, int seekable)
+{
+    qk_framer *f = framer_new();
+    if (!f) return NULL;
+    f->buf = (uint8_t *)data;
+    f->cap = f->have = n;
+    f->eof = 1;
+    f->seekable = seekable;
+    return f;
+}
+
+void qk_framer_close(qk_framer *f)
+{
+    if (!f) return;
+    if (f->fd >= 0) close(f->fd);
+    if (f->own_buf) free(f->buf);
+    free(f);
+}
+
+void qk_framer_get_stats(const qk_framer *f, qk_framer_stats *st)
+{
+    if (f && st) *st = f->st;
+}
+
+/* slide the unread tail to the front and read more; returns bytes added (0 at EOF) */
+static long framer_refill(qk_framer *f)
+{
+    if (f->eof || f->fd < 0) { f->eof = 1; return 0; }
+    if (f->pos) {
+        memmove(f->buf, f->buf + f->pos, f->have - f->pos);
+        f->have -= f->pos;
+        f->pos = 0;
+    }
+    if (f->have == f->cap) { /* one line larger than the window: grow */
+        uint8_t *nb = realloc(f->buf, f->cap * 2);
+        if (!nb) return -1;
+        f->buf = nb;
+        f->cap *= 2;
+    }
+    for (;;) {
+        ssize_t got = read(f->fd, f->buf + f->have, f->cap - f->have);
+        if (got < 0 && errno == EINTR) continue;
+        if (got < 0) return -1;
+        if (got == 0) f->eof = 1;
+        f->have += (size_t)got;
+        return (long)got;
+    }
+}
+
+int qk_framer_next(qk_framer *f, uint8_t *dst, size_t cap, size_t *n_bytes, uint32_t *line_off, uint32_t off_cap,
+                   uint32_t *n_lines)
+{
+    if (!f || !dst || !n_bytes || cap < 100000) return -QK_ERR_ARG;
+    size_t out = 0;
+    uint32_t nl = 0;
+    if (line_off) {
+        if (off_cap < 2) return -QK_ERR_ARG;
+        line_off[0] = 0;
+    }
+    for (;;) {
+        size_t searched = 0;
+        const uint8_t *line = f->buf + f->pos;
+        const uint8_t *end = NULL;
+        size_t avail = f->have - f->pos;
+        if (avail) end = memchr(line, '\n', avail);
+        int unterminated = 0;
+        size_t len;
+        (void)searched;
+        if (!end) {
+            if (!f->eof) {
+                long got = framer_refill(f);
+                if (got < 0) return -QK_ERR_IO;
+                continue;
+            }
+            if (avail == 0) break;          /* end of input */
+            unterminated = 1;               /* T9: reference is undefined; we terminate the line */
+            len = avail;
+        } else {
+            len = (size_t)(end - line) + 1; /* includes the '\n' */
+        }
+        if (!f->started) {                  /* Q.c:393-396 */
+            f->started = 1;
+            if (line[0] == '@') { f->st.fastq = 1; goto consume; }
+            if (!f->seekable) goto consume; /* fseek on a pipe fails: first line is lost */
+        }
+        if (f->skip) { f->skip--; goto consume; }
+        if (line[0] == '>') goto consume;   /* Q.c:398 */
+        {
+            size_t need = len + (size_t)unterminated;
+            if (out + need > cap || (line_off && nl + 2 > off_cap)) {
+                if (out == 0) return -QK_ERR_ARG; /* a single line larger than the chunk */
+                break;                            /* chunk full: leave the line for the next call */
+            }
+            memcpy(dst + out, line, len);
+            if (unterminated) { dst[out + len] = '\n'; f->st.unterminated++; }
+            out += need;
+            ++nl;
+            if (line_off) line_off[nl] = (uint32_t)out;
+            f->st.lines++;
+            f->st.bases += need - 1;
+            if (need > QK_MAX_LINE_BYTES) f->st.long_lines++;
+            if (f->st.fastq) f->skip = 3;   /* Q.c:451-455 */
+        }
+    consume:
+        f->pos += len;
+        f->st.raw_bytes += len;
+    }
+    *n_bytes = out;
+    if (n_lines) *n_lines = nl;
+    return out ? 1 : 0;
+}
+
+/* ------------------------------------------------------------------ writers ---------- */
+int qk_write_bin(const char *path, const uint16_t *counts, uint64_t n)
+{
+    FILE *f = fopen(path, "wb");
+    if (!f) return QK_ERR_IO;
+    size_t w = fwrite(counts, sizeof(uint16_t), n, f); /* Q.c:512,517 */
+    int rc = (w == n) ? QK_OK : QK_ERR_IO;
+    if (fclose(f) != 0) rc = QK_ERR_IO;
+    return rc;
+}
+
+int qk_write_gc_txt(const char *path, const uint64_t sum[QK_GC_BINS], const int64_t sumsq[QK_GC_BINS],
+                    const uint64_t count[QK_GC_BINS], double *mean_depth)
+{
+    FILE *f = fopen(path, "w");
+    if (!f) return QK_ERR_IO;
+    double total_depth = 0;
+    uint64_t total_count = 0;
+    for (int i = 0; i < QK_GC_BINS; ++i) {          /* Q.c:529-538 */
+        double curve = (double)sum[i], sd = (double)sumsq[i];
+        uint32_t c32 = (uint32_t)count[i];            /* uint32_t Control_count, Q.c:497 */
+        total_count += c32;
+        total_depth += curve;
+        if (c32) {
+            curve /= c32;
+            volatile double m2 = curve * curve;       /* keep the product rounded: no FMA */
+            sd = sd / c32 - m2;
+        }
+        fprintf(f, "%.2f\t%f\t%i\t%f\n", i / 4.0, curve, (int)c32, sd);
+    }
+    if (mean_depth) *mean_depth = total_depth / (double)total_count; /* Q.c:539 */
+    return fclose(f) == 0 ? QK_OK : QK_ERR_IO;
+}
+
+/* ------------------------------------------------------------------ driver ----------- */
+int qk_count_framer(qk_ctx *ctx, qk_framer *f, qk_framer_stats *st)
+{
+    uint32_t n_slots = 0;
+    size_t cap = 0;
+    int rc = qk_ctx_info(ctx, &n_slots, &cap);
+    if (rc) return rc;
+    uint32_t slot = 0;
+    for (;;) {
+        rc = qk_wait_slot(ctx, slot);       /* "find an idle worker", Q.c:433-437 */
+        if (rc) return rc;
+        uint8_t *dst = qk_slot_host_buffer(ctx, slot);
+        size_t n = 0;
+        uint32_t nl = 0;
+        int r = qk_framer_next(f, dst, cap, &n, NULL, 0, &nl);
+        if (r < 0) return -r;
+        if (r == 0) break;
+        rc = qk_submit(ctx, slot, dst, n, NULL, nl); /* "sem_post", Q.c:431-432 */
+        if (rc) return rc;
+        slot = (slot + 1) % n_slots;
+    }
+    rc = qk_sync(ctx);                       /* drain + join, Q.c:458-479 */
+    if (st) qk_framer_get_stats(f, st);
+    return rc;
+}
+
+int qk_count_file(qk_ctx *ctx, const char *reads_path, qk_framer_stats *st)
+{
+    qk_framer *f = qk_framer_open(reads_path);
+    if (!f) return QK_ERR_IO;
+    int rc = qk_count_framer(ctx, f, st);
+    qk_framer_close(f);
+    return rc;
+}
+
+/* ------------------------------------------------------------------ command ---------- */
+static void help_count(void)
+{
+    puts("\nquicKmer2 count [Options] ref.fa sample.fast[a/q] Out_prefix\n\nOptions:");
+    puts("-h\t\tShow this help information");
+    puts("-t [num]\tNumber of threads (accepted for compatibility; counting runs on the GPU)");
+    puts("-g [num]\tCUDA device index (default 0)");
+}
+
+static double now_sec(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + ts.tv_nsec * 1e-9;
+}
+
+int qk_count_main(int argc, char **argv)
+{
+    int device = 0;
+    unsigned threads = 0;
+    if (argc < 2) { help_count(); return 1; }          /* Q.c:309-312 */
+    int opt;
+    optind = 1;
+    while ((opt = getopt(argc, argv, "ht:g:")) != -1) { /* Q.c:314-333 */
+        switch (opt) {
+        case 'h': help_count(); return 1;
+        case 't':
+            threads = (uint8_t)atoi(optarg);            /* uint8_t thread_count, Q.c:306 */
+            printf("[Option] Set %u threads\n", threads);
+            break;
+        case 'g': device = atoi(optarg); break;
+        case '?': puts("Option error, check help"); help_count(); return 1;
+        default: return 1;
+        }
+    }
+    if (argc < 4) { help_count(); return 1; }
+    const char *ref_prefix = argv[argc - 3], *reads = argv[argc - 2], *out_prefix = argv[argc - 1]; /* Q.c:335-342 */
+    char path[65536];
+    snprintf(path, sizeof path, "%s.qm", ref_prefix);
+    qk_qm_header hdr;
+    if (qk_qm_read_header(path, &hdr) != QK_OK) {
+        printf("Dictionary %s open fail\n", path);
+        return 1;
+    }
+    qk_framer *fr = qk_framer_open(reads);
+    if (!fr) { puts("Input open fail"); return 1; }    /* Q.c:339-341 (the reference goes on and crashes) */
+    printf("Hash Size: 0x%lX\nFirst location: 0x%lX\n", (unsigned long)hdr.hash_size, (unsigned long)hdr.first_idx);
+
+    double t0 = now_sec();
+    qk_ctx *ctx = NULL;
+    int rc = qk_ctx_create(&ctx, device, 4, (size_t)32 << 20);
+    if (rc) {
+        printf("GPU context failed: %s\n", ctx ? qk_last_error(ctx) : "no CUDA device");
+        qk_ctx_destroy(ctx);
+        return 1;
+    }
+    uint64_t n_kmers = 0;
+    rc = qk_qm_load(ctx, path, NULL, &n_kmers);
+    if (rc) {
+        printf("Dictionary load failed: %s\n", rc == QK_ERR_IO ? "short read" : qk_last_error(ctx));
+        if (rc == QK_ERR_NOMEM) puts("Memory allocation failed"); /* Q.c:355,362 */
+        qk_ctx_destroy(ctx);
+        return 1;
+    }
+    printf("Read 0x%lX hash\n", (unsigned long)hdr.hash_size);            /* Q.c:359 */
+    double t1 = now_sec();
+    time_t start_time, end_time;
+    time(&start_time);                                                     /* Q.c:387 */
+    qk_framer_stats st;
+    rc = qk_count_framer(ctx, fr, &st);
+    qk_framer_close(fr);
+    uint64_t total = 0, hits = 0;
+    if (!rc) rc = qk_stats(ctx, &total, &hits, NULL);
+    if (rc) { printf("Counting failed: %s\n", qk_last_error(ctx)); qk_ctx_destroy(ctx); return 1; }
+    time(&end_time);
+    double t2 = now_sec();
+    printf("Counting elapse %u sec, total %lu kmers\n", (unsigned)(end_time - start_time), (unsigned long)total); /* Q.c:481 */
+    printf("Pileup finish\nRead chain file %lu entries\n", (unsigned long)hdr.hash_size);                         /* Q.c:483 */
+
+    uint16_t *counts = malloc((n_kmers ? n_kmers : 1) * sizeof(uint16_t));
+    if (!counts) { puts("Memory allocation failed"); qk_ctx_destroy(ctx); return 1; }
+    rc = qk_finish(ctx, counts, n_kmers);
+    if (rc) { printf("Result download failed: %s\n", qk_last_error(ctx)); free(counts); qk_ctx_destroy(ctx); return 1; }
+    snprintf(path, sizeof path, "%s.bin", out_prefix);
+    if (qk_write_bin(path, counts, n_kmers)) { printf("Cannot write %s\n", path); free(counts); qk_ctx_destroy(ctx); return 1; }
+    free(counts);
+
+    snprintf(path, sizeof path, "%s.qgc", ref_prefix);                     /* Q.c:484-488 */
+    FILE *gc = fopen(path, "rb");
+    if (!gc) printf("GC control file %s absent. Continue without GC correction!\n", path);
+    else {
+        uint16_t *qgc = calloc(n_kmers ? n_kmers : 1, sizeof(uint16_t));
+        if (!qgc) { puts("Memory allocation failed"); fclose(gc); qk_ctx_destroy(ctx); return 1; }
+        size_t got = fread(qgc, sizeof(uint16_t), n_kmers, gc);
+        (void)got;
+        fclose(gc);
+        uint64_t sum[QK_GC_BINS], cnt[QK_GC_BINS];
+        int64_t sq[QK_GC_BINS];
+        rc = qk_gc_curve(ctx, qgc, n_kmers, sum, sq, cnt);
+        free(qgc);
+        if (rc) { printf("GC curve failed: %s\n", qk_last_error(ctx)); qk_ctx_destroy(ctx); return 1; }
+        double mean = 0;
+        snprintf(path, sizeof path, "%s.txt", out_prefix);                 /* Q.c:523-525 */
+        if (qk_write_gc_txt(path, sum, sq, cnt, &mean)) { printf("Cannot write %s\n", path); qk_ctx_destroy(ctx); return 1; }
+        printf("Mean sequencing depth: %.2f\n", mean);                     /* Q.c:540 */
+    }
+    double t3 = now_sec();
+    double kms = 0, hms = 0;
+    uint64_t launches = 0;
+    qk_timing(ctx, &kms, &hms, &launches);
+    qk_ctx_destroy(ctx);
+    puts("Exit quicK-mer2 count");                                          /* Q.c:543 */
+    fprintf(stderr,
+            "{\"total_kmers\": %llu, \"hits\": %llu, \"lines\": %llu, \"bases\": %llu, \"fastq\": %d, "
+            "\"n_kmers\": %llu, \"load_s\": %.3f, \"count_s\": %.3f, \"dump_s\": %.3f, \"kernel_ms\": %.3f, "
+            "\"h2d_ms\": %.3f, \"launches\": %llu, \"threads_option\": %u}\n",
+            (unsigned long long)total, (unsigned long long)hits, (unsigned long long)st.lines,
+            (unsigned long long)st.bases, st.fastq, (unsigned long long)n_kmers, t1 - t0, t2 - t1, t3 - t2, kms, hms,
+            (unsigned long long)launches, threads);
+    return 0;
+}

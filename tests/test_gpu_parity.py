@@ -1,0 +1,277 @@
+"""Parity of the CUDA count path with the reference, through the C ABI
+(include/quickmer2_b200.h + include/qk_host.h).  Bit-exact: this is integer work.
+
+Three anchors:
+  * the golden .bin/.txt written by the unmodified reference (tests/golden/),
+  * the oracle (oracle/qk_oracle.c, itself pinned in tests/test_oracle.py) on seeded inputs,
+  * size-independent properties at larger sizes (counter sum = hits, additivity, chunking
+    and tiling invariance).
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_binding
+from conftest import GOLDEN, golden_cases, golden_meta
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_bin(ctx, qm, reads=None, raw=None, seekable=True):
+    ctx.load_dictionary(qm)
+    st = ctx.count_file(reads) if reads is not None else ctx.count_raw(raw, seekable)
+    st.update(ctx.stats())
+    return ctx.finish(), st
+
+
+# ------------------------------------------------------------------ golden fixtures -------
+@pytest.mark.parametrize("case", golden_cases())
+def test_golden_bin_and_txt(case, qk, tmp_path):
+    """quicKmer2 count ref.fa reads out -> same .bin and .txt bytes as the reference wrote."""
+    meta = golden_meta(case)
+    d = GOLDEN / case
+    st = qk.count(d / "ref.fa", d / meta["reads"], tmp_path / "out")
+    assert (tmp_path / "out.bin").read_bytes() == (d / "expect.bin").read_bytes()
+    assert st["total_kmers"] == meta["total_kmers"]
+    assert st["n_kmers"] == meta["n_kmers"]
+    if meta["has_txt"]:
+        assert (tmp_path / "out.txt").read_bytes() == (d / "expect.txt").read_bytes()
+    else:
+        assert not (tmp_path / "out.txt").exists()
+    assert st["launches"] >= 1 and st["kernel_ms"] > 0
+
+
+@pytest.mark.parametrize("case", ["k30_fasta_t0", "k30_fastq_t3", "k25_fastq"])
+def test_cli_is_a_drop_in(case, qk, tmp_path):
+    """The C command prints the reference's stdout lines and writes the reference's files."""
+    meta = golden_meta(case)
+    d = GOLDEN / case
+    res = qk.run_cli(["count", "-t", "4", d / "ref.fa", d / meta["reads"], tmp_path / "cli"])
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert (tmp_path / "cli.bin").read_bytes() == (d / "expect.bin").read_bytes()
+    if meta["has_txt"]:
+        assert (tmp_path / "cli.txt").read_bytes() == (d / "expect.txt").read_bytes()
+    got = [l for l in res.stdout.splitlines() if not l.startswith("[Option]")]
+    want = meta["reference_stdout"]
+    norm = lambda l: "Counting elapse" if l.startswith("Counting elapse") else l
+    if not meta["has_txt"]:
+        want = [l if not l.startswith("GC control file") else l.replace(l.split(" ")[3], str(d / "ref.fa.qgc")) for l in want]
+    assert [norm(l) for l in got] == [norm(l) for l in want]
+    total = [l for l in got if l.startswith("Counting elapse")][0]
+    assert total.endswith(f"total {meta['total_kmers']} kmers")
+
+
+def test_cli_reads_from_a_pipe(qk, oracle, tmp_path):
+    """README.md:89-90: samtools | awk | quicKmer2 count ref /dev/fd/0 out.  On a pipe the
+    reference's fseek(0) fails and the first line is consumed (Q.c:396)."""
+    d = GOLDEN / "k30_fasta_t0"
+    data = (d / "reads.fa").read_bytes()
+    res = subprocess.run([str(qk.CLI_PATH), "count", str(d / "ref.fa"), "/dev/fd/0", str(tmp_path / "p")],
+                         input=data, capture_output=True)
+    assert res.returncode == 0, res.stdout
+    # first line is a '>' header, so losing it changes nothing
+    assert (tmp_path / "p.bin").read_bytes() == (d / "expect.bin").read_bytes()
+
+
+# ------------------------------------------------------------------ chunking / tiling ------
+@pytest.mark.parametrize("case", ["k30_fasta_t0", "k30_long_lines", "k12_fasta", "k31_fasta"])
+def test_chunk_boundaries_do_not_matter(case, qk, oracle, gpu_ctx):
+    meta = golden_meta(case)
+    d = GOLDEN / case
+    want = np.fromfile(d / "expect.bin", dtype=np.uint16)
+    framed, _ = oracle.frame_file(d / meta["reads"])
+    lines = framed.split(b"\n")[:-1]
+    gpu_ctx.load_dictionary(d / "ref.fa.qm")
+    for cap in (100000, 131071, 250000, 1 << 20):
+        gpu_ctx.reset()
+        chunk, slot = b"", 0
+        for l in lines:
+            if len(chunk) + len(l) + 1 > cap:
+                gpu_ctx.submit_chunk(chunk, slot=slot)
+                slot = (slot + 1) % gpu_ctx.n_slots
+                chunk = b""
+            chunk += l + b"\n"
+        gpu_ctx.submit_chunk(chunk, slot=slot)
+        assert np.array_equal(gpu_ctx.finish(), want), cap
+        assert gpu_ctx.stats()["total_kmers"] == meta["total_kmers"]
+
+
+@pytest.mark.parametrize("tiles", [1, 2, 3, 7, 64])
+def test_cta_span_boundaries_do_not_matter(tiles, qk, tmp_path):
+    """Long lines cross tiles and CTA spans; the carried reset position and the 32-base halo
+    must make the split invisible.  Separate process: the span length is an
+    environment knob read once."""
+    d = GOLDEN / "k30_long_lines"
+    code = (
+        "import sys; sys.path.insert(0, %r); from conftest import load_package; qk = load_package();"
+        "qk.count(%r, %r, %r)" % (str(GOLDEN.parent), str(d / "ref.fa"), str(d / "reads.fa"), str(tmp_path / "o"))
+    )
+    env = dict(os.environ, QK_TILES_PER_CTA=str(tiles))
+    res = subprocess.run(["python", "-c", code], env=env, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    assert (tmp_path / "o.bin").read_bytes() == (d / "expect.bin").read_bytes()
+
+
+def test_unaligned_tail_and_tiny_chunks(qk, oracle, gpu_ctx):
+    d = GOLDEN / "k30_fasta_t0"
+    gpu_ctx.load_dictionary(d / "ref.fa.qm")
+    framed, _ = oracle.frame_file(d / "reads.fa")
+    lines = framed.split(b"\n")[:-1]
+    gpu_ctx.reset()
+    for i, l in enumerate(lines):                       # one line per chunk, lengths 0..300
+        gpu_ctx.submit_chunk(l + b"\n", slot=i % gpu_ctx.n_slots)
+    assert np.array_equal(gpu_ctx.finish(), np.fromfile(d / "expect.bin", dtype=np.uint16))
+    gpu_ctx.reset()
+    gpu_ctx.submit_chunk(b"")                           # empty chunk is legal
+    gpu_ctx.submit_chunk(b"\n")
+    assert gpu_ctx.stats()["total_kmers"] == 0
+
+
+# ------------------------------------------------------------------ oracle, seeded inputs --
+@pytest.fixture(scope="module")
+def mid_dict(synth, tmp_path_factory):
+    """2 Mb reference with segmental duplications and an N block; dictionary by qk_synth dict."""
+    d = tmp_path_factory.mktemp("mid")
+    synth("ref", "--out", d / "ref.fa", "--bases", 2000000, "--contigs", 3, "--seed", 11, "--segdups", 10,
+          "--segdup-len", 5000, "--nblock", 3000)
+    synth("dict", "--ref", d / "ref.fa", "--k", 30, "--ctrl-block", 20000)
+    return d
+
+
+@pytest.mark.parametrize("kind", ["fasta", "fastq", "lower_crlf", "hifi"])
+def test_against_oracle_seeded(kind, mid_dict, qk, oracle, synth, tmp_path):
+    args = {
+        "fasta": ["--n", 200000, "--len", 150],
+        "fastq": ["--n", 150000, "--len", 150, "--fastq", "--rand-qual"],
+        "lower_crlf": ["--n", 50000, "--len", 101, "--lower-ppm", 300000, "--crlf"],
+        "hifi": ["--n", 300, "--len", 15000, "--hifi", "--max-len", 99998, "--err-ppm", 1000],
+    }[kind]
+    reads = tmp_path / ("reads.fq" if kind == "fastq" else "reads.fa")
+    synth("reads", "--ref", mid_dict / "ref.fa", "--out", reads, "--seed", 1234, *args)
+    ost = oracle.count(mid_dict / "ref.fa", reads, tmp_path / "want")
+    st = qk.count(mid_dict / "ref.fa", reads, tmp_path / "got")
+    assert (tmp_path / "got.bin").read_bytes() == (tmp_path / "want.bin").read_bytes()
+    assert (tmp_path / "got.txt").read_bytes() == (tmp_path / "want.txt").read_bytes()
+    for key in ("total_kmers", "hits", "lines", "bases"):
+        assert st[key] == ost[key], key
+    assert st["hits"] > 0.4 * st["total_kmers"]
+
+
+@pytest.mark.parametrize("k", [3, 5, 12, 20, 25, 29, 30, 31])
+def test_k_sweep_against_oracle(k, qk, oracle, synth, tmp_path):
+    """T2: the 60-bit reverse-complement register is independent of k."""
+    bases = 60 if k < 6 else 300000
+    synth("ref", "--out", tmp_path / "ref.fa", "--bases", bases, "--seed", 100 + k)
+    synth("dict", "--ref", tmp_path / "ref.fa", "--k", k)
+    synth("reads", "--ref", tmp_path / "ref.fa", "--out", tmp_path / "r.fa", "--n", 20000, "--len", min(150, bases - 1),
+          "--seed", k)
+    want, ost = oracle.count_bin(tmp_path / "ref.fa.qm", tmp_path / "r.fa")
+    with qk.Context(n_slots=2, chunk_capacity=1 << 20) as ctx:
+        got, st = gpu_bin(ctx, tmp_path / "ref.fa.qm", tmp_path / "r.fa")
+    assert np.array_equal(got, want)
+    assert st["total_kmers"] == ost["total_kmers"] and st["hits"] == ost["hits"]
+
+
+def test_duplicate_keys_from_index(qk, oracle, gpu_ctx, tmp_path):
+    """T14: `index` can write the same k-mer into two slots (Q.c:209-216); both are on the
+    chain, only the one Find_hash reaches first ever receives counts."""
+    rng = np.random.default_rng(5)
+    uniq = rng.integers(1, 1 << 60, size=400, dtype=np.uint64)
+    order = np.concatenate([uniq, uniq[:50], uniq[100:120]])      # 70 duplicated entries
+    rng.shuffle(order)
+    keys, nxt, first = oracle_binding.build_qm_arrays(oracle, order, 2048)
+    oracle_binding.write_qm(tmp_path / "d.qm", 30, keys, nxt, first)
+
+    def decode(key):                                               # key -> a 30-mer whose canonical key it is
+        return "".join("ACTG"[(int(key) >> (2 * (29 - i))) & 3] for i in range(30))
+    reads = "".join(f">r{i}\n{decode(kk)}\n" for i, kk in enumerate(order.tolist() * 3))
+    (tmp_path / "r.fa").write_text(reads)
+    want, ost = oracle.count_bin(tmp_path / "d.qm", tmp_path / "r.fa")
+    got, st = gpu_bin(gpu_ctx, tmp_path / "d.qm", tmp_path / "r.fa")
+    assert got.size == order.size == want.size
+    assert np.array_equal(got, want)
+    assert (want == 0).sum() >= 70                                  # the shadowed copies never count
+    assert gpu_ctx.table_desc().skipped_keys == 70
+
+
+def test_dictionary_keys_no_read_can_produce(qk, oracle, gpu_ctx, tmp_path):
+    """Keys >= 2^60 (possible with `index`, k >= 31) are on the chain but can never match:
+    the canonical key is <= the 60-bit reverse-complement register (Q.c:415-420)."""
+    order = np.array([5, (1 << 61) + 3, 77, (1 << 62) - 1, 9], dtype=np.uint64)
+    keys, nxt, first = oracle_binding.build_qm_arrays(oracle, order, 64)
+    oracle_binding.write_qm(tmp_path / "d.qm", 31, keys, nxt, first)
+    (tmp_path / "r.fa").write_text(">a\n" + "A" * 28 + "CC" + "A" + "\n")
+    want, _ = oracle.count_bin(tmp_path / "d.qm", tmp_path / "r.fa")
+    got, _ = gpu_bin(gpu_ctx, tmp_path / "d.qm", tmp_path / "r.fa")
+    assert np.array_equal(got, want) and got.size == 5
+    assert gpu_ctx.table_desc().skipped_keys == 2
+
+
+def test_corrupt_chain_is_rejected(qk, oracle, gpu_ctx):
+    order = np.arange(1, 200, dtype=np.uint64) * 7919
+    keys, nxt, first = oracle_binding.build_qm_arrays(oracle, order, 1024)
+    bad = nxt.copy()
+    occupied = np.flatnonzero(keys)
+    bad[occupied[10]] = occupied[10]                    # a self-loop: the walk never returns to first
+    with pytest.raises(qk.QkError) as e:
+        gpu_ctx.load_dictionary_arrays(30, keys, bad, first)
+    assert e.value.code == 5                            # QK_ERR_FORMAT
+    bad = nxt.copy()
+    bad[first] = np.flatnonzero(keys == 0)[0]           # chain runs into an empty slot
+    with pytest.raises(qk.QkError):
+        gpu_ctx.load_dictionary_arrays(30, keys, bad, first)
+    assert gpu_ctx.load_dictionary_arrays(30, keys, nxt, first) == order.size   # and the intact one loads
+
+
+# ------------------------------------------------------------------ properties at size -----
+def test_properties_at_size(qk, synth, tmp_path):
+    """16 Mb dictionary, 2 M reads (~240 M k-mers): too slow for the oracle in a unit test, so
+    check what must hold at any size."""
+    synth("ref", "--out", tmp_path / "ref.fa", "--bases", 16000000, "--contigs", 4, "--seed", 2024, "--segdups", 50,
+          "--segdup-len", 20000, "--nblock", 50000)
+    synth("dict", "--ref", tmp_path / "ref.fa", "--k", 30)
+    synth("reads", "--ref", tmp_path / "ref.fa", "--out", tmp_path / "a.fa", "--n", 1000000, "--len", 150, "--seed", 1)
+    synth("reads", "--ref", tmp_path / "ref.fa", "--out", tmp_path / "b.fq", "--n", 1000000, "--len", 150, "--seed", 2,
+          "--fastq")
+    with qk.Context(n_slots=4, chunk_capacity=16 << 20) as ctx:
+        n = ctx.load_dictionary(tmp_path / "ref.fa.qm")
+        p, n2 = ctx.counters_device_ptr()
+        assert n2 == n
+        sa = ctx.count_file(tmp_path / "a.fa"); sa.update(ctx.stats())
+        a32 = ctx.counters().astype(np.int64)
+        assert int(a32.sum()) == sa["hits"]                          # every hit lands on exactly one counter
+        assert sa["total_kmers"] == 1000000 * 121                    # N-free 150 bp reads, k=30
+        a = ctx.finish()
+        assert np.array_equal(a, (a32 & 0xFFFF).astype(np.uint16))
+        ctx.count_file(tmp_path / "b.fq")                            # additivity: counters accumulate
+        ab = ctx.finish().astype(np.int64)
+        ctx.reset()
+        sb = ctx.count_file(tmp_path / "b.fq"); sb.update(ctx.stats())
+        b = ctx.finish().astype(np.int64)
+        assert np.array_equal(ab, a.astype(np.int64) + b)
+        assert sb["fastq"] == 1 and sb["total_kmers"] == 1000000 * 121
+        # depth ~ 2 * 150 bp * 1 M / 16 Mb ~ 18x on unique sequence
+        assert 10 < ab[ab > 0].mean() < 25
+    with qk.Context(n_slots=2, chunk_capacity=1 << 20) as ctx2:      # other chunking, same answer
+        ctx2.load_dictionary(tmp_path / "ref.fa.qm")
+        ctx2.count_file(tmp_path / "b.fq")
+        assert np.array_equal(ctx2.finish().astype(np.int64), b)
+
+
+def test_depth_wraps_like_uint16(qk, oracle, gpu_ctx, tmp_path):
+    """T12: one 30-mer seen 70,000 times reads 70,000 mod 65,536 = 4,464 (no saturation)."""
+    kmer = "ACGTTGCATGCCGATAGGCTAACGTTAGCC"
+    order = np.array(oracle.chunk_keys(30, kmer.encode() + b"\n"), dtype=np.uint64)
+    keys, nxt, first = oracle_binding.build_qm_arrays(oracle, order, 16)
+    oracle_binding.write_qm(tmp_path / "d.qm", 30, keys, nxt, first)
+    (tmp_path / "r.fa").write_text((kmer + "\n") * 70000)
+    got, st = gpu_bin(gpu_ctx, tmp_path / "d.qm", tmp_path / "r.fa")
+    assert got.tolist() == [4464] and st["hits"] == 70000
+
+
+def test_roofline_microbenchmarks_run(qk, gpu_ctx):
+    g = gpu_ctx.bench_gather(1 << 30, gran=32, loads_in_flight=4, n_gathers=1 << 26)
+    h = gpu_ctx.bench_h2d(8 << 20, repeats=8)
+    assert 50 < g < 8000 and 1 < h < 200

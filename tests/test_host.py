@@ -1,0 +1,206 @@
+"""Host-side C code (no GPU needed): the C-ABI library loads and exports every symbol the
+headers declare, the record framer reproduces the reference's fgets loop (Q.c:393-398,
+451-455), the QM11 header reader and the .bin/.txt writers produce the reference's bytes."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, golden_cases, golden_meta
+
+
+def declared_symbols():
+    names = set()
+    for h in (ROOT / "include").glob("*.h"):
+        text = re.sub(r"/\*.*?\*/", "", h.read_text(), flags=re.S)
+        names |= set(re.findall(r"\b(qk_[a-z0-9_]+)\s*\(", text))
+    return names
+
+
+def test_library_exports_every_declared_symbol(qk):
+    lib = qk.lib()
+    declared = declared_symbols()
+    assert len(declared) >= 35
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/*.h but not exported"
+    # and the ctypes table of the Python face covers them all
+    assert declared <= set(qk.SIGNATURES), declared - set(qk.SIGNATURES)
+    out = subprocess.run(["nm", "-D", "--defined-only", str(qk.LIB_PATH)], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (qk_\w+)", out))
+    assert declared <= exported
+
+
+def test_library_is_sm100a_only(qk):
+    out = subprocess.run(["cuobjdump", "-lelf", str(qk.LIB_PATH)], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_no_cpu_fallback_without_a_device(qk):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    assert qk.lib().qk_device_count() <= 0
+    with pytest.raises(qk.QkError) as e:
+        qk.Context()
+    assert e.value.code == 1  # QK_ERR_CUDA
+
+
+def test_product_does_not_reference_the_oracle():
+    """The oracle is the checker: nothing under the package may import, link or run it."""
+    for p in (ROOT / "quick-mer2_b200").rglob("*"):
+        if p.is_file() and p.suffix in {".py", ".c", ".cu", ".cuh", ".h", ""} and "build" not in p.parts \
+                and "bin" not in p.parts and p.name != "Makefile":
+            assert "oracle" not in p.read_text(errors="ignore").lower(), p
+    assert "oracle" not in (ROOT / "quick-mer2_b200" / "Makefile").read_text().lower()
+    out = subprocess.run(["ldd", str(ROOT / "quick-mer2_b200" / "libquickmer2_b200.so")], capture_output=True, text=True).stdout
+    assert "oracle" not in out
+
+
+# ---------------------------------------------------------------------------- framer -----
+@pytest.mark.parametrize("case", golden_cases())
+@pytest.mark.parametrize("cap", [100000, 1 << 20])
+def test_framer_matches_oracle_on_golden_reads(case, cap, qk, oracle):
+    meta = golden_meta(case)
+    path = GOLDEN / case / meta["reads"]
+    want, ost = oracle.frame_file(path)
+    chunks, st = qk.frame(path.read_bytes(), seekable=True, chunk_capacity=cap)
+    assert b"".join(chunks) == want
+    assert all(c.endswith(b"\n") and len(c) <= cap for c in chunks)
+    assert st["lines"] == ost["lines"] and st["bases"] == ost["bases"] and st["fastq"] == ost["fastq"]
+    assert st["raw_bytes"] == path.stat().st_size
+
+
+def frame_all(qk, data, **kw):
+    chunks, st = qk.frame(data, **kw)
+    return b"".join(chunks), st
+
+
+def test_framer_fasta_rules(qk):
+    data = b">r1 desc\nACGT\nGGCC\n>r2\n\nTTTT\n>\n"
+    out, st = frame_all(qk, data)
+    # '>' lines skipped, every other line (also the empty one) is an independent read (T10)
+    assert out == b"ACGT\nGGCC\n\nTTTT\n"
+    assert st["lines"] == 4 and st["bases"] == 12 and st["fastq"] == 0
+
+
+def test_framer_fastq_rules(qk):
+    # quality lines starting with '>' or '@' are skipped by position, not by content (Q.c:451-455)
+    data = b"@r1\nACGT\n+\n>III\n@r2\nGGNC\n+r2\n@@@@\n"
+    out, st = frame_all(qk, data)
+    assert out == b"ACGT\nGGNC\n"
+    assert st["fastq"] == 1 and st["lines"] == 2
+    # a '>' line where a read is expected is skipped WITHOUT consuming the 3 trailing lines (Q.c:398)
+    data = b"@r1\n>odd\nACGT\n+\nIIII\n@r2\nTTTT\n+\nIIII\n"
+    out, _ = frame_all(qk, data)
+    assert out == b"ACGT\nTTTT\n"
+
+
+def test_framer_pipe_loses_first_line(qk, oracle, tmp_path):
+    data = b"ACGTACGT\n>h\nGGGG\n"
+    assert frame_all(qk, data, seekable=True)[0] == b"ACGTACGT\nGGGG\n"
+    assert frame_all(qk, data, seekable=False)[0] == b"GGGG\n"          # Q.c:396: fseek fails on a pipe
+    fq = b"@h\nACGT\n+\nIIII\n"
+    assert frame_all(qk, fq, seekable=False)[0] == b"ACGT\n"            # FASTQ never rewinds
+    # through a real pipe with the C entry point
+    r, w = os.pipe()
+    os.write(w, data)
+    os.close(w)
+    L = qk.lib()
+    fr = L.qk_framer_open_fd(r, 0)
+    dst = np.empty(100000, dtype=np.uint8)
+    n, nl = C.c_size_t(), C.c_uint32()
+    assert L.qk_framer_next(fr, dst.ctypes.data, dst.size, C.byref(n), None, 0, C.byref(nl)) == 1
+    assert dst[: n.value].tobytes() == b"GGGG\n" and nl.value == 1
+    assert L.qk_framer_next(fr, dst.ctypes.data, dst.size, C.byref(n), None, 0, C.byref(nl)) == 0
+    L.qk_framer_close(fr)
+
+
+def test_framer_edge_inputs(qk):
+    assert frame_all(qk, b"")[0] == b""
+    assert frame_all(qk, b"\n")[0] == b"\n"
+    out, st = frame_all(qk, b">h\nACGT")                 # T9: unterminated last line gets a '\n'
+    assert out == b"ACGT\n" and st["unterminated"] == 1
+    out, st = frame_all(qk, b"ACGT\r\nGG\r\n")           # T6: '\r' stays in the line (a base for the codec)
+    assert out == b"ACGT\r\nGG\r\n" and st["bases"] == 8
+    big = b"A" * 99998 + b"\n"                           # T8: the longest line the reference reads whole
+    out, st = frame_all(qk, b">h\n" + big + b"CC\n", chunk_capacity=100000)
+    assert out == big + b"CC\n" and st["long_lines"] == 0
+    chunks, _ = qk.frame(b">h\n" + big + b"CC\n", chunk_capacity=100000)
+    assert chunks == [big, b"CC\n"]                      # chunk boundaries fall between lines
+
+
+def test_framer_offsets(qk):
+    data = b">a\nACGT\nGG\n\nTTTTT\n"
+    chunks, offsets, st = qk.frame(data, with_offsets=True)
+    assert chunks == [b"ACGT\nGG\n\nTTTTT\n"]
+    assert offsets[0].tolist() == [0, 5, 8, 9, 15]
+
+
+def test_framer_streams_a_file_larger_than_its_window(qk, oracle, synth, tmp_path):
+    synth("ref", "--out", tmp_path / "ref.fa", "--bases", 300000, "--seed", 3)
+    synth("reads", "--ref", tmp_path / "ref.fa", "--out", tmp_path / "r.fq", "--n", 60000, "--len", 150, "--seed", 9,
+          "--fastq", "--rand-qual")                       # ~19 MB > the 8 MiB read window
+    want, ost = oracle.frame_file(tmp_path / "r.fq")
+    L = qk.lib()
+    fr = L.qk_framer_open(os.fsencode(str(tmp_path / "r.fq")))
+    assert fr
+    dst = np.empty(1 << 20, dtype=np.uint8)
+    n, nl = C.c_size_t(), C.c_uint32()
+    got, lines = [], 0
+    while L.qk_framer_next(fr, dst.ctypes.data, dst.size, C.byref(n), None, 0, C.byref(nl)) == 1:
+        got.append(dst[: n.value].tobytes())
+        lines += nl.value
+    st = qk.FramerStats()
+    L.qk_framer_get_stats(fr, C.byref(st))
+    L.qk_framer_close(fr)
+    assert b"".join(got) == want
+    assert lines == ost["lines"] == 60000 == st.lines
+    assert L.qk_framer_open(b"/nonexistent/reads.fa") is None
+
+
+# ---------------------------------------------------------------------------- files ------
+def test_qm_header(qk):
+    hdr = qk.QmHeader()
+    assert qk.lib().qk_qm_read_header(os.fsencode(str(GOLDEN / "k30_fasta_t0" / "ref.fa.qm")), C.byref(hdr)) == 0
+    assert (hdr.k, hdr.hash_size, hdr.first_idx) == (30, 0x4000, 0x3A61)   # meta.json: reference stdout
+    assert qk.lib().qk_qm_read_header(b"/nonexistent.qm", C.byref(hdr)) == 6
+
+
+@pytest.mark.parametrize("case", [c for c in golden_cases() if golden_meta(c)["has_txt"]])
+def test_gc_txt_writer_matches_reference(case, qk, tmp_path):
+    """.txt from (.bin, .qgc) with the sums done in numpy: the formatting and the
+    mean/variance arithmetic of Q.c:529-538 are the host's."""
+    d = GOLDEN / case
+    depth = np.fromfile(d / "expect.bin", dtype=np.uint16).astype(np.int64)
+    qgc = np.fromfile(d / "ref.fa.qgc", dtype=np.uint16)
+    ctrl = (qgc & 0x8000) != 0
+    bins = (qgc & 0x1FF).astype(np.int64)
+    s = np.bincount(bins[ctrl], weights=depth[ctrl], minlength=401).astype(np.uint64)
+    q = np.bincount(bins[ctrl], weights=depth[ctrl] ** 2, minlength=401).astype(np.int64)
+    c = np.bincount(bins[ctrl], minlength=401).astype(np.uint64)
+    mean = qk.write_gc_txt(tmp_path / "o.txt", s, q, c)
+    assert (tmp_path / "o.txt").read_bytes() == (d / "expect.txt").read_bytes()
+    line = [l for l in golden_meta(case)["reference_stdout"] if l.startswith("Mean sequencing depth")][0]
+    assert line == f"Mean sequencing depth: {mean:.2f}"
+
+
+def test_bin_writer(qk, tmp_path):
+    a = np.arange(70000, dtype=np.uint32).astype(np.uint16)
+    assert qk.lib().qk_write_bin(os.fsencode(str(tmp_path / "a.bin")), a.ctypes.data, a.size) == 0
+    assert (tmp_path / "a.bin").read_bytes() == a.astype("<u2").tobytes()
+    assert qk.lib().qk_write_bin(b"/nonexistent/dir/a.bin", a.ctypes.data, a.size) == 6
+
+
+def test_cli_usage_and_missing_inputs(qk, tmp_path):
+    res = qk.run_cli(["count"])
+    assert res.returncode == 1 and "quicKmer2 count [Options] ref.fa sample.fast[a/q] Out_prefix" in res.stdout
+    res = qk.run_cli(["count", "-h"])
+    assert res.returncode == 1
+    res = qk.run_cli(["count", tmp_path / "missing", tmp_path / "r.fa", tmp_path / "o"])
+    assert res.returncode == 1 and "open fail" in res.stdout       # the reference segfaults here (Q.c:345)
+    res = qk.run_cli(["est"])
+    assert res.returncode == 1

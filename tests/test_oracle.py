@@ -1,0 +1,118 @@
+"""Pin the oracle (oracle/qk_oracle.c) against the reference.
+
+The reference ships no tests or golden vectors for `count`.  The fixtures
+under tests/golden/ were produced by the UNMODIFIED reference compiled from
+/root/reference/QuicKmer.c (tests/golden/make_golden.py); the oracle must reproduce every
+one of them byte for byte.  Where the compiled reference is present (oracle/_ref/quicKmer2:
+the authoring container, and the GPU box because the binary travels with the snapshot) the
+oracle is also checked against live runs on fresh seeded inputs.
+"""
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_cases, golden_meta
+
+
+@pytest.mark.parametrize("case", golden_cases())
+def test_oracle_matches_reference_golden(case, oracle, tmp_path):
+    meta = golden_meta(case)
+    d = GOLDEN / case
+    st = oracle.count(d / "ref.fa", d / meta["reads"], tmp_path / "out")
+    assert (tmp_path / "out.bin").read_bytes() == (d / "expect.bin").read_bytes()
+    assert st["total_kmers"] == meta["total_kmers"]          # Q.c:481 "total %lu kmers"
+    assert st["fastq"] == int(meta["fastq"])
+    assert st["undefined_lines"] == 0                        # fixtures stay inside defined behaviour
+    if meta["has_txt"]:
+        assert (tmp_path / "out.txt").read_bytes() == (d / "expect.txt").read_bytes()
+    else:
+        assert not (tmp_path / "out.txt").exists()
+
+
+def test_golden_cover_the_known_answer_matrix():
+    """k sweep, FASTA+FASTQ, threaded+unthreaded, long lines, counter wrap."""
+    metas = [golden_meta(c) for c in golden_cases()]
+    assert {m["k"] for m in metas} >= {3, 12, 20, 25, 30, 31}
+    assert any(m["fastq"] for m in metas) and any(not m["fastq"] for m in metas)
+    assert any(m["threads"] for m in metas) and any(not m["threads"] for m in metas)
+    assert any(m["has_txt"] for m in metas)
+    wrap = np.fromfile(GOLDEN / "k30_wrap_t2" / "expect.bin", dtype=np.uint16)
+    reads = (GOLDEN / "k30_wrap_t2" / "reads.fa").read_text()
+    # T12: (AC)^49999 twice = 2 * 49,985 windows of (AC)^15 or (CA)^15 >= 65,536 hits on one
+    # dictionary k-mer, so its depth must have wrapped; no entry may read 65,535 (no saturation)
+    assert reads.count("AC" * 49999) == 2
+    assert wrap.max() < 65535
+    long_reads = [len(l) for l in (GOLDEN / "k30_long_lines" / "reads.fa").read_text().split("\n")]
+    assert {65535, 65536, 70000, 99998} <= set(long_reads)   # T7/T8
+
+
+def test_djb_known_values(oracle):
+    # Q.c:66-76: h = 5381; h = h*33 + byte, 8 bytes LSB first, u64 wrap
+    def djb(key):
+        h = 5381
+        for b in range(8):
+            h = (h * 33 + ((key >> (8 * b)) & 0xFF)) & 0xFFFFFFFFFFFFFFFF
+        return h
+    for key in (0, 1, 0xFF, 0x0123456789ABCDEF, (1 << 60) - 1, 0xFFFFFFFFFFFFFFFF):
+        assert oracle.djb(key) == djb(key)
+
+
+def py_codec(k, line: bytes):
+    """Literal transcription of SURVEY.md Appendix A process(line) -- a third, independent statement."""
+    mask = (1 << (2 * k)) - 1 if k < 32 else 0
+    fwd = rc = cur = 0
+    out = []
+    for c in line:
+        if c == 0x4E:
+            fwd = rc = cur = 0
+            continue
+        cur = (cur + 1) & 0xFFFF
+        L = (c >> 1) & 3
+        fwd = ((fwd << 2) | L) & 0xFFFFFFFFFFFFFFFF
+        rc = (rc | (((L - 2) & 3) << 60)) >> 2
+        if cur >= k:
+            key = fwd & mask
+            out.append(min(key, rc))
+    return out
+
+
+@pytest.mark.parametrize("k", [3, 12, 20, 25, 30, 31, 32])
+def test_codec_restatement(k, oracle):
+    rng = np.random.default_rng(k)
+    lines = [bytes(rng.choice(np.frombuffer(b"ACGTacgtNn\r-", dtype=np.uint8), size=int(n)))
+             for n in (0, 1, k - 1, k, k + 1, 64, 150, 151, 1000)]
+    chunk = b"".join(l + b"\n" for l in lines)
+    want = [key for l in lines for key in py_codec(k, l)]
+    got = oracle.chunk_keys(k, chunk)
+    assert got.tolist() == want
+
+
+def test_run_counter_wraps_at_65536(oracle):
+    # T7: after 65,536 non-N bytes cur_chars is 0 and the next k-1 positions emit nothing
+    k = 30
+    line = b"ACGT" * 17000  # 68,000 bases
+    got = oracle.chunk_keys(k, line + b"\n").size
+    assert got == (65535 - k + 1) + (68000 - 65536 - k + 1)
+
+
+def test_oracle_against_live_reference(oracle, ref_binary, synth, tmp_path):
+    if ref_binary is None:
+        pytest.skip("oracle/_ref/quicKmer2 not built here")
+    synth("ref", "--out", tmp_path / "ref.fa", "--bases", 200000, "--contigs", 3, "--seed", 77, "--segdups", 4,
+          "--segdup-len", 3000, "--nblock", 500)
+    synth("ctrl", "--ref", tmp_path / "ref.fa", "--out", tmp_path / "ctrl.bed", "--block", 5000)
+    res = subprocess.run([str(ref_binary), "search", "-k", "30", "-e", "0", "-s", "1M", "-c", "ctrl.bed", "ref.fa"],
+                         cwd=tmp_path, capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    for name, extra in (("reads.fq", ["--fastq", "--rand-qual"]), ("reads.fa", ["--lower-ppm", 100000])):
+        synth("reads", "--ref", tmp_path / "ref.fa", "--out", tmp_path / name, "--n", 20000, "--len", 150, "--seed", 5,
+              *extra)
+        res = subprocess.run([str(ref_binary), "count", "-t", "3", "ref.fa", name, "live"], cwd=tmp_path,
+                             capture_output=True, text=True)
+        assert res.returncode == 0, res.stdout + res.stderr
+        st = oracle.count(tmp_path / "ref.fa", tmp_path / name, tmp_path / "port")
+        assert (tmp_path / "port.bin").read_bytes() == (tmp_path / "live.bin").read_bytes()
+        assert (tmp_path / "port.txt").read_bytes() == (tmp_path / "live.txt").read_bytes()
+        assert f"total {st['total_kmers']} kmers" in res.stdout
+        assert st["hits"] > 0.5 * st["total_kmers"]
