@@ -242,7 +242,7 @@ def test_properties_at_size(qk, synth, tmp_path):
         sa = ctx.count_file(tmp_path / "a.fa"); sa.update(ctx.stats())
         a32 = ctx.counters().astype(np.int64)
         assert int(a32.sum()) == sa["hits"]                          # every hit lands on exactly one counter
-        assert sa["total_kmers"] == 1000000 * 121                    # N-free 150 bp reads, k=30
+        assert 0.99 * 121e6 < sa["total_kmers"] <= 1000000 * 121     # 150 bp reads, k=30; a few reads cross the N block
         a = ctx.finish()
         assert np.array_equal(a, (a32 & 0xFFFF).astype(np.uint16))
         ctx.count_file(tmp_path / "b.fq")                            # additivity: counters accumulate
@@ -251,7 +251,7 @@ def test_properties_at_size(qk, synth, tmp_path):
         sb = ctx.count_file(tmp_path / "b.fq"); sb.update(ctx.stats())
         b = ctx.finish().astype(np.int64)
         assert np.array_equal(ab, a.astype(np.int64) + b)
-        assert sb["fastq"] == 1 and sb["total_kmers"] == 1000000 * 121
+        assert sb["fastq"] == 1 and 0.99 * 121e6 < sb["total_kmers"] <= 1000000 * 121
         # depth ~ 2 * 150 bp * 1 M / 16 Mb ~ 18x on unique sequence
         assert 10 < ab[ab > 0].mean() < 25
     with qk.Context(n_slots=2, chunk_capacity=1 << 20) as ctx2:      # other chunking, same answer
