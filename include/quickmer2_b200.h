@@ -149,7 +149,7 @@ int qk_timing(qk_ctx *ctx, double *kernel_ms, double *h2d_ms, uint64_t *launches
 int qk_span_begin(qk_ctx *ctx);
 int qk_span_end(qk_ctx *ctx, double *elapsed_ms);
 /* Micro-benchmarks for the roofline denominators: random `gran`-byte
- * (32 or 64) gathers over a `table_bytes` region with `loads_in_flight` independent loads
+ * (32, 64 or 128) gathers over a `table_bytes` region with `loads_in_flight` independent loads
  * per thread; and pinned host -> device copy.  Both return GB/s. */
 int qk_bench_gather(qk_ctx *ctx, uint64_t table_bytes, uint32_t gran, uint32_t loads_in_flight,
                     uint64_t n_gathers, double *gbs);

@@ -75,6 +75,7 @@ struct qk_ctx {
     double kernel_ms, h2d_ms;
     uint64_t launches;
     cudaEvent_t span_a, span_b, span_join;
+    uint16_t *narrow_dev, *narrow_host; // qk_finish staging (device / pinned), allocated on first use
 };
 
 int qk_fail(qk_ctx *ctx, int code, const char *fmt, ...);

@@ -27,6 +27,7 @@
 #include <limits.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "qk_common.cuh"
 
@@ -385,6 +386,10 @@ __global__ void qk_narrow_kernel(const uint32_t *__restrict__ counters, uint16_t
         out[i] = (uint16_t)(counters[i] & 0xFFFFu);
 }
 
+// D2H of the depths.  Pageable destinations go through two pinned staging buffers so the PCIe
+// copy of piece i+1 overlaps the host memcpy of piece i (a direct pageable cudaMemcpy runs at a
+// few GB/s); a destination that is already pinned is written directly.
+#define QK_FINISH_PIECE ((uint64_t)4 << 20) // entries per staged piece (8 MiB)
 extern "C" int qk_finish(qk_ctx *ctx, uint16_t *counts_out, uint64_t n_kmers)
 {
     if (!ctx || !counts_out) return QK_ERR_ARG;
@@ -393,16 +398,39 @@ extern "C" int qk_finish(qk_ctx *ctx, uint16_t *counts_out, uint64_t n_kmers)
     int rc = qk_sync(ctx);
     if (rc) return rc;
     QK_CUDA(ctx, cudaSetDevice(ctx->device));
-    const uint64_t piece = (uint64_t)64 << 20; // entries per pass
-    uint16_t *tmp = NULL;
-    QK_CUDA(ctx, cudaMalloc((void **)&tmp, (n_kmers < piece ? n_kmers : piece) * sizeof(uint16_t)));
-    for (uint64_t at = 0; at < n_kmers; at += piece) {
-        const uint64_t m = n_kmers - at < piece ? n_kmers - at : piece;
-        qk_narrow_kernel<<<ctx->sm_count * 8, 256>>>(ctx->counters + at, tmp, m);
-        cudaError_t e = cudaMemcpy(counts_out + at, tmp, m * sizeof(uint16_t), cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) { cudaFree(tmp); return qk_cuda_fail(ctx, e, "D2H of counts"); }
+    cudaStream_t st = ctx->slots[0].stream;
+    cudaPointerAttributes attr;
+    bool pinned = cudaPointerGetAttributes(&attr, counts_out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (!ctx->narrow_dev) QK_CUDA(ctx, cudaMalloc((void **)&ctx->narrow_dev, 2 * QK_FINISH_PIECE * sizeof(uint16_t)));
+    if (!pinned && !ctx->narrow_host)
+        QK_CUDA(ctx, cudaHostAlloc((void **)&ctx->narrow_host, 2 * QK_FINISH_PIECE * sizeof(uint16_t), cudaHostAllocDefault));
+    cudaEvent_t done[2];
+    QK_CUDA(ctx, cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming));
+    QK_CUDA(ctx, cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
+    cudaError_t e = cudaSuccess;
+    uint64_t prev_at = 0, prev_m = 0;
+    int b = 0;
+    for (uint64_t at = 0; at < n_kmers && e == cudaSuccess; at += QK_FINISH_PIECE, b ^= 1) {
+        const uint64_t m = n_kmers - at < QK_FINISH_PIECE ? n_kmers - at : QK_FINISH_PIECE;
+        uint16_t *dev = ctx->narrow_dev + (uint64_t)b * QK_FINISH_PIECE;
+        qk_narrow_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->counters + at, dev, m);
+        uint16_t *dst = pinned ? counts_out + at : ctx->narrow_host + (uint64_t)b * QK_FINISH_PIECE;
+        e = cudaMemcpyAsync(dst, dev, m * sizeof(uint16_t), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaEventRecord(done[b], st);
+        if (!pinned && prev_m && e == cudaSuccess) { // drain the other buffer while this piece is in flight
+            e = cudaEventSynchronize(done[b ^ 1]);
+            memcpy(counts_out + prev_at, ctx->narrow_host + (uint64_t)(b ^ 1) * QK_FINISH_PIECE, prev_m * sizeof(uint16_t));
+        }
+        prev_at = at;
+        prev_m = m;
     }
-    cudaFree(tmp);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (!pinned && prev_m && e == cudaSuccess)
+        memcpy(counts_out + prev_at, ctx->narrow_host + (uint64_t)(b ^ 1) * QK_FINISH_PIECE, prev_m * sizeof(uint16_t));
+    cudaEventDestroy(done[0]);
+    cudaEventDestroy(done[1]);
+    if (e != cudaSuccess) return qk_cuda_fail(ctx, e, "D2H of counts");
     return QK_OK;
 }
 

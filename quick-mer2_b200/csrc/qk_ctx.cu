@@ -63,6 +63,14 @@ extern "C" int qk_ctx_create(qk_ctx **out, int device, uint32_t n_slots, size_t 
     *out = ctx; // returned even on failure below so the caller can read the message
     QK_CUDA(ctx, cudaSetDevice(device));
     QK_CUDA(ctx, cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
+    {   // The probe reads one random 32-byte sector per k-mer; ask L2 not to widen the DRAM fetch
+        // beyond what QK_L2_FETCH_GRANULARITY (32/64/128, default 32; 0 = leave the driver default) says.  A hint: see DESIGN.md.
+        const char *e = getenv("QK_L2_FETCH_GRANULARITY");
+        size_t g = e ? (size_t)atoi(e) : 32;
+        if (g == 32 || g == 64 || g == 128) {
+            if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, g) != cudaSuccess) cudaGetLastError();
+        }
+    }
     for (uint32_t s = 0; s < n_slots; ++s) {
         qk_slot *sl = &ctx->slots[s];
         QK_CUDA(ctx, cudaHostAlloc((void **)&sl->host, ctx->chunk_capacity, cudaHostAllocDefault));
@@ -108,6 +116,8 @@ extern "C" void qk_ctx_destroy(qk_ctx *ctx)
     cudaFree(ctx->stash);
     cudaFree(ctx->counters);
     cudaFree(ctx->stats);
+    cudaFree(ctx->narrow_dev);
+    if (ctx->narrow_host) cudaFreeHost(ctx->narrow_host);
     cudaGetLastError();
     free(ctx);
 }
@@ -292,7 +302,7 @@ static int qk_gather_dispatch(int mlp, dim3 grid, cudaStream_t st, const qk_buck
 extern "C" int qk_bench_gather(qk_ctx *ctx, uint64_t table_bytes, uint32_t gran, uint32_t loads_in_flight,
                                uint64_t n_gathers, double *gbs)
 {
-    if (!ctx || !gbs || (gran != 32 && gran != 64) || table_bytes < (1u << 20)) return QK_ERR_ARG;
+    if (!ctx || !gbs || (gran != 32 && gran != 64 && gran != 128) || table_bytes < (1u << 20)) return QK_ERR_ARG;
     QK_CUDA(ctx, cudaSetDevice(ctx->device));
     qk_bucket *table = NULL;
     QK_CUDA(ctx, cudaMalloc((void **)&table, table_bytes));
@@ -311,7 +321,8 @@ extern "C" int qk_bench_gather(qk_ctx *ctx, uint64_t table_bytes, uint32_t gran,
     for (int rep = 0; rep < 4; ++rep) { // first repetition is the warm-up
         QK_CUDA(ctx, cudaEventRecord(a, st));
         if (gran == 32) qk_gather_dispatch<32>(mlp, dim3(blocks), st, table, units, per, ctx->stats + 3);
-        else qk_gather_dispatch<64>(mlp, dim3(blocks), st, table, units, per, ctx->stats + 3);
+        else if (gran == 64) qk_gather_dispatch<64>(mlp, dim3(blocks), st, table, units, per, ctx->stats + 3);
+        else qk_gather_dispatch<128>(mlp, dim3(blocks), st, table, units, per, ctx->stats + 3);
         QK_CUDA(ctx, cudaEventRecord(b, st));
         QK_CUDA(ctx, cudaEventSynchronize(b));
         QK_CUDA(ctx, cudaGetLastError());
