@@ -81,6 +81,13 @@ int qk_write_gc_txt(const char *path, const uint64_t sum[QK_GC_BINS], const int6
 int qk_count_file(qk_ctx *ctx, const char *reads_path, qk_framer_stats *st);
 int qk_count_framer(qk_ctx *ctx, qk_framer *f, qk_framer_stats *st);
 
+/* Same result with the framing done on the device (qk_raw_begin / qk_submit_raw): the host
+ * only cuts the stream at line ends.  `data` may be pinned (then chunks are DMA'd straight
+ * from it) or pageable (then they pass through the slots' pinned buffers). */
+int qk_count_raw_mem(qk_ctx *ctx, const uint8_t *data, size_t n, int seekable, qk_framer_stats *st);
+int qk_count_raw_fd(qk_ctx *ctx, int fd, int seekable, qk_framer_stats *st); /* does not close fd */
+int qk_count_raw_file(qk_ctx *ctx, const char *reads_path, qk_framer_stats *st);
+
 /* ---- the command: main_count, Q.c:304-545 -----------------------------------------------
  * quicKmer2 count [-h] [-t N] [-g device] ref_prefix reads out_prefix
  * Same positional-from-the-end convention, same stdout lines, same files. */

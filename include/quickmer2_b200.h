@@ -111,6 +111,20 @@ int qk_submit(qk_ctx *ctx, uint32_t slot, const uint8_t *bytes, size_t n_bytes,
               const uint32_t *line_off, uint32_t n_lines);
 /* Same, for a chunk already resident in device memory (16-byte aligned). */
 int qk_submit_device(qk_ctx *ctx, uint32_t slot, const uint8_t *dev_bytes, size_t n_bytes);
+/* Raw streams: the record framing of Q.c:393-398,451-455 done ON THE DEVICE.  qk_raw_begin
+ * starts a stream: `fastq` = its first byte is '@' (Q.c:395); `skip_first_line` = the first line
+ * is consumed without being examined (always for FASTQ, and for FASTA on a pipe where the
+ * reference's fseek fails, Q.c:396).  qk_submit_raw then takes consecutive pieces of the
+ * stream, each made of WHOLE lines (last byte '\n') of any kind -- headers, reads, '+',
+ * qualities; H2D copy, framing passes and the count kernel are enqueued on the slot's stream
+ * and the call returns at once.  Pieces must be submitted in stream order; the line-phase
+ * state is carried from piece to piece on the device. */
+int qk_raw_begin(qk_ctx *ctx, int fastq, int skip_first_line);
+int qk_submit_raw(qk_ctx *ctx, uint32_t slot, const uint8_t *bytes, size_t n_bytes);
+/* Totals of the raw stream so far (syncs): sequence lines, their bases, all lines seen. */
+int qk_raw_stats(qk_ctx *ctx, uint64_t *read_lines, uint64_t *bases, uint64_t *raw_lines);
+/* 1 if `p` is page-locked host memory known to CUDA (async copies from it are true DMA). */
+int qk_host_is_pinned(const void *p);
 /* Block until the host buffer last submitted on `slot` may be overwritten. */
 int qk_wait_slot(qk_ctx *ctx, uint32_t slot);
 /* Block until every enqueued chunk has been counted. */

@@ -101,6 +101,10 @@ SIGNATURES = {
     "qk_slot_host_buffer": (_P, [_P, C.c_uint32]),
     "qk_submit": (C.c_int, [_P, C.c_uint32, _P, C.c_size_t, _P, C.c_uint32]),
     "qk_submit_device": (C.c_int, [_P, C.c_uint32, _P, C.c_size_t]),
+    "qk_raw_begin": (C.c_int, [_P, C.c_int, C.c_int]),
+    "qk_submit_raw": (C.c_int, [_P, C.c_uint32, _P, C.c_size_t]),
+    "qk_raw_stats": (C.c_int, [_P, _U64P, _U64P, _U64P]),
+    "qk_host_is_pinned": (C.c_int, [_P]),
     "qk_wait_slot": (C.c_int, [_P, C.c_uint32]),
     "qk_sync": (C.c_int, [_P]),
     "qk_stats": (C.c_int, [_P, _U64P, _U64P, _U64P]),
@@ -127,6 +131,9 @@ SIGNATURES = {
     "qk_write_gc_txt": (C.c_int, [C.c_char_p, _P, _P, _P, C.POINTER(C.c_double)]),
     "qk_count_file": (C.c_int, [_P, C.c_char_p, C.POINTER(FramerStats)]),
     "qk_count_framer": (C.c_int, [_P, _P, C.POINTER(FramerStats)]),
+    "qk_count_raw_mem": (C.c_int, [_P, _P, C.c_size_t, C.c_int, C.POINTER(FramerStats)]),
+    "qk_count_raw_fd": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(FramerStats)]),
+    "qk_count_raw_file": (C.c_int, [_P, C.c_char_p, C.POINTER(FramerStats)]),
     "qk_count_main": (C.c_int, [C.c_int, C.POINTER(C.c_char_p)]),
 }
 
@@ -254,25 +261,21 @@ class Context:
         return out
 
     # -- counting -------------------------------------------------------------------------
-    def count_file(self, reads_path) -> dict:
-        """Frame a FASTA/FASTQ file on the host and count it (Q.c:393-479)."""
+    def count_file(self, reads_path, host_framer: bool = False) -> dict:
+        """Count a FASTA/FASTQ file (Q.c:393-479).  Default: raw pieces cut at line ends go to
+        the device, which frames them; host_framer=True frames on the host instead."""
         st = FramerStats()
-        rc = self._lib.qk_count_file(self._h, os.fsencode(str(reads_path)), C.byref(st))
+        fn = self._lib.qk_count_file if host_framer else self._lib.qk_count_raw_file
+        rc = fn(self._h, os.fsencode(str(reads_path)), C.byref(st))
         if rc == 6:
             raise QkError(rc, f"cannot read {reads_path}")
         self._check(rc)
         return st.as_dict()
 
-    def count_raw(self, data: bytes, seekable: bool = True) -> dict:
-        """Frame an in-memory FASTA/FASTQ byte string and count it."""
-        buf = np.frombuffer(data, dtype=np.uint8)
-        fr = self._lib.qk_framer_open_mem(_np_ptr(buf), buf.size, int(seekable))
-        st = FramerStats()
-        try:
-            self._check(self._lib.qk_count_framer(self._h, fr, C.byref(st)))
-        finally:
-            self._lib.qk_framer_close(fr)
-        return st.as_dict()
+    def count_raw(self, data: bytes, seekable: bool = True, host_framer: bool = False) -> dict:
+        """Count an in-memory FASTA/FASTQ byte string (device framing unless host_framer)."""
+        buf = np.frombuffer(data, dtype=np.uint8) if len(data) else np.zeros(0, np.uint8)
+        return self.count_mem(buf.ctypes.data, buf.size, seekable, host_framer)
 
     def submit_chunk(self, chunk: bytes, slot: int = 0, n_lines: int = 0):
         """Count an already framed chunk (sequence lines only, each ending in a newline)."""
@@ -329,15 +332,25 @@ class Context:
         """Count a framed chunk straight from (ideally pinned) host memory: async H2D + kernel."""
         self._check(self._lib.qk_submit(self._h, slot, host_ptr, n_bytes, None, n_lines))
 
-    def count_mem(self, host_ptr: int, n_bytes: int, seekable: bool = True) -> dict:
-        """Frame + count raw FASTA/FASTQ bytes at a host address (the whole reads stream)."""
-        fr = self._lib.qk_framer_open_mem(host_ptr, n_bytes, int(seekable))
+    def count_mem(self, host_ptr: int, n_bytes: int, seekable: bool = True, host_framer: bool = False) -> dict:
+        """Count raw FASTA/FASTQ bytes at a host address (the whole reads stream).  Pinned
+        memory is DMA'd from directly; the device does the record framing unless host_framer."""
         st = FramerStats()
+        if not host_framer:
+            self._check(self._lib.qk_count_raw_mem(self._h, host_ptr, n_bytes, int(seekable), C.byref(st)))
+            return st.as_dict()
+        fr = self._lib.qk_framer_open_mem(host_ptr, n_bytes, int(seekable))
         try:
             self._check(self._lib.qk_count_framer(self._h, fr, C.byref(st)))
         finally:
             self._lib.qk_framer_close(fr)
         return st.as_dict()
+
+    def submit_raw(self, host_ptr: int, n_bytes: int, slot: int = 0):
+        self._check(self._lib.qk_submit_raw(self._h, slot, host_ptr, n_bytes))
+
+    def raw_begin(self, fastq: bool, skip_first_line: bool):
+        self._check(self._lib.qk_raw_begin(self._h, int(fastq), int(skip_first_line)))
 
     # -- measurement ----------------------------------------------------------------------
     def bench_gather(self, table_bytes: int, gran: int = 32, loads_in_flight: int = 4, n_gathers: int = 1 << 30) -> float:
@@ -386,15 +399,16 @@ def frame(data: bytes, seekable: bool = True, chunk_capacity: int = 1 << 20, wit
     return (chunks, offsets, st.as_dict()) if with_offsets else (chunks, st.as_dict())
 
 
-def count(ref_prefix, reads_path, out_prefix, threads: int = 0, device: int = 0) -> dict:
+def count(ref_prefix, reads_path, out_prefix, threads: int = 0, device: int = 0, host_framer: bool = False,
+          n_slots: int = 4, chunk_capacity: int = 32 << 20) -> dict:
     """``quicKmer2 count [-t N] ref.fa reads Out_prefix`` on the GPU, in-process.
 
     Same files as the reference: reads ``<ref_prefix>.qm`` (and ``.qgc`` if present), writes
     ``<out_prefix>.bin`` (and ``.txt``).  Returns the counting statistics.
     """
-    with Context(device=device) as ctx:
+    with Context(device=device, n_slots=n_slots, chunk_capacity=chunk_capacity) as ctx:
         n = ctx.load_dictionary(f"{ref_prefix}.qm")
-        st = ctx.count_file(reads_path)
+        st = ctx.count_file(reads_path, host_framer=host_framer)
         st.update(ctx.stats())
         counts = ctx.finish()
         counts.tofile(f"{out_prefix}.bin")

@@ -22,6 +22,7 @@
 #define QK_TIMING_RING 64
 #define QK_KEY_BITS 60
 #define QK_BUCKET_ENTRIES 4
+#define QK_FRAME_MAX_CTAS 2048   // CTAs of the device framing passes (per chunk)
 
 struct __align__(32) qk_bucket { unsigned long long e[QK_BUCKET_ENTRIES]; };
 struct __align__(16) qk_stash_entry { unsigned long long key; uint32_t ord1; uint32_t pad; };
@@ -45,6 +46,7 @@ struct qk_slot {
     uint8_t *dev;
     cudaStream_t stream;
     cudaEvent_t h2d_done;
+    cudaEvent_t frame_done;   // this slot's chunk has handed the framing state on
     qk_timing_pair ring[QK_TIMING_RING];
     uint32_t ring_head, ring_count;
 };
@@ -76,6 +78,12 @@ struct qk_ctx {
     uint64_t launches;
     cudaEvent_t span_a, span_b, span_join;
     uint16_t *narrow_dev, *narrow_host; // qk_finish staging (device / pinned), allocated on first use
+
+    // device-side record framing (qk_frame.cu)
+    unsigned long long *frame_stream;   // device: [0] FSM state, [1] read lines, [2] bases, [3] raw lines
+    uint32_t *frame_elems;              // device: n_slots x QK_FRAME_MAX_CTAS per-CTA words
+    int raw_fastq, raw_active, raw_prev_slot;
+    uint64_t frame_launches;
 };
 
 int qk_fail(qk_ctx *ctx, int code, const char *fmt, ...);

@@ -207,14 +207,25 @@ __global__ void __launch_bounds__(QK_THREADS, 3) qk_count_kernel(const qk_count_
             uint64_t key[QK_UNROLL], q[QK_UNROLL];
             const qk_bucket *bp[QK_UNROLL];
             bool valid[QK_UNROLL];
+            uint32_t run[QK_UNROLL];
             qk_bucket bk[QK_UNROLL];
+            bool any = false;
 #pragma unroll
             for (int u = 0; u < QK_UNROLL; ++u) {
                 const uint32_t w = (it * QK_UNROLL + u) * (QK_THREADS / 32) + warp; // word holding p
                 const uint32_t p = base + w * 32 + lane;
                 const uint32_t m = s_mask[buf][w] & (0xFFFFFFFFu >> (31 - lane));
                 const int last = m ? (int)(base + w * 32 + 31 - __clz(m)) : s_last[buf][w];
-                const uint32_t r = (uint32_t)((int)p - last);
+                run[u] = (uint32_t)((int)p - last);
+                valid[u] = p < n && run[u] != 0 && (run[u] & 0xFFFFu) >= k;
+                any = any || valid[u];
+            }
+            // header / quality lines blanked by the device framer, runs of N: nothing to look up
+            if (!__any_sync(0xffffffffu, any)) continue;
+#pragma unroll
+            for (int u = 0; u < QK_UNROLL; ++u) {
+                const uint32_t w = (it * QK_UNROLL + u) * (QK_THREADS / 32) + warp;
+                const uint32_t r = run[u];
                 const uint64_t A = s_codes[buf][w], B = s_codes[buf][w + 1];
                 const uint32_t sh = 2 * (31 - lane);
                 const uint64_t x = (B >> sh) | ((A << 1) << (63 - sh)); // 32 bases ending at p
@@ -223,7 +234,6 @@ __global__ void __launch_bounds__(QK_THREADS, 3) qk_count_kernel(const qk_count_
                 uint64_t rc = (qk_rev_pairs(x & QK_M60) >> 4) ^ 0x0AAAAAAAAAAAAAAAull;
                 rc &= QK_M60 & ~(((uint64_t)1 << (60 - 2 * keep)) - 1);
                 key[u] = min(fwd, rc);
-                valid[u] = p < n && r != 0 && (r & 0xFFFFu) >= k;
                 const uint64_t h = qk_mix60(key[u]);
                 bp[u] = tv.buckets + (h >> tv.rem_bits);
                 q[u] = (h & rem_mask) << tv.ord_bits;
@@ -279,7 +289,7 @@ static int qk_table_view_of(qk_ctx *ctx, qk_table_view *tv)
     return QK_OK;
 }
 
-static int qk_launch_count(qk_ctx *ctx, qk_slot *sl, const uint8_t *dev_bytes, size_t n_bytes)
+int qk_launch_count(qk_ctx *ctx, qk_slot *sl, const uint8_t *dev_bytes, size_t n_bytes)
 {
     qk_count_args a;
     int rc = qk_table_view_of(ctx, &a.tv);

@@ -78,6 +78,7 @@ extern "C" int qk_ctx_create(qk_ctx **out, int device, uint32_t n_slots, size_t 
         QK_CUDA(ctx, cudaStreamCreateWithFlags(&sl->stream, cudaStreamNonBlocking));
         QK_CUDA(ctx, cudaEventCreateWithFlags(&sl->h2d_done, cudaEventDisableTiming));
         QK_CUDA(ctx, cudaEventRecord(sl->h2d_done, sl->stream));
+        QK_CUDA(ctx, cudaEventCreateWithFlags(&sl->frame_done, cudaEventDisableTiming));
         for (int i = 0; i < QK_TIMING_RING; ++i) {
             QK_CUDA(ctx, cudaEventCreate(&sl->ring[i].a));
             QK_CUDA(ctx, cudaEventCreate(&sl->ring[i].b));
@@ -88,6 +89,10 @@ extern "C" int qk_ctx_create(qk_ctx **out, int device, uint32_t n_slots, size_t 
     QK_CUDA(ctx, cudaEventCreateWithFlags(&ctx->span_join, cudaEventDisableTiming));
     QK_CUDA(ctx, cudaMalloc((void **)&ctx->stats, 4 * sizeof(unsigned long long)));
     QK_CUDA(ctx, cudaMemset(ctx->stats, 0, 4 * sizeof(unsigned long long)));
+    QK_CUDA(ctx, cudaMalloc((void **)&ctx->frame_stream, 4 * sizeof(unsigned long long)));
+    QK_CUDA(ctx, cudaMemset(ctx->frame_stream, 0, 4 * sizeof(unsigned long long)));
+    QK_CUDA(ctx, cudaMalloc((void **)&ctx->frame_elems, (size_t)n_slots * QK_FRAME_MAX_CTAS * sizeof(uint32_t)));
+    ctx->raw_prev_slot = -1;
     return QK_OK;
 }
 
@@ -102,6 +107,7 @@ extern "C" void qk_ctx_destroy(qk_ctx *ctx)
         if (sl->dev) cudaFree(sl->dev);
         if (sl->stream) cudaStreamDestroy(sl->stream);
         if (sl->h2d_done) cudaEventDestroy(sl->h2d_done);
+        if (sl->frame_done) cudaEventDestroy(sl->frame_done);
         for (int i = 0; i < QK_TIMING_RING; ++i) {
             if (sl->ring[i].a) cudaEventDestroy(sl->ring[i].a);
             if (sl->ring[i].b) cudaEventDestroy(sl->ring[i].b);
@@ -116,6 +122,8 @@ extern "C" void qk_ctx_destroy(qk_ctx *ctx)
     cudaFree(ctx->stash);
     cudaFree(ctx->counters);
     cudaFree(ctx->stats);
+    cudaFree(ctx->frame_stream);
+    cudaFree(ctx->frame_elems);
     cudaFree(ctx->narrow_dev);
     if (ctx->narrow_host) cudaFreeHost(ctx->narrow_host);
     cudaGetLastError();

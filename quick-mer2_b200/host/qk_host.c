@@ -292,6 +292,143 @@ int qk_count_file(qk_ctx *ctx, const char *reads_path, qk_framer_stats *st)
     return rc;
 }
 
+/* ---- raw streams: the device frames (qk_frame.cu); the host only cuts at line ends ------ */
+static void raw_mode(uint8_t first_byte, int seekable, int *fastq, int *skip_first)
+{
+    *fastq = first_byte == '@';             /* Q.c:395 */
+    *skip_first = *fastq || !seekable;      /* FASTQ: the first line is consumed; pipe: fseek fails (Q.c:396) */
+}
+
+static int raw_finish(qk_ctx *ctx, qk_framer_stats *st, uint64_t raw_bytes, uint64_t unterminated, int fastq)
+{
+    int rc = qk_sync(ctx);
+    if (rc || !st) return rc;
+    memset(st, 0, sizeof *st);
+    uint64_t lines = 0, bases = 0;
+    rc = qk_raw_stats(ctx, &lines, &bases, NULL);
+    st->lines = lines;
+    st->bases = bases;
+    st->raw_bytes = raw_bytes;
+    st->unterminated = unterminated;
+    st->fastq = fastq;
+    return rc;
+}
+
+int qk_count_raw_mem(qk_ctx *ctx, const uint8_t *data, size_t n, int seekable, qk_framer_stats *st)
+{
+    uint32_t n_slots = 0;
+    size_t cap = 0;
+    int rc = qk_ctx_info(ctx, &n_slots, &cap);
+    if (rc) return rc;
+    if (!data && n) return QK_ERR_ARG;
+    int fastq = 0, skip_first = 0;
+    if (n) raw_mode(data[0], seekable, &fastq, &skip_first);
+    rc = qk_raw_begin(ctx, fastq, skip_first);
+    if (rc) return rc;
+    const int pinned = n && qk_host_is_pinned(data) && qk_host_is_pinned(data + n - 1);
+    uint64_t unterminated = 0;
+    uint32_t slot = 0;
+    for (size_t pos = 0; pos < n; slot = (slot + 1) % n_slots) {
+        const size_t end = n - pos > cap ? pos + cap : n;
+        const uint8_t *nl = memrchr(data + pos, '\n', end - pos);
+        const size_t take = nl ? (size_t)(nl - (data + pos)) + 1 : 0;
+        if (take && pinned) {               /* true DMA straight from the caller's buffer */
+            rc = qk_submit_raw(ctx, slot, data + pos, take);
+            pos += take;
+        } else {
+            if (!take && (end < n || end - pos >= cap)) return QK_ERR_ARG; /* a line longer than a chunk */
+            rc = qk_wait_slot(ctx, slot);
+            if (rc) return rc;
+            uint8_t *host = qk_slot_host_buffer(ctx, slot);
+            if (take) {
+                memcpy(host, data + pos, take);
+                rc = qk_submit_raw(ctx, slot, host, take);
+                pos += take;
+            } else {                        /* T9: last line without '\n' -- we terminate it */
+                memcpy(host, data + pos, end - pos);
+                host[end - pos] = '\n';
+                rc = qk_submit_raw(ctx, slot, host, end - pos + 1);
+                pos = end;
+                unterminated++;
+            }
+        }
+        if (rc) return rc;
+    }
+    return raw_finish(ctx, st, n, unterminated, fastq);
+}
+
+int qk_count_raw_fd(qk_ctx *ctx, int fd, int seekable, qk_framer_stats *st)
+{
+    uint32_t n_slots = 0;
+    size_t cap = 0;
+    int rc = qk_ctx_info(ctx, &n_slots, &cap);
+    if (rc) return rc;
+    uint8_t *tail = malloc(cap);            /* the partial last line of the previous piece */
+    if (!tail) return QK_ERR_NOMEM;
+    size_t tail_len = 0;
+    uint64_t raw_bytes = 0, unterminated = 0;
+    int fastq = 0, started = 0, eof = 0;
+    uint32_t slot = 0;
+    while (!eof || tail_len) {
+        rc = qk_wait_slot(ctx, slot);       /* "find an idle worker", Q.c:433-437 */
+        if (rc) break;
+        uint8_t *host = qk_slot_host_buffer(ctx, slot);
+        memcpy(host, tail, tail_len);
+        size_t have = tail_len;
+        tail_len = 0;
+        while (!eof && have < cap) {
+            ssize_t got = read(fd, host + have, cap - have);
+            if (got < 0 && errno == EINTR) continue;
+            if (got < 0) { rc = QK_ERR_IO; break; }
+            if (got == 0) eof = 1;
+            have += (size_t)got;
+        }
+        if (rc || have == 0) break;
+        if (!started) {
+            int skip_first;
+            raw_mode(host[0], seekable, &fastq, &skip_first);
+            rc = qk_raw_begin(ctx, fastq, skip_first);
+            if (rc) break;
+            started = 1;
+        }
+        const uint8_t *nl = memrchr(host, '\n', have);
+        size_t take = nl ? (size_t)(nl - host) + 1 : 0;
+        if (eof && take < have) {           /* T9: unterminated last line */
+            if (have >= cap) { rc = QK_ERR_ARG; break; }
+            host[have] = '\n';
+            raw_bytes += have;
+            take = have + 1;
+            have = take;
+            unterminated++;
+        } else {
+            if (!take) { rc = QK_ERR_ARG; break; } /* a line longer than a chunk */
+            raw_bytes += take;
+        }
+        tail_len = have - take;
+        memcpy(tail, host + take, tail_len);
+        rc = qk_submit_raw(ctx, slot, host, take); /* "sem_post", Q.c:431-432 */
+        if (rc) break;
+        slot = (slot + 1) % n_slots;
+    }
+    free(tail);
+    if (rc) return rc;
+    if (!started) {
+        rc = qk_raw_begin(ctx, 0, 0);
+        if (rc) return rc;
+    }
+    return raw_finish(ctx, st, raw_bytes, unterminated, fastq);
+}
+
+int qk_count_raw_file(qk_ctx *ctx, const char *reads_path, qk_framer_stats *st)
+{
+    int fd = open(reads_path, O_RDONLY);
+    if (fd < 0) return QK_ERR_IO;
+    int seekable = lseek(fd, 0, SEEK_CUR) != (off_t)-1;
+    int rc = qk_count_raw_fd(ctx, fd, seekable, st);
+    close(fd);
+    return rc;
+}
+
 /* ------------------------------------------------------------------ command ---------- */
 static void help_count(void)
 {
@@ -336,8 +473,15 @@ int qk_count_main(int argc, char **argv)
         printf("Dictionary %s open fail\n", path);
         return 1;
     }
-    qk_framer *fr = qk_framer_open(reads);
-    if (!fr) { puts("Input open fail"); return 1; }    /* Q.c:339-341 (the reference goes on and crashes) */
+    const int host_framer = getenv("QK_HOST_FRAMER") != NULL; /* default: the device frames the raw stream */
+    qk_framer *fr = NULL;
+    int reads_fd = -1, reads_seekable = 0;
+    if (host_framer) fr = qk_framer_open(reads);
+    else {
+        reads_fd = open(reads, O_RDONLY);
+        reads_seekable = reads_fd >= 0 && lseek(reads_fd, 0, SEEK_CUR) != (off_t)-1;
+    }
+    if (!fr && reads_fd < 0) { puts("Input open fail"); return 1; } /* Q.c:339-341 (the reference goes on and crashes) */
     printf("Hash Size: 0x%lX\nFirst location: 0x%lX\n", (unsigned long)hdr.hash_size, (unsigned long)hdr.first_idx);
 
     double t0 = now_sec();
@@ -361,8 +505,13 @@ int qk_count_main(int argc, char **argv)
     time_t start_time, end_time;
     time(&start_time);                                                     /* Q.c:387 */
     qk_framer_stats st;
-    rc = qk_count_framer(ctx, fr, &st);
-    qk_framer_close(fr);
+    if (host_framer) {
+        rc = qk_count_framer(ctx, fr, &st);
+        qk_framer_close(fr);
+    } else {
+        rc = qk_count_raw_fd(ctx, reads_fd, reads_seekable, &st);
+        close(reads_fd);
+    }
     uint64_t total = 0, hits = 0;
     if (!rc) rc = qk_stats(ctx, &total, &hits, NULL);
     if (rc) { printf("Counting failed: %s\n", qk_last_error(ctx)); qk_ctx_destroy(ctx); return 1; }

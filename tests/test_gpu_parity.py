@@ -27,12 +27,17 @@ def gpu_bin(ctx, qm, reads=None, raw=None, seekable=True):
 
 
 # ------------------------------------------------------------------ golden fixtures -------
+@pytest.mark.parametrize("framer", ["device", "host", "device_small_chunks"])
 @pytest.mark.parametrize("case", golden_cases())
-def test_golden_bin_and_txt(case, qk, tmp_path):
-    """quicKmer2 count ref.fa reads out -> same .bin and .txt bytes as the reference wrote."""
+def test_golden_bin_and_txt(case, framer, qk, tmp_path):
+    """quicKmer2 count ref.fa reads out -> same .bin and .txt bytes as the reference wrote,
+    with the record framing done on the device (default) or by the host framer."""
     meta = golden_meta(case)
     d = GOLDEN / case
-    st = qk.count(d / "ref.fa", d / meta["reads"], tmp_path / "out")
+    kw = dict(host_framer=True) if framer == "host" else {}
+    if framer == "device_small_chunks":
+        kw = dict(n_slots=3, chunk_capacity=200000)
+    st = qk.count(d / "ref.fa", d / meta["reads"], tmp_path / "out", **kw)
     assert (tmp_path / "out.bin").read_bytes() == (d / "expect.bin").read_bytes()
     assert st["total_kmers"] == meta["total_kmers"]
     assert st["n_kmers"] == meta["n_kmers"]
@@ -223,6 +228,100 @@ def test_corrupt_chain_is_rejected(qk, oracle, gpu_ctx):
     with pytest.raises(qk.QkError):
         gpu_ctx.load_dictionary_arrays(30, keys, bad, first)
     assert gpu_ctx.load_dictionary_arrays(30, keys, nxt, first) == order.size   # and the intact one loads
+
+
+# ------------------------------------------------------------------ device framing ---------
+def weird_stream(rng, seq, fastq_like, n_lines):
+    """Lines in arbitrary order -- not a valid FASTA/FASTQ -- so that the reference's line state
+    machine (Q.c:397-398, 451-455) is driven through every phase: '>' where a read is expected,
+    quality lines that start with '>' or '@', empty lines, N runs, CR."""
+    out = []
+    for _ in range(n_lines):
+        kind = rng.integers(0, 10)
+        a = int(rng.integers(0, len(seq) - 400))
+        body = seq[a:a + int(rng.integers(0, 300))]
+        if kind == 0:
+            out.append(">" + body[:20])
+        elif kind == 1:
+            out.append("@" + body[:30])
+        elif kind == 2:
+            out.append("+")
+        elif kind == 3:
+            out.append("")
+        elif kind == 4:
+            out.append(">" * int(rng.integers(1, 4)) + "III@@>>")
+        elif kind == 5:
+            out.append(body[:50] + "N" * int(rng.integers(1, 5)) + body[50:] + "\r")
+        else:
+            out.append(body)
+    first = "@first" if fastq_like else rng.choice([">first", seq[5:160], ""])
+    return "\n".join([first] + out) + "\n"
+
+
+@pytest.mark.parametrize("fastq_like", [True, False])
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_device_framing_state_machine(seed, fastq_like, mid_dict, qk, oracle, tmp_path):
+    rng = np.random.default_rng(seed)
+    seq = "".join(l.strip() for l in open(mid_dict / "ref.fa") if not l.startswith(">"))[:400000].replace("N", "")
+    text = weird_stream(rng, seq, fastq_like, 6000)
+    (tmp_path / "w.txt").write_text(text, newline="")
+    want, ost = oracle.count_bin(mid_dict / "ref.fa.qm", tmp_path / "w.txt")
+    assert ost["fastq"] == int(fastq_like) and ost["lines"] > 500
+    for cap in (200000, 1 << 20):
+        with qk.Context(n_slots=3, chunk_capacity=cap) as ctx:
+            ctx.load_dictionary(mid_dict / "ref.fa.qm")
+            st = ctx.count_file(tmp_path / "w.txt"); st.update(ctx.stats())
+            assert np.array_equal(ctx.finish(), want)
+            for key in ("lines", "bases", "fastq", "total_kmers", "hits"):
+                assert st[key] == ost[key], (key, cap)
+            # the same bytes from memory (pageable -> staged through the pinned slots)
+            ctx.reset()
+            st2 = ctx.count_raw(text.encode()); st2.update(ctx.stats())
+            assert np.array_equal(ctx.finish(), want) and st2["lines"] == ost["lines"]
+
+
+def test_device_framing_pipe_and_unterminated(mid_dict, qk, oracle, gpu_ctx, tmp_path):
+    seq = "".join(l.strip() for l in open(mid_dict / "ref.fa") if not l.startswith(">"))[:100000].replace("N", "")
+    body = "".join(f">r{i}\n{seq[i * 100:i * 100 + 150]}\n" for i in range(500))
+    gpu_ctx.load_dictionary(mid_dict / "ref.fa.qm")
+
+    def run(data, seekable):
+        gpu_ctx.reset()
+        st = gpu_ctx.count_raw(data.encode(), seekable=seekable); st.update(gpu_ctx.stats())
+        return gpu_ctx.finish(), st
+
+    def want(data):
+        (tmp_path / "x.fa").write_text(data, newline="")
+        return oracle.count_bin(mid_dict / "ref.fa.qm", tmp_path / "x.fa")
+
+    first = seq[7000:7150] + "\n"
+    got, st = run(first + body, True)                       # seekable FASTA: the first line is a read
+    w, ost = want(first + body)
+    assert np.array_equal(got, w) and st["lines"] == ost["lines"] == 501
+    got, st = run(first + body, False)                      # pipe: the first line is lost (Q.c:396)
+    w, ost = want(body)
+    assert np.array_equal(got, w) and st["lines"] == ost["lines"] == 500
+    got, st = run(body + seq[9000:9150], True)              # T9: unterminated last line gets its '\n'
+    w, ost = want(body + seq[9000:9150] + "\n")
+    assert np.array_equal(got, w) and st["lines"] == 501 and st["unterminated"] == 1
+    got, st = run("", True)
+    assert st["lines"] == 0 and st["total_kmers"] == 0 and not got.any()
+    got, st = run("@only a header\n", True)
+    assert st["lines"] == 0 and st["fastq"] == 1
+
+
+def test_pinned_source_is_dmaed_directly(mid_dict, qk, oracle, synth, tmp_path):
+    import torch
+    synth("reads", "--ref", mid_dict / "ref.fa", "--out", tmp_path / "r.fq", "--n", 100000, "--len", 150, "--seed", 8,
+          "--fastq", "--rand-qual")
+    want, ost = oracle.count_bin(mid_dict / "ref.fa.qm", tmp_path / "r.fq")
+    raw = torch.from_numpy(np.fromfile(tmp_path / "r.fq", dtype=np.uint8)).pin_memory()
+    assert qk.lib().qk_host_is_pinned(raw.data_ptr()) == 1
+    with qk.Context(n_slots=4, chunk_capacity=4 << 20) as ctx:
+        ctx.load_dictionary(mid_dict / "ref.fa.qm")
+        st = ctx.count_mem(raw.data_ptr(), raw.numel()); st.update(ctx.stats())
+        assert np.array_equal(ctx.finish(), want)
+        assert st["lines"] == ost["lines"] == 100000 and st["total_kmers"] == ost["total_kmers"]
 
 
 # ------------------------------------------------------------------ properties at size -----
