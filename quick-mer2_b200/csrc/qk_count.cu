@@ -369,6 +369,7 @@ extern "C" int qk_reset_counters(qk_ctx *ctx)
     if (rc) return rc;
     QK_CUDA(ctx, cudaMemset(ctx->counters, 0, (ctx->desc.n_kmers + 1) * sizeof(uint32_t)));
     QK_CUDA(ctx, cudaMemset(ctx->stats, 0, 4 * sizeof(unsigned long long)));
+    QK_CUDA(ctx, cudaMemset(ctx->frame_stream + 1, 0, 3 * sizeof(unsigned long long))); // totals, not the line state
     QK_CUDA(ctx, cudaDeviceSynchronize()); // the slot streams do not order against stream 0
     ctx->lines = 0;
     ctx->kernel_ms = ctx->h2d_ms = 0;

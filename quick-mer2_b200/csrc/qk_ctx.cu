@@ -203,7 +203,11 @@ extern "C" int qk_stats(qk_ctx *ctx, uint64_t *total_kmers, uint64_t *hits, uint
     QK_CUDA(ctx, cudaMemcpy(h, ctx->stats, sizeof h, cudaMemcpyDeviceToHost));
     if (total_kmers) *total_kmers = h[0];
     if (hits) *hits = h[1];
-    if (lines) *lines = ctx->lines;
+    if (lines) { // framed chunks are counted by the host, raw pieces by the device framer
+        unsigned long long f[4];
+        QK_CUDA(ctx, cudaMemcpy(f, ctx->frame_stream, sizeof f, cudaMemcpyDeviceToHost));
+        *lines = ctx->lines + f[1];
+    }
     return QK_OK;
 }
 

@@ -258,6 +258,7 @@ static int qk_alloc_table(qk_ctx *ctx, const qk_table_desc *d)
     QK_CUDA(ctx, cudaMalloc((void **)&ctx->counters, (d->n_kmers + 1) * sizeof(uint32_t)));
     QK_CUDA(ctx, cudaMemset(ctx->counters, 0, (d->n_kmers + 1) * sizeof(uint32_t)));
     QK_CUDA(ctx, cudaMemset(ctx->stats, 0, 4 * sizeof(unsigned long long))); // a new dictionary starts a new count
+    QK_CUDA(ctx, cudaMemset(ctx->frame_stream, 0, 4 * sizeof(unsigned long long)));
     QK_CUDA(ctx, cudaDeviceSynchronize()); // the slot streams do not order against stream 0
     ctx->lines = 0;
     ctx->kernel_ms = ctx->h2d_ms = 0;
