@@ -305,9 +305,12 @@ class Context:
         return {"kernel_ms": k.value, "h2d_ms": h.value, "launches": n.value}
 
     # -- results --------------------------------------------------------------------------
-    def finish(self) -> np.ndarray:
-        """Depths in .bin order, uint16 with the reference's wrap (Q.c:498-518)."""
-        out = np.empty(self.n_kmers, dtype=np.uint16)
+    def finish(self, out: np.ndarray | None = None) -> np.ndarray:
+        """Depths in .bin order, uint16 with the reference's wrap (Q.c:498-518).  `out` may be
+        a caller-owned (ideally pinned) uint16 array of n_kmers entries."""
+        if out is None:
+            out = np.empty(self.n_kmers, dtype=np.uint16)
+        assert out.dtype == np.uint16 and out.size == self.n_kmers and out.flags.c_contiguous
         self._check(self._lib.qk_finish(self._h, _np_ptr(out), self.n_kmers))
         return out
 
