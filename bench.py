@@ -296,12 +296,6 @@ def reference_arm(args):
 
 
 # --------------------------------------------------------------------------- GPU arm ------
-class DevMem:
-    """A raw device allocation seen through __cuda_array_interface__ (for torch.as_tensor)."""
-    def __init__(self, ptr, n, typestr="|u1"):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3}
-
-
 def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -324,6 +318,8 @@ def gpu_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     qk = load_package()
+    import importlib
+    qd = importlib.import_module("quickmer2_b200.dist")
     if rank == 0:
         qk.build()
     if world > 1:
@@ -348,21 +344,11 @@ def gpu_arm(args):
     if world > 1:
         # replicate the built table: descriptor through the host, image over NCCL/NVLink
         t0 = time.perf_counter()
-        desc = ctx.table_desc() if rank == 0 else qk.TableDesc()
-        raw = torch.frombuffer(bytearray(bytes(desc)), dtype=torch.uint8).cuda()
-        dist.broadcast(raw, 0)
-        if rank != 0:
-            desc = qk.TableDesc.from_buffer_copy(raw.cpu().numpy().tobytes())
-            ctx.adopt(desc)
-        n_kmers = int(desc.n_kmers)
-        tptr, sptr = ctx.table_device_ptrs()
-        for ptr, nbytes in ((tptr, int(desc.table_bytes)), (sptr, int(desc.stash_bytes))):
-            dist.broadcast(torch.as_tensor(DevMem(ptr, nbytes), device=f"cuda:{local}"), 0)
+        n_kmers = qd.replicate_dictionary(qk, ctx, rank, local, dist)
         torch.cuda.synchronize()
         bcast_s = time.perf_counter() - t0
     desc = ctx.table_desc()
-    cptr, _ = ctx.counters_device_ptr()
-    counters_t = torch.as_tensor(DevMem(cptr, n_kmers, "<i4"), device=f"cuda:{local}")
+    counters_t = qd.counters_tensor(ctx, local)
 
     # ---- host side: raw reads in memory, framed chunks (pinned), device-resident copy ----
     raw_np = np.fromfile(reads, dtype=np.uint8)

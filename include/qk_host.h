@@ -17,6 +17,7 @@ extern "C" {
 #endif
 
 #define QK_ERR_IO 6 /* file cannot be opened / short read */
+#define QK_HOST_MAX_SLOTS 8
 
 /* ---- QM11 dictionary file: written at Q.c:1284-1299, read at Q.c:345-359 and 483 ---- */
 typedef struct qk_qm_header {
@@ -87,6 +88,23 @@ int qk_count_framer(qk_ctx *ctx, qk_framer *f, qk_framer_stats *st);
 int qk_count_raw_mem(qk_ctx *ctx, const uint8_t *data, size_t n, int seekable, qk_framer_stats *st);
 int qk_count_raw_fd(qk_ctx *ctx, int fd, int seekable, qk_framer_stats *st); /* does not close fd */
 int qk_count_raw_file(qk_ctx *ctx, const char *reads_path, qk_framer_stats *st);
+/* Regular files: `threads` readers (0 = QK_READER_THREADS or 4, at most the slot count)
+ * pread() pieces into the pinned slot buffers in parallel; lines longer than 128 KiB are an
+ * error on this path.  Pipes fall back to qk_count_raw_fd. */
+int qk_count_raw_file_mt(qk_ctx *ctx, const char *reads_path, uint32_t threads, qk_framer_stats *st);
+
+/* ---- one reads file, several GPUs ---------------------------------------------------------
+ * qk_shard_bounds: the line-aligned byte range [begin, end) of shard `rank` of `world`
+ * (regular files only).  qk_count_raw_range counts that range on one context, starting the
+ * reference's line state machine in `line_state` (see qk_raw_begin_state) and returning the
+ * state after the last line.  FASTA shards always start in state 0; for FASTQ the state of a
+ * shard is whatever the previous shard ends in: qk_fastq_state_guess proposes it from the
+ * first lines of the shard so that all shards can run at once, and the caller compares each
+ * shard's assumed state with its predecessor's final state afterwards (quick-mer2_b200/dist.py). */
+int qk_shard_bounds(const char *reads_path, uint32_t rank, uint32_t world, uint64_t *begin, uint64_t *end);
+int qk_fastq_state_guess(const uint8_t *window, size_t n, uint32_t *line_state);
+int qk_count_raw_range(qk_ctx *ctx, const char *reads_path, uint64_t begin, uint64_t end, int fastq, uint32_t line_state,
+                       qk_framer_stats *st, uint32_t *final_state);
 
 /* ---- the command: main_count, Q.c:304-545 -----------------------------------------------
  * quicKmer2 count [-h] [-t N] [-g device] ref_prefix reads out_prefix

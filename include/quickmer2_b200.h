@@ -120,6 +120,11 @@ int qk_submit_device(qk_ctx *ctx, uint32_t slot, const uint8_t *dev_bytes, size_
  * and the call returns at once.  Pieces must be submitted in stream order; the line-phase
  * state is carried from piece to piece on the device. */
 int qk_raw_begin(qk_ctx *ctx, int fastq, int skip_first_line);
+/* The same with an explicit line state: the number (0..3) of lines still to be discarded
+ * before a line is examined again -- for a shard that starts in the middle of a stream.
+ * qk_raw_state returns the state after everything submitted so far (syncs). */
+int qk_raw_begin_state(qk_ctx *ctx, int fastq, uint32_t line_state);
+int qk_raw_state(qk_ctx *ctx, uint32_t *line_state);
 int qk_submit_raw(qk_ctx *ctx, uint32_t slot, const uint8_t *bytes, size_t n_bytes);
 /* Totals of the raw stream so far (syncs): sequence lines, their bases, all lines seen. */
 int qk_raw_stats(qk_ctx *ctx, uint64_t *read_lines, uint64_t *bases, uint64_t *raw_lines);

@@ -102,6 +102,8 @@ SIGNATURES = {
     "qk_submit": (C.c_int, [_P, C.c_uint32, _P, C.c_size_t, _P, C.c_uint32]),
     "qk_submit_device": (C.c_int, [_P, C.c_uint32, _P, C.c_size_t]),
     "qk_raw_begin": (C.c_int, [_P, C.c_int, C.c_int]),
+    "qk_raw_begin_state": (C.c_int, [_P, C.c_int, C.c_uint32]),
+    "qk_raw_state": (C.c_int, [_P, C.POINTER(C.c_uint32)]),
     "qk_submit_raw": (C.c_int, [_P, C.c_uint32, _P, C.c_size_t]),
     "qk_raw_stats": (C.c_int, [_P, _U64P, _U64P, _U64P]),
     "qk_host_is_pinned": (C.c_int, [_P]),
@@ -134,6 +136,11 @@ SIGNATURES = {
     "qk_count_raw_mem": (C.c_int, [_P, _P, C.c_size_t, C.c_int, C.POINTER(FramerStats)]),
     "qk_count_raw_fd": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(FramerStats)]),
     "qk_count_raw_file": (C.c_int, [_P, C.c_char_p, C.POINTER(FramerStats)]),
+    "qk_shard_bounds": (C.c_int, [C.c_char_p, C.c_uint32, C.c_uint32, _U64P, _U64P]),
+    "qk_fastq_state_guess": (C.c_int, [_P, C.c_size_t, C.POINTER(C.c_uint32)]),
+    "qk_count_raw_range": (C.c_int, [_P, C.c_char_p, C.c_uint64, C.c_uint64, C.c_int, C.c_uint32, C.POINTER(FramerStats),
+                                     C.POINTER(C.c_uint32)]),
+    "qk_count_raw_file_mt": (C.c_int, [_P, C.c_char_p, C.c_uint32, C.POINTER(FramerStats)]),
     "qk_count_main": (C.c_int, [C.c_int, C.POINTER(C.c_char_p)]),
 }
 
@@ -261,12 +268,15 @@ class Context:
         return out
 
     # -- counting -------------------------------------------------------------------------
-    def count_file(self, reads_path, host_framer: bool = False) -> dict:
+    def count_file(self, reads_path, host_framer: bool = False, threads: int = 0) -> dict:
         """Count a FASTA/FASTQ file (Q.c:393-479).  Default: raw pieces cut at line ends go to
-        the device, which frames them; host_framer=True frames on the host instead."""
+        the device, which frames them (`threads` readers fill the pinned buffers);
+        host_framer=True frames on the host instead."""
         st = FramerStats()
-        fn = self._lib.qk_count_file if host_framer else self._lib.qk_count_raw_file
-        rc = fn(self._h, os.fsencode(str(reads_path)), C.byref(st))
+        if host_framer:
+            rc = self._lib.qk_count_file(self._h, os.fsencode(str(reads_path)), C.byref(st))
+        else:
+            rc = self._lib.qk_count_raw_file_mt(self._h, os.fsencode(str(reads_path)), threads, C.byref(st))
         if rc == 6:
             raise QkError(rc, f"cannot read {reads_path}")
         self._check(rc)
@@ -348,6 +358,16 @@ class Context:
         finally:
             self._lib.qk_framer_close(fr)
         return st.as_dict()
+
+    def count_range(self, reads_path, begin: int, end: int, fastq: bool, line_state: int):
+        """Count bytes [begin, end) of a reads file starting in `line_state`; returns (stats, final state)."""
+        st, fin = FramerStats(), C.c_uint32()
+        rc = self._lib.qk_count_raw_range(self._h, os.fsencode(str(reads_path)), begin, end, int(fastq), line_state,
+                                          C.byref(st), C.byref(fin))
+        if rc == 6:
+            raise QkError(rc, f"cannot read {reads_path}")
+        self._check(rc)
+        return st.as_dict(), fin.value
 
     def submit_raw(self, host_ptr: int, n_bytes: int, slot: int = 0):
         self._check(self._lib.qk_submit_raw(self._h, slot, host_ptr, n_bytes))

@@ -258,11 +258,27 @@ __global__ void qk_frame_carry(uint32_t *cta_elem, uint32_t n_ctas, unsigned lon
 
 extern "C" int qk_raw_begin(qk_ctx *ctx, int fastq, int skip_first_line)
 {
-    if (!ctx) return QK_ERR_ARG;
+    return qk_raw_begin_state(ctx, fastq, skip_first_line ? 3u : 0u);
+}
+
+extern "C" int qk_raw_state(qk_ctx *ctx, uint32_t *line_state)
+{
+    if (!ctx || !line_state) return QK_ERR_ARG;
+    int rc = qk_sync(ctx);
+    if (rc) return rc;
+    unsigned long long s = 0;
+    QK_CUDA(ctx, cudaMemcpy(&s, ctx->frame_stream, sizeof s, cudaMemcpyDeviceToHost));
+    *line_state = (uint32_t)s & 3u;
+    return QK_OK;
+}
+
+extern "C" int qk_raw_begin_state(qk_ctx *ctx, int fastq, uint32_t line_state)
+{
+    if (!ctx || line_state > 3) return QK_ERR_ARG;
     int rc = qk_sync(ctx);
     if (rc) return rc;
     QK_CUDA(ctx, cudaSetDevice(ctx->device));
-    unsigned long long init[4] = {skip_first_line ? 3ull : 0ull, 0, 0, 0};
+    unsigned long long init[4] = {line_state, 0, 0, 0};
     QK_CUDA(ctx, cudaMemcpy(ctx->frame_stream, init, sizeof init, cudaMemcpyHostToDevice));
     ctx->raw_fastq = fastq ? 1 : 0;
     ctx->raw_active = 1;

@@ -7,6 +7,7 @@
 #define _FILE_OFFSET_BITS 64
 #include <errno.h>
 #include <fcntl.h>
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -419,14 +420,275 @@ int qk_count_raw_fd(qk_ctx *ctx, int fd, int seekable, qk_framer_stats *st)
     return raw_finish(ctx, st, raw_bytes, unterminated, fastq);
 }
 
-int qk_count_raw_file(qk_ctx *ctx, const char *reads_path, qk_framer_stats *st)
+/* ---- sharding one reads file over several GPUs ------------------------------------------- */
+/* first line start at or after `at` (a line starts at 0 and after every '\n') */
+static int64_t line_start_at_or_after(int fd, uint64_t at, uint64_t size)
+{
+    if (at == 0) return 0;
+    uint8_t buf[65536];
+    uint64_t pos = at - 1;              /* if byte at-1 is '\n', `at` itself is a line start */
+    while (pos < size) {
+        ssize_t got = pread(fd, buf, sizeof buf, (off_t)pos);
+        if (got < 0 && errno == EINTR) continue;
+        if (got <= 0) return got < 0 ? -1 : (int64_t)size;
+        const uint8_t *nl = memchr(buf, '\n', (size_t)got);
+        if (nl) return (int64_t)(pos + (uint64_t)(nl - buf) + 1);
+        pos += (uint64_t)got;
+    }
+    return (int64_t)size;
+}
+
+int qk_shard_bounds(const char *reads_path, uint32_t rank, uint32_t world, uint64_t *begin, uint64_t *end)
+{
+    if (!reads_path || !begin || !end || world == 0 || rank >= world) return QK_ERR_ARG;
+    int fd = open(reads_path, O_RDONLY);
+    if (fd < 0) return QK_ERR_IO;
+    struct stat sb;
+    if (fstat(fd, &sb) != 0 || !S_ISREG(sb.st_mode)) { close(fd); return QK_ERR_IO; }
+    const uint64_t size = (uint64_t)sb.st_size;
+    int64_t b = line_start_at_or_after(fd, size / world * rank, size);
+    int64_t e = rank + 1 == world ? (int64_t)size : line_start_at_or_after(fd, size / world * (rank + 1), size);
+    close(fd);
+    if (b < 0 || e < 0) return QK_ERR_IO;
+    *begin = (uint64_t)b;
+    *end = (uint64_t)e;
+    return QK_OK;
+}
+
+/* Guess the line state of a FASTQ stream at a line start from the next few lines: find a line
+ * i starting with '@' whose line i+2 starts with '+' and whose lines i+1 and i+3 have equal
+ * length -- a record header, examined in state 3 -- so the state at line 0 is (3 - i) mod 4.
+ * A guess only: callers verify it against the true state handed on by the previous shard. */
+int qk_fastq_state_guess(const uint8_t *window, size_t n, uint32_t *line_state)
+{
+    if (!window || !line_state) return QK_ERR_ARG;
+    size_t start[12], len[12];
+    int nl = 0;
+    size_t pos = 0;
+    while (nl < 12 && pos < n) {
+        const uint8_t *e = memchr(window + pos, '\n', n - pos);
+        if (!e) break;
+        start[nl] = pos;
+        len[nl] = (size_t)(e - (window + pos));
+        pos += len[nl] + 1;
+        ++nl;
+    }
+    for (int i = 0; i + 3 < nl && i < 8; ++i)
+        if (window[start[i]] == '@' && len[i + 2] >= 1 && window[start[i + 2]] == '+' && len[i + 1] == len[i + 3]) {
+            *line_state = (uint32_t)((3 - i) & 3);
+            return QK_OK;
+        }
+    *line_state = 0;
+    return QK_ERR_FORMAT;
+}
+
+int qk_count_raw_range(qk_ctx *ctx, const char *reads_path, uint64_t begin, uint64_t end, int fastq, uint32_t line_state,
+                       qk_framer_stats *st, uint32_t *final_state)
+{
+    uint32_t n_slots = 0;
+    size_t cap = 0;
+    int rc = qk_ctx_info(ctx, &n_slots, &cap);
+    if (rc) return rc;
+    int fd = open(reads_path, O_RDONLY);
+    if (fd < 0) return QK_ERR_IO;
+    rc = qk_raw_begin_state(ctx, fastq, line_state);
+    uint64_t unterminated = 0, pos = begin;
+    uint32_t slot = 0;
+    while (!rc && pos < end) {
+        rc = qk_wait_slot(ctx, slot);
+        if (rc) break;
+        uint8_t *host = qk_slot_host_buffer(ctx, slot);
+        size_t want = end - pos > cap ? cap : (size_t)(end - pos), have = 0;
+        while (have < want) {
+            ssize_t got = pread(fd, host + have, want - have, (off_t)(pos + have));
+            if (got < 0 && errno == EINTR) continue;
+            if (got <= 0) break;
+            have += (size_t)got;
+        }
+        if (have == 0) { rc = QK_ERR_IO; break; }
+        const uint8_t *nl = memrchr(host, '\n', have);
+        size_t take = nl ? (size_t)(nl - host) + 1 : 0;
+        if (pos + have >= end && take < have) {           /* unterminated last line of the file */
+            if (have >= cap) { rc = QK_ERR_ARG; break; }
+            host[have] = '\n';
+            rc = qk_submit_raw(ctx, slot, host, have + 1);
+            unterminated++;
+            pos += have;
+        } else {
+            if (!take) { rc = QK_ERR_ARG; break; }
+            rc = qk_submit_raw(ctx, slot, host, take);
+            pos += take;
+        }
+        slot = (slot + 1) % n_slots;
+    }
+    close(fd);
+    if (rc) return rc;
+    if (final_state) {
+        rc = qk_raw_state(ctx, final_state);
+        if (rc) return rc;
+    }
+    return raw_finish(ctx, st, end - begin, unterminated, fastq);
+}
+
+/* ---- parallel ingest of a regular file -----------------------------------------------------
+ * The reference has ONE producer thread (Q.c:397-456) and is bound by it.  Here the producer's
+ * only per-byte work is getting the bytes into pinned memory, and that is what is
+ * parallelised: reader threads pread() fixed-size pieces of the range straight into the slots'
+ * pinned buffers (at offset QK_HEAD), the submitting thread takes the pieces in order, puts
+ * the partial last line of the previous piece in front (that is what the QK_HEAD bytes of
+ * headroom are for), cuts at the last '\n' and enqueues H2D + framing + counting. */
+#define QK_HEAD ((size_t)128 << 10) /* >= the longest line the reference reads (100,000 bytes) */
+
+typedef struct {
+    qk_ctx *ctx;
+    int fd;
+    uint64_t begin, end;
+    size_t body;                 /* file bytes per piece */
+    uint32_t n_slots;
+    uint64_t n_pieces;
+    pthread_mutex_t mu;
+    pthread_cond_t cv;
+    uint64_t next_piece;         /* next piece a reader may claim            */
+    uint64_t submitted;          /* pieces the submitting thread is done with */
+    uint64_t filled[QK_HOST_MAX_SLOTS]; /* piece index + 1 sitting in each slot, 0 = none */
+    size_t filled_len[QK_HOST_MAX_SLOTS];
+    int err;
+} qk_ingest;
+
+static void *ingest_reader(void *arg)
+{
+    qk_ingest *g = arg;
+    for (;;) {
+        pthread_mutex_lock(&g->mu);
+        const uint64_t i = g->next_piece;
+        if (i >= g->n_pieces || g->err) { pthread_mutex_unlock(&g->mu); return NULL; }
+        g->next_piece++;
+        while (!g->err && i >= g->submitted + g->n_slots) pthread_cond_wait(&g->cv, &g->mu); /* slot still holds piece i - n_slots */
+        pthread_mutex_unlock(&g->mu);
+        const uint32_t slot = (uint32_t)(i % g->n_slots);
+        int rc = qk_wait_slot(g->ctx, slot);     /* its last H2D has left the pinned buffer */
+        uint8_t *host = qk_slot_host_buffer(g->ctx, slot) + QK_HEAD;
+        const uint64_t at = g->begin + i * g->body;
+        const size_t want = g->end - at > g->body ? g->body : (size_t)(g->end - at);
+        size_t have = 0;
+        while (!rc && have < want) {
+            ssize_t got = pread(g->fd, host + have, want - have, (off_t)(at + have));
+            if (got < 0 && errno == EINTR) continue;
+            if (got <= 0) { rc = QK_ERR_IO; break; }
+            have += (size_t)got;
+        }
+        pthread_mutex_lock(&g->mu);
+        if (rc) g->err = rc;
+        g->filled[slot] = i + 1;
+        g->filled_len[slot] = have;
+        pthread_cond_broadcast(&g->cv);
+        pthread_mutex_unlock(&g->mu);
+    }
+}
+
+static int count_range_mt(qk_ctx *ctx, int fd, uint64_t begin, uint64_t end, uint32_t threads, uint64_t *unterminated)
+{
+    qk_ingest g;
+    memset(&g, 0, sizeof g);
+    size_t cap = 0;
+    int rc = qk_ctx_info(ctx, &g.n_slots, &cap);
+    if (rc) return rc;
+    if (cap < 4 * QK_HEAD || g.n_slots > QK_HOST_MAX_SLOTS) return QK_ERR_ARG;
+    g.ctx = ctx;
+    g.fd = fd;
+    g.begin = begin;
+    g.end = end;
+    g.body = cap - QK_HEAD - 1;
+    g.n_pieces = (end - begin + g.body - 1) / g.body;
+    pthread_mutex_init(&g.mu, NULL);
+    pthread_cond_init(&g.cv, NULL);
+    if (threads > g.n_slots) threads = g.n_slots;
+    if (threads < 1) threads = 1;
+    pthread_t th[QK_HOST_MAX_SLOTS];
+    uint32_t started = 0;
+    for (; started < threads; ++started)
+        if (pthread_create(&th[started], NULL, ingest_reader, &g) != 0) break;
+    if (started == 0) rc = QK_ERR_NOMEM;
+    uint8_t *tail = malloc(QK_HEAD);
+    size_t tail_len = 0;
+    if (!tail) rc = QK_ERR_NOMEM;
+    for (uint64_t i = 0; !rc && i < g.n_pieces; ++i) {
+        const uint32_t slot = (uint32_t)(i % g.n_slots);
+        pthread_mutex_lock(&g.mu);
+        while (!g.err && g.filled[slot] != i + 1) pthread_cond_wait(&g.cv, &g.mu);
+        rc = g.err;
+        size_t have = g.filled_len[slot];
+        pthread_mutex_unlock(&g.mu);
+        if (rc) break;
+        uint8_t *body = qk_slot_host_buffer(ctx, slot) + QK_HEAD;
+        uint8_t *from = body - tail_len;
+        memcpy(from, tail, tail_len);
+        size_t total = tail_len + have;
+        const uint8_t *nl = memrchr(from, '\n', total);
+        size_t take = nl ? (size_t)(nl - from) + 1 : 0;
+        if (i + 1 == g.n_pieces && take < total) {      /* unterminated last line of the range */
+            from[total] = '\n';                          /* body is one byte short of the buffer end */
+            take = ++total;
+            ++*unterminated;
+        }
+        tail_len = total - take;
+        if (tail_len > QK_HEAD) { rc = QK_ERR_ARG; break; } /* a line longer than 128 KiB */
+        memcpy(tail, from + take, tail_len);
+        if (take) rc = qk_submit_raw(ctx, slot, from, take);
+        pthread_mutex_lock(&g.mu);
+        g.submitted = i + 1;
+        pthread_cond_broadcast(&g.cv);
+        pthread_mutex_unlock(&g.mu);
+    }
+    pthread_mutex_lock(&g.mu);
+    if (rc && !g.err) g.err = rc;                        /* stop the readers */
+    pthread_cond_broadcast(&g.cv);
+    pthread_mutex_unlock(&g.mu);
+    for (uint32_t t = 0; t < started; ++t) pthread_join(th[t], NULL);
+    free(tail);
+    pthread_mutex_destroy(&g.mu);
+    pthread_cond_destroy(&g.cv);
+    return rc ? rc : g.err;
+}
+
+static uint32_t reader_threads_default(void)
+{
+    const char *e = getenv("QK_READER_THREADS");
+    int n = e ? atoi(e) : 4;
+    return n < 1 ? 1u : (uint32_t)n;
+}
+
+int qk_count_raw_file_mt(qk_ctx *ctx, const char *reads_path, uint32_t threads, qk_framer_stats *st)
 {
     int fd = open(reads_path, O_RDONLY);
     if (fd < 0) return QK_ERR_IO;
-    int seekable = lseek(fd, 0, SEEK_CUR) != (off_t)-1;
-    int rc = qk_count_raw_fd(ctx, fd, seekable, st);
+    struct stat sb;
+    size_t cap = 0;
+    qk_ctx_info(ctx, NULL, &cap);
+    if (fstat(fd, &sb) != 0 || !S_ISREG(sb.st_mode) || sb.st_size == 0 || cap < 4 * QK_HEAD) {
+        /* pipe, device, empty file, or slots too small for the headroom: sequential path */
+        int seekable = lseek(fd, 0, SEEK_CUR) != (off_t)-1;
+        int rc = qk_count_raw_fd(ctx, fd, seekable, st);
+        close(fd);
+        return rc;
+    }
+    uint8_t first = 0;
+    int fastq = 0, skip_first = 0;
+    int rc = pread(fd, &first, 1, 0) == 1 ? QK_OK : QK_ERR_IO;
+    if (!rc) {
+        raw_mode(first, 1, &fastq, &skip_first);
+        rc = qk_raw_begin(ctx, fastq, skip_first);
+    }
+    uint64_t unterminated = 0;
+    if (!rc) rc = count_range_mt(ctx, fd, 0, (uint64_t)sb.st_size, threads ? threads : reader_threads_default(), &unterminated);
     close(fd);
-    return rc;
+    if (rc) return rc;
+    return raw_finish(ctx, st, (uint64_t)sb.st_size, unterminated, fastq);
+}
+
+int qk_count_raw_file(qk_ctx *ctx, const char *reads_path, qk_framer_stats *st)
+{
+    return qk_count_raw_file_mt(ctx, reads_path, 0, st);
 }
 
 /* ------------------------------------------------------------------ command ---------- */
@@ -434,7 +696,7 @@ static void help_count(void)
 {
     puts("\nquicKmer2 count [Options] ref.fa sample.fast[a/q] Out_prefix\n\nOptions:");
     puts("-h\t\tShow this help information");
-    puts("-t [num]\tNumber of threads (accepted for compatibility; counting runs on the GPU)");
+    puts("-t [num]\tNumber of threads reading the input into pinned memory (counting runs on the GPU)");
     puts("-g [num]\tCUDA device index (default 0)");
 }
 
@@ -486,7 +748,7 @@ int qk_count_main(int argc, char **argv)
 
     double t0 = now_sec();
     qk_ctx *ctx = NULL;
-    int rc = qk_ctx_create(&ctx, device, 4, (size_t)32 << 20);
+    int rc = qk_ctx_create(&ctx, device, 8, (size_t)32 << 20);
     if (rc) {
         printf("GPU context failed: %s\n", ctx ? qk_last_error(ctx) : "no CUDA device");
         qk_ctx_destroy(ctx);
@@ -509,8 +771,9 @@ int qk_count_main(int argc, char **argv)
         rc = qk_count_framer(ctx, fr, &st);
         qk_framer_close(fr);
     } else {
-        rc = qk_count_raw_fd(ctx, reads_fd, reads_seekable, &st);
         close(reads_fd);
+        (void)reads_seekable;
+        rc = qk_count_raw_file_mt(ctx, reads, threads, &st); /* -t N: reader threads (0 = default) */
     }
     uint64_t total = 0, hits = 0;
     if (!rc) rc = qk_stats(ctx, &total, &hits, NULL);

@@ -36,6 +36,13 @@ def load_package():
     return mod
 
 
+def load_dist():
+    """quick-mer2_b200/dist.py as quickmer2_b200.dist."""
+    import importlib
+    load_package()
+    return importlib.import_module("quickmer2_b200.dist")
+
+
 @pytest.fixture(scope="session")
 def built():
     """Build everything that can be built on this machine (nvcc cross-compiles without a GPU)."""

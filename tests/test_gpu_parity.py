@@ -324,6 +324,52 @@ def test_pinned_source_is_dmaed_directly(mid_dict, qk, oracle, synth, tmp_path):
         assert st["lines"] == ost["lines"] == 100000 and st["total_kmers"] == ost["total_kmers"]
 
 
+# ------------------------------------------------------------------ sharded file -----------
+@pytest.mark.parametrize("world", [2, 3, 5])
+@pytest.mark.parametrize("kind", ["fastq", "fasta", "fastq_out_of_phase"])
+def test_sharded_file_equals_whole_file(kind, world, mid_dict, qk, oracle, synth, tmp_path):
+    """One reads file cut into `world` line-aligned shards, each counted by its own context
+    (the ranks of quick-mer2_b200/dist.py, emulated one after another on this GPU), counters
+    added: must equal the reference's whole-file result, for FASTQ through the guessed line
+    state and -- when the guess is wrong -- through the verify-and-recount loop."""
+    from conftest import load_dist
+    qd = load_dist()
+    reads = tmp_path / ("r.fa" if kind == "fasta" else "r.fq")
+    synth("reads", "--ref", mid_dict / "ref.fa", "--out", reads, "--n", 30000, "--len", 150, "--seed", 77,
+          *(["--fastq", "--rand-qual"] if kind != "fasta" else []))
+    if kind == "fastq_out_of_phase":                      # '>' where a read is expected shifts the phase (Q.c:398)
+        data = reads.read_bytes()
+        cut = data.index(b"\n@", len(data) // 10) + 1
+        reads.write_bytes(data[:cut] + b"@odd\n>not a read\n+\nIIII\n" + data[cut:])
+    want, ost = oracle.count_bin(mid_dict / "ref.fa.qm", reads)
+    plans = [qd.shard_plan(qk, reads, r, world) for r in range(world)]
+    ctxs = [qk.Context(n_slots=2, chunk_capacity=1 << 20) for _ in range(world)]
+    try:
+        finals, stats = [], []
+        for ctx, p in zip(ctxs, plans):
+            ctx.load_dictionary(mid_dict / "ref.fa.qm")
+            st, fin = ctx.count_range(reads, p["begin"], p["end"], p["fastq"], p["state"])
+            finals.append(fin); stats.append(st)
+        recounts = 0
+        while True:
+            bad = qd.first_wrong_guess([p["state"] for p in plans], finals, [p["end"] - p["begin"] for p in plans])
+            if bad is None:
+                break
+            recounts += 1
+            assert recounts <= world
+            plans[bad]["state"] = finals[bad - 1]
+            ctxs[bad].reset()
+            stats[bad], finals[bad] = ctxs[bad].count_range(reads, plans[bad]["begin"], plans[bad]["end"], True, plans[bad]["state"])
+        total = sum(c.counters().astype(np.int64) for c in ctxs)
+        assert np.array_equal(qd.wrap16(total), want)
+        assert sum(s["lines"] for s in stats) == ost["lines"]
+        assert sum(c.stats()["total_kmers"] for c in ctxs) == ost["total_kmers"]
+        assert (recounts > 0) == (kind == "fastq_out_of_phase")
+    finally:
+        for c in ctxs:
+            c.close()
+
+
 # ------------------------------------------------------------------ properties at size -----
 def test_properties_at_size(qk, synth, tmp_path):
     """16 Mb dictionary, 2 M reads (~240 M k-mers): too slow for the oracle in a unit test, so
