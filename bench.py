@@ -62,6 +62,29 @@ WORKLOADS = {
         reads=["--n", 1000000, "--len", 150, "--err-ppm", 2000], fastq=False, seed=42,
         sample_reads=1000000,
         desc="1 Mb ref, k=30 (4Mi-slot .qm), 1M x 150bp FASTA"),
+    # config 4 shape: HiFi-like reads (log-normal, median 15 kb, up to the 99,998-base line limit,
+    # some past the 65,536 run-counter wrap) against the config-2 dictionary, FASTA as the
+    # documented samtools|awk pipe produces it
+    "hifi": dict(
+        ref=["--bases", 64000000, "--contigs", 4, "--seed", 2024, "--segdups", 200, "--segdup-len", 20000,
+             "--divergence-ppm", 10000, "--nblock", 50000],
+        dict=["--k", 30, "--slots", "128M", "--ctrl-block", 100000],
+        reads=["--n", 128000, "--len", 15000, "--hifi", "--max-len", 99998, "--min-len", 1000, "--err-ppm", 1000],
+        fastq=False, seed=42, sample_reads=12800,
+        desc="config-2 dictionary, 30x HiFi-like reads (median 15 kb, max 99,998), FASTA"),
+    # config 5: k sweep and a sparse (1/10) dictionary that sits near the L2 size
+    **{f"k{k}": dict(
+        ref=["--bases", 64000000, "--contigs", 4, "--seed", 2024, "--segdups", 200, "--segdup-len", 20000,
+             "--divergence-ppm", 10000, "--nblock", 50000],
+        dict=["--k", k, "--slots", "128M", "--ctrl-block", 100000],
+        reads=["--n", 12800000, "--len", 150, "--err-ppm", 2000, "--fastq"], fastq=True, seed=42,
+        sample_reads=1600000, desc=f"config-2 reference and reads, k={k}") for k in (20, 25, 31)},
+    "sparse10": dict(
+        ref=["--bases", 64000000, "--contigs", 4, "--seed", 2024, "--segdups", 200, "--segdup-len", 20000,
+             "--divergence-ppm", 10000, "--nblock", 50000],
+        dict=["--k", 30, "--slots", "128M", "--ctrl-block", 100000], sparse=10,
+        reads=["--n", 12800000, "--len", 150, "--err-ppm", 2000, "--fastq"], fastq=True, seed=42,
+        sample_reads=1600000, desc="config-2 reference and reads, dictionary thinned 1/10 by the reference's `sparse` (5.8M k-mers)"),
     "tiny": dict(
         ref=["--bases", 300000, "--contigs", 2, "--seed", 5],
         dict=["--k", 30, "--ctrl-block", 10000],
@@ -137,7 +160,17 @@ def prepare(name, cdir, rank_seed_offset=0, sample=False):
         os.replace(tmp, ref)
         synth("dict", "--ref", ref, "--out", d / "tmpdict", "--threads", min(16, os.cpu_count() or 1), *w["dict"])
         os.replace(d / "tmpdict.qgc", d / "ref.fa.qgc")
-        os.replace(d / "tmpdict.qm", d / "ref.fa.qm")
+        if w.get("sparse"):          # thin with the reference's own `sparse` (Q.c:1306-1483): writes ref.fa.rqm
+            os.replace(d / "tmpdict.qm", d / "full.fa.qm")
+            os.symlink(ref, d / "full.fa")
+            res = subprocess.run([str(REF_BIN), "sparse", str(w["sparse"]), "full.fa"], cwd=d, capture_output=True, text=True)
+            if res.returncode or not (d / "full.fa.rqm").exists():
+                raise RuntimeError("reference sparse failed: " + res.stdout[-300:])
+            (d / "full.fa.qm").unlink()
+            (d / "ref.fa.qgc").unlink()   # ordinals changed; the bench does not use it
+            os.replace(d / "full.fa.rqm", d / "ref.fa.qm")
+        else:
+            os.replace(d / "tmpdict.qm", d / "ref.fa.qm")
     ensure(d / "ref.fa.qm", make_dict)
     ext = "fq" if w["fastq"] else "fa"
     seed = w["seed"] + rank_seed_offset
@@ -335,7 +368,7 @@ def gpu_arm(args):
     d, ref, reads = prepare(args.workload, cdir, rank)
 
     chunk_cap = args.chunk_mib << 20
-    ctx = qk.Context(device=local, n_slots=4, chunk_capacity=chunk_cap)
+    ctx = qk.Context(device=local, n_slots=8, chunk_capacity=chunk_cap)
     t0 = time.perf_counter()
     if rank == 0:
         n_kmers = ctx.load_dictionary(ref.with_suffix(".fa.qm"))
@@ -465,6 +498,14 @@ def gpu_arm(args):
         h2d_ms_step = ctx.timing()["h2d_ms"]
         raw_s = timed_host(job_raw, e2e_steps, 1)
 
+    # ---- e2e from a FILE (page cache): reader threads pread() into the pinned slots ---------
+    file_s = None
+    if world == 1 and not args.kernel_only:
+        def job_file():
+            ctx.reset()
+            ctx.count_file(reads, threads=args.reader_threads)
+        file_s = timed_host(job_file, 2, 1)
+
     if rank != 0:
         ctx.close()
         if world > 1:
@@ -523,6 +564,9 @@ def gpu_arm(args):
         "e2e_preframed": {"value": job_kmers / pre_s, "unit": "k-mers/s", "h2d_gbs": n_framed / pre_s / 1e9,
                           "h2d_ms_per_step": h2d_ms_step,
                           "path": "pre-framed pinned host chunks -> qk_submit (H2D + kernel per chunk) -> qk_finish"},
+        "e2e_file": None if file_s is None else {
+            "value": job_kmers / file_s, "unit": "k-mers/s", "file_gbs": raw_np.size / file_s / 1e9, "reader_threads": args.reader_threads,
+            "path": "reads FILE (page cache) -> qk_count_raw_file_mt (pread into pinned slots, H2D, device framing, count) -> qk_finish"},
         "gpu_launches": launches * args.steps,
         "clocks": clocks,
         "roofline": roofline,
@@ -547,6 +591,7 @@ def main():
     ap.add_argument("--cache-dir", default=None)
     ap.add_argument("--chunk-mib", type=int, default=64)
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--reader-threads", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--kernel-only", action="store_true",
                     help="device-resident leg only (no e2e, micro-benchmarks or CPU leg): for ncu and quick iteration")
