@@ -2,7 +2,9 @@
 //
 // Table layout in HBM (DESIGN.md "data layout"):
 //   bucket  = 4 x uint64 entries = one 32-byte sector, fetched with one LDG.E.256
-//   entry   = (remainder << ord_bits) | (ordinal + 1), 0 = empty
+//   entry   = (remainder << ord_bits) | (ordinal + 1), 0 = empty; bit 63 is spare (rem_bits +
+//              ord_bits <= 63, ord_bits <= 32), so the probe compares the high words with one
+//              32-bit op and the low words with another
 //   key     -> h = mix60(key) (a bijection on [0, 2^60)); bucket = top bucket_bits of h,
 //              remainder = low rem_bits = 60 - bucket_bits of h (quotienting: the bucket
 //              index is implied, so remainder + ordinal fit one 64-bit word)
@@ -97,15 +99,14 @@ int qk_cuda_fail(qk_ctx *ctx, cudaError_t e, const char *what);
 // ---- 60-bit bijective mixer ---------------------------------------------------------
 // xorshift and odd multiplication are both invertible mod 2^60, so distinct keys map to
 // distinct (bucket, remainder) pairs and the remainder identifies the key in its bucket.
+// One round is enough here: the bucket index is the TOP bits of the product, which depend on
+// every bit of the input; the remainder (low bits) only has to be a bijection, not mixed.
+// (Build-time check: the stash fill matches the Poisson expectation, tests/test_gpu_parity.py.)
 #define QK_M60 0x0FFFFFFFFFFFFFFFull
 __host__ __device__ __forceinline__ uint64_t qk_mix60(uint64_t x)
 {
     x ^= x >> 31;
-    x = (x * 0x9E3779B97F4A7C15ull) & QK_M60;
-    x ^= x >> 29;
-    x = (x * 0xBF58476D1CE4E5B9ull) & QK_M60;
-    x ^= x >> 32;
-    return x;
+    return (x * 0x9E3779B97F4A7C15ull) & QK_M60;
 }
 // second, independent hash for the stash
 __host__ __device__ __forceinline__ uint64_t qk_mix_stash(uint64_t x)

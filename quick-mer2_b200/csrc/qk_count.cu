@@ -126,6 +126,7 @@ __device__ __noinline__ uint32_t qk_stash_find(const qk_table_view &tv, uint64_t
 __global__ void __launch_bounds__(QK_THREADS, 3) qk_count_kernel(const qk_count_args a)
 {
     __shared__ uint64_t s_codes[2][QK_WORDS + 1]; // [0] = halo: the 32 bases before the tile
+    __shared__ uint64_t s_rc[2][QK_WORDS + 1];    // the same bases complemented, in reverse order
     __shared__ uint32_t s_mask[2][QK_WORDS];      // reset flags, bit j of word w = byte 32w+j
     __shared__ int s_last[2][QK_WORDS];           // last reset before word w (chunk position)
     __shared__ int s_red[QK_THREADS / 32];
@@ -162,13 +163,14 @@ __global__ void __launch_bounds__(QK_THREADS, 3) qk_count_kernel(const qk_count_
             if (base >= 32)
                 halo = ((uint64_t)qk_codes16(qk_load16(bytes, base - 32, n)) << 32) | qk_codes16(qk_load16(bytes, base - 16, n));
             s_codes[(tile0 & 1) ^ 1][QK_WORDS] = halo; // where the "previous tile" leaves its last word
+            s_rc[(tile0 & 1) ^ 1][QK_WORDS] = qk_rev_pairs(halo) ^ 0xAAAAAAAAAAAAAAAAull;
         }
     }
 
     const qk_table_view tv = a.tv;
     const uint32_t k = tv.k;
     const uint64_t rem_mask = ((uint64_t)1 << tv.rem_bits) - 1;
-    const uint64_t ord_mask = ((uint64_t)1 << tv.ord_bits) - 1;
+    const uint32_t ord_mask = tv.ord_bits >= 32 ? 0xFFFFFFFFu : (1u << tv.ord_bits) - 1; // ord_bits <= 32
     uint32_t n_emit = 0, n_hit = 0;
 
     uint4 cur = qk_load16(bytes, tile0 * QK_TILE + tid * 16, n);
@@ -176,9 +178,21 @@ __global__ void __launch_bounds__(QK_THREADS, 3) qk_count_kernel(const qk_count_
         const uint32_t buf = tile & 1;
         const uint32_t base = tile * QK_TILE;
         __syncthreads(); // previous tile's readers are done with buf; s_carry / halo visible
-        reinterpret_cast<uint32_t *>(s_codes[buf])[2 + (tid ^ 1)] = qk_codes16(cur);
+        {
+            // forward codes: first base of the word in the top pair; reverse-complement stream:
+            // complemented codes ((L-2)&3 = L^2, Q.c:414), first base of the word in the BOTTOM
+            // pair -- so both strands of the window ending at p are one funnel shift away
+            const uint32_t c = qk_codes16(cur);
+            uint32_t z = __brev(c);
+            z = ((z & 0x55555555u) << 1) | ((z >> 1) & 0x55555555u);
+            reinterpret_cast<uint32_t *>(s_codes[buf])[2 + (tid ^ 1)] = c;
+            reinterpret_cast<uint32_t *>(s_rc[buf])[2 + tid] = z ^ 0xAAAAAAAAu;
+        }
         reinterpret_cast<uint16_t *>(s_mask[buf])[tid] = (uint16_t)qk_resets16(cur);
-        if (tid == 0) s_codes[buf][0] = s_codes[buf ^ 1][QK_WORDS];
+        if (tid == 0) {
+            s_codes[buf][0] = s_codes[buf ^ 1][QK_WORDS];
+            s_rc[buf][0] = s_rc[buf ^ 1][QK_WORDS];
+        }
         if (tile + 1 < tile_end) cur = qk_load16(bytes, base + QK_TILE + tid * 16, n); // prefetch
         __syncthreads();
         if (warp == 0) { // exclusive max-scan of the per-word last reset
@@ -230,9 +244,11 @@ __global__ void __launch_bounds__(QK_THREADS, 3) qk_count_kernel(const qk_count_
                 const uint32_t sh = 2 * (31 - lane);
                 const uint64_t x = (B >> sh) | ((A << 1) << (63 - sh)); // 32 bases ending at p
                 const uint64_t fwd = x & tv.kmask;
-                const uint32_t keep = min(r, 30u);
-                uint64_t rc = (qk_rev_pairs(x & QK_M60) >> 4) ^ 0x0AAAAAAAAAAAAAAAull;
-                rc &= QK_M60 & ~(((uint64_t)1 << (60 - 2 * keep)) - 1);
+                const uint64_t RA = s_rc[buf][w], RB = s_rc[buf][w + 1];
+                // 32 complemented bases ending at p, newest in the top pair; >> 4 leaves the 30
+                // newest with the newest at bits 59:58 (the reference's 60-bit register)
+                uint64_t rc = ((RB << sh) | ((RA >> 1) >> (63 - sh))) >> 4;
+                if (k < 30) rc &= ~(((uint64_t)1 << (60 - 2 * min(r, 30u))) - 1); // zero fill below the run
                 key[u] = min(fwd, rc);
                 const uint64_t h = qk_mix60(key[u]);
                 bp[u] = tv.buckets + (h >> tv.rem_bits);
@@ -247,15 +263,18 @@ __global__ void __launch_bounds__(QK_THREADS, 3) qk_count_kernel(const qk_count_
             for (int u = 0; u < QK_UNROLL; ++u) {
                 if (!valid[u]) continue;
                 ++n_emit;
-                uint64_t ord1 = 0;
-                bool full = true;
+                // entry == (rem << ord_bits) | ord1: high words equal (bit 63 aside) and the low
+                // words differ only inside the ordinal field, which is then ord1 != 0
+                uint32_t ord1 = 0;
+                const uint32_t qhi = (uint32_t)(q[u] >> 32), qlo = (uint32_t)q[u];
 #pragma unroll
                 for (int e = 0; e < QK_BUCKET_ENTRIES; ++e) {
-                    const uint64_t d = bk[u].e[e] ^ q[u];
-                    if (d - 1 < ord_mask) ord1 = d;
-                    full = full && bk[u].e[e] != 0;
+                    const uint32_t dhi = ((uint32_t)(bk[u].e[e] >> 32) ^ qhi) & 0x7FFFFFFFu;
+                    const uint32_t dlo = (uint32_t)bk[u].e[e] ^ qlo;
+                    if (dhi == 0 && dlo - 1 < ord_mask) ord1 = dlo;
                 }
-                if (ord1 == 0 && full && tv.has_stash) ord1 = qk_stash_find(tv, key[u]);
+                // entries fill a bucket in order, so it is full iff the last one is taken
+                if (ord1 == 0 && bk[u].e[QK_BUCKET_ENTRIES - 1] != 0 && tv.has_stash) ord1 = qk_stash_find(tv, key[u]);
                 if (ord1) {
                     ++n_hit;
                     atomicAdd(a.counters + (ord1 - 1), 1u);

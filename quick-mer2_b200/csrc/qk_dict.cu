@@ -231,6 +231,12 @@ static void qk_geometry(uint64_t n, uint32_t k, uint64_t stash_slots_min, qk_tab
     d->rem_bits = QK_KEY_BITS - d->bucket_bits;
     d->ord_bits = qk_bits_for(n); // holds ordinal + 1 <= n
     if (d->ord_bits == 0) d->ord_bits = 1;
+    while (d->rem_bits + d->ord_bits > 63) { // keep bit 63 of an entry spare: small dictionaries get more buckets
+        nb <<= 1;
+        d->n_buckets = nb;
+        d->bucket_bits = qk_bits_for(nb - 1);
+        d->rem_bits = QK_KEY_BITS - d->bucket_bits;
+    }
     // expected fraction of keys that find their 4-entry bucket full, keys/bucket ~ Poisson(lambda)
     const double lambda = (double)n / (double)nb;
     double p = exp(-lambda), over = 0;
@@ -327,7 +333,7 @@ extern "C" int qk_dict_build(qk_ctx *ctx, uint64_t *n_kmers_out)
 
     for (int attempt = 0; attempt < 4; ++attempt) {
         qk_geometry(total, ctx->k, stash_min, &d);
-        if (d.rem_bits + d.ord_bits > 64) {
+        if (d.rem_bits + d.ord_bits > 63 || d.ord_bits > 32) {
             rc = qk_fail(ctx, QK_ERR_FORMAT, "entry needs %u bits", d.rem_bits + d.ord_bits);
             goto done;
         }
@@ -388,7 +394,8 @@ extern "C" int qk_dict_adopt(qk_ctx *ctx, const qk_table_desc *desc)
     if (!ctx || !desc) return QK_ERR_ARG;
     if (desc->n_buckets == 0 || (desc->n_buckets & (desc->n_buckets - 1)) || desc->stash_slots == 0 ||
         (desc->stash_slots & (desc->stash_slots - 1)) || desc->table_bytes != desc->n_buckets * sizeof(qk_bucket) ||
-        desc->stash_bytes != desc->stash_slots * sizeof(qk_stash_entry) || desc->rem_bits + desc->ord_bits > 64 ||
+        desc->stash_bytes != desc->stash_slots * sizeof(qk_stash_entry) || desc->rem_bits + desc->ord_bits > 63 ||
+        desc->ord_bits > 32 ||
         desc->rem_bits + desc->bucket_bits != QK_KEY_BITS || desc->k < 1 || desc->k > 32)
         return qk_fail(ctx, QK_ERR_ARG, "inconsistent table descriptor");
     QK_CUDA(ctx, cudaSetDevice(ctx->device));
