@@ -84,6 +84,10 @@ typedef struct qk_table_desc {
     uint32_t rem_bits;       /* 60 - bucket_bits                                 */
     uint64_t skipped_keys;   /* dictionary keys no read can produce (>= 2^60) or
                                 shadowed duplicates; their ordinals stay 0       */
+    uint64_t ext_bytes;      /* bytes of each 2-bit-per-ordinal extension array  */
+    uint64_t cont_bytes;     /* bytes of the 1-bit-per-ordinal continuation array */
+    uint32_t has_ext;        /* 1: dictionary-order extension arrays present (k = 30) */
+    uint32_t reserved;
 } qk_table_desc;
 
 int qk_dict_describe(const qk_ctx *ctx, qk_table_desc *desc);
@@ -92,6 +96,9 @@ int qk_dict_describe(const qk_ctx *ctx, qk_table_desc *desc);
 int qk_dict_adopt(qk_ctx *ctx, const qk_table_desc *desc);
 /* Device pointers of the table image (for NCCL broadcast / peer copies). */
 int qk_dict_device_ptrs(const qk_ctx *ctx, void **table, void **stash);
+/* ... and of the extension arrays (NULL when has_ext == 0): last base and first base of every
+ * dictionary k-mer in its walking orientation (ext_bytes each), continuation bits (cont_bytes). */
+int qk_dict_ext_ptrs(const qk_ctx *ctx, void **last, void **first, void **cont);
 
 /* ------------------------------------------------------------------ counting --------
  * A chunk is a run of SEQUENCE LINES ONLY, each terminated by '\n', each at most
@@ -138,6 +145,9 @@ int qk_sync(qk_ctx *ctx);
 /* Running totals (call after qk_sync): emitted k-mers = the reference's process_kmers
  * ("total %lu kmers", Q.c:445,481), dictionary hits, and sequence lines seen. */
 int qk_stats(qk_ctx *ctx, uint64_t *total_kmers, uint64_t *hits, uint64_t *lines);
+/* How many of the hits were derived from a neighbouring k-mer through the dictionary-order
+ * extension arrays instead of a table probe (0 when the dictionary has none, k != 30). */
+int qk_stats_ext(qk_ctx *ctx, uint64_t *verified_by_extension);
 
 /* Device pointer of the per-ordinal uint32 counters (n_kmers entries), for an NCCL
  * reduce across GPUs; the low 16 bits are the reference's uint16 depth (Q.c:23,291). */

@@ -56,6 +56,10 @@ class TableDesc(C.Structure):
         ("ord_bits", C.c_uint32),
         ("rem_bits", C.c_uint32),
         ("skipped_keys", C.c_uint64),
+        ("ext_bytes", C.c_uint64),
+        ("cont_bytes", C.c_uint64),
+        ("has_ext", C.c_uint32),
+        ("reserved", C.c_uint32),
     ]
 
     def as_dict(self):
@@ -98,6 +102,7 @@ SIGNATURES = {
     "qk_dict_describe": (C.c_int, [_P, C.POINTER(TableDesc)]),
     "qk_dict_adopt": (C.c_int, [_P, C.POINTER(TableDesc)]),
     "qk_dict_device_ptrs": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),
+    "qk_dict_ext_ptrs": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     "qk_slot_host_buffer": (_P, [_P, C.c_uint32]),
     "qk_submit": (C.c_int, [_P, C.c_uint32, _P, C.c_size_t, _P, C.c_uint32]),
     "qk_submit_device": (C.c_int, [_P, C.c_uint32, _P, C.c_size_t]),
@@ -110,6 +115,7 @@ SIGNATURES = {
     "qk_wait_slot": (C.c_int, [_P, C.c_uint32]),
     "qk_sync": (C.c_int, [_P]),
     "qk_stats": (C.c_int, [_P, _U64P, _U64P, _U64P]),
+    "qk_stats_ext": (C.c_int, [_P, _U64P]),
     "qk_counters_device_ptr": (C.c_int, [_P, C.POINTER(_P), _U64P]),
     "qk_reset_counters": (C.c_int, [_P]),
     "qk_counters_download": (C.c_int, [_P, C.c_uint64, _P, C.c_uint64]),
@@ -256,6 +262,17 @@ class Context:
         self._check(self._lib.qk_dict_device_ptrs(self._h, C.byref(t), C.byref(s)))
         return t.value, s.value
 
+    def table_images(self):
+        """(device pointer, bytes) of everything a replica needs: table, stash, extension arrays."""
+        d = self.table_desc()
+        t, s = self.table_device_ptrs()
+        out = [(t, int(d.table_bytes)), (s, int(d.stash_bytes))]
+        if d.has_ext:
+            a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+            self._check(self._lib.qk_dict_ext_ptrs(self._h, C.byref(a), C.byref(b), C.byref(c)))
+            out += [(a.value, int(d.ext_bytes)), (b.value, int(d.ext_bytes)), (c.value, int(d.cont_bytes))]
+        return out
+
     def counters_device_ptr(self):
         p, n = C.c_void_p(), C.c_uint64()
         self._check(self._lib.qk_counters_device_ptr(self._h, C.byref(p), C.byref(n)))
@@ -307,7 +324,9 @@ class Context:
     def stats(self) -> dict:
         t, h, l = C.c_uint64(), C.c_uint64(), C.c_uint64()
         self._check(self._lib.qk_stats(self._h, C.byref(t), C.byref(h), C.byref(l)))
-        return {"total_kmers": t.value, "hits": h.value, "lines": l.value}
+        e = C.c_uint64()
+        self._check(self._lib.qk_stats_ext(self._h, C.byref(e)))
+        return {"total_kmers": t.value, "hits": h.value, "lines": l.value, "ext_verified": e.value}
 
     def timing(self) -> dict:
         k, h, n = C.c_double(), C.c_double(), C.c_uint64()

@@ -39,6 +39,8 @@ struct qk_table_view {
     uint32_t rem_bits;        // 60 - bucket_bits
     uint32_t ord_bits;
     uint32_t has_stash;       // stash_used != 0
+    const uint32_t *ext_last, *ext_first, *ext_cont; // NULL unless k = 30
+    uint64_t n_kmers;
 };
 
 struct qk_timing_pair { cudaEvent_t a, b; int kind; /* 0 = h2d, 1 = kernel */ };
@@ -70,6 +72,7 @@ struct qk_ctx {
 
     qk_bucket *buckets;
     qk_stash_entry *stash;
+    uint32_t *ext_last, *ext_first, *ext_cont; // dictionary-order extension arrays (k = 30), else NULL
     qk_table_desc desc;
 
     uint32_t *counters;       // n_kmers x u32, indexed by ordinal

@@ -111,13 +111,17 @@ __device__ __forceinline__ uint64_t qk_rev_pairs(uint64_t x)
 }
 
 // stash probe: linear over 16-byte entries; returns ordinal + 1 or 0
-__device__ __noinline__ uint32_t qk_stash_find(const qk_table_view &tv, uint64_t key)
+// (the strand bit of the entry comes back in bit 0 of *strand)
+__device__ __noinline__ uint32_t qk_stash_find(const qk_table_view &tv, uint64_t key, uint32_t *strand = nullptr)
 {
     uint64_t s = qk_mix_stash(key) & tv.stash_mask;
     for (;;) {
         const uint4 v = __ldg(reinterpret_cast<const uint4 *>(tv.stash + s));
         const uint64_t sk = ((uint64_t)v.y << 32) | v.x;
-        if (sk == key) return v.z;
+        if (sk == key) {
+            if (strand) *strand = v.w & 1u;
+            return v.z;
+        }
         if (sk == 0) return 0;
         s = (s + 1) & tv.stash_mask;
     }
@@ -293,6 +297,288 @@ __global__ void __launch_bounds__(QK_THREADS, 3) qk_count_kernel(const qk_count_
     }
 }
 
+
+// =============================================================================================
+// qk_count_ext_kernel -- the same result with far fewer table probes (k = 30).
+//
+// The probe is the expensive part: one random 32-byte sector = one DRAM row activation, and
+// HBM3e sustains ~42 G of those per second whatever the load instruction (profiles/).  But
+// the k-mers of a read are not independent: consecutive positions are consecutive dictionary
+// ordinals wherever the read matches the reference.  The build pass (qk_orient_insert_kernel)
+// left, per ordinal o, the last/first base of the dictionary k-mer F_o in a walking orientation
+// and a bit cont[o] = "F_o is F_{o-1} shifted by one base".  So here a thread owns QK_RUN = 16
+// consecutive positions, probes the table for the FIRST emitting one only (the anchor), and
+// derives the neighbours from it:
+//     anchor k-mer f, key = K_o.  Same strand as F_o (strand bit == (key == fwd)):
+//         f shifted by read base b equals F_{o+1}  iff  cont[o+1] and b == last[o+1]
+//     opposite strand:
+//         f shifted by b equals rc(F_{o-1})        iff  cont[o] and comp(b) == first[o-1]
+// i.e. position anchor+i has ordinal o+i (o-i) as long as every step so far held -- an exact
+// statement about keys, not a heuristic.  All 15 steps are checked at once with bit-parallel
+// compares of 30-bit fields.  Positions after the first failed step (sequencing error, N,
+// end of a unique stretch) are probed individually as before; an anchor that misses leaves
+// its whole run to individual probes.  Per thread: 1 probe + the failures instead of 16.
+#define QK_RUN 16
+
+__device__ __forceinline__ uint32_t qk_rev16pairs(uint32_t c)
+{
+    uint32_t z = __brev(c);
+    return ((z & 0x55555555u) << 1) | ((z >> 1) & 0x55555555u);
+}
+// 15 two-bit fields starting at ordinal q of a packed array (ordinal q in bits 1:0)
+__device__ __forceinline__ uint32_t qk_extract30(const uint32_t *__restrict__ arr, uint64_t q)
+{
+    const uint32_t lo = __ldg(arr + (q >> 4)), hi = __ldg(arr + (q >> 4) + 1);
+    return __funnelshift_r(lo, hi, 2 * (uint32_t)(q & 15)) & 0x3FFFFFFFu;
+}
+// 15 one-bit fields starting at ordinal q
+__device__ __forceinline__ uint32_t qk_extract15(const uint32_t *__restrict__ arr, uint64_t q)
+{
+    const uint32_t lo = __ldg(arr + (q >> 5)), hi = __ldg(arr + (q >> 5) + 1);
+    return __funnelshift_r(lo, hi, (uint32_t)(q & 31)) & 0x7FFFu;
+}
+
+struct qk_probe {
+    const qk_bucket *bp;
+    uint64_t key, q;
+};
+__device__ __forceinline__ qk_probe qk_probe_prepare(const qk_table_view &tv, uint64_t key)
+{
+    qk_probe p;
+    const uint64_t h = qk_mix60(key);
+    p.key = key;
+    p.bp = tv.buckets + (h >> tv.rem_bits);
+    p.q = (h & (((uint64_t)1 << tv.rem_bits) - 1)) << tv.ord_bits;
+    return p;
+}
+// ordinal + 1 of the probed key (0 = absent); *strand = strand bit of its entry
+__device__ __forceinline__ uint32_t qk_probe_resolve(const qk_table_view &tv, const qk_probe &p, const qk_bucket &bk,
+                                                     uint32_t ord_mask, uint32_t *strand)
+{
+    uint32_t ord1 = 0;
+    const uint32_t qhi = (uint32_t)(p.q >> 32), qlo = (uint32_t)p.q;
+#pragma unroll
+    for (int e = 0; e < QK_BUCKET_ENTRIES; ++e) {
+        const uint32_t ehi = (uint32_t)(bk.e[e] >> 32);
+        const uint32_t dlo = (uint32_t)bk.e[e] ^ qlo;
+        if (((ehi ^ qhi) & 0x7FFFFFFFu) == 0 && dlo - 1 < ord_mask) {
+            ord1 = dlo;
+            *strand = ehi >> 31;
+        }
+    }
+    if (ord1 == 0 && bk.e[QK_BUCKET_ENTRIES - 1] != 0 && tv.has_stash) ord1 = qk_stash_find(tv, p.key, strand);
+    return ord1;
+}
+
+__global__ void __launch_bounds__(QK_THREADS, 4) qk_count_ext_kernel(const qk_count_args a)
+{
+    __shared__ uint64_t s_codes[2][QK_WORDS + 1]; // [0] = halo: the 32 bases before the tile
+    __shared__ uint32_t s_mask[2][QK_WORDS + 1];  // reset flags; [0] = halo word
+    __shared__ int s_last[2][QK_WORDS];           // last reset before word w (chunk position)
+    __shared__ int s_red[QK_THREADS / 32];
+    __shared__ int s_carry;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tile0 = blockIdx.x * a.tiles_per_cta;
+    if (tile0 >= a.n_tiles) return;
+    const uint32_t tile_end = min(tile0 + a.tiles_per_cta, a.n_tiles);
+    const uint8_t *__restrict__ bytes = a.bytes;
+    const uint32_t n = a.n_bytes;
+
+    // ---- span start: last reset before the span, halo codes and halo reset bits --------------
+    {
+        int found = QK_NONE;
+        uint32_t pos = tile0 * QK_TILE;
+        while (pos > 0 && found == QK_NONE) {
+            pos -= QK_TILE;
+            const uint32_t at = pos + tid * 16;
+            const uint32_t m = qk_resets16(qk_load16(bytes, at, n));
+            int own = m ? (int)(at + 31 - __clz(m)) : QK_NONE;
+            for (int o = 16; o; o >>= 1) own = max(own, __shfl_xor_sync(0xffffffffu, own, o));
+            if (lane == 0) s_red[warp] = own;
+            __syncthreads();
+            found = s_red[0];
+#pragma unroll
+            for (int w = 1; w < QK_THREADS / 32; ++w) found = max(found, s_red[w]);
+            __syncthreads();
+        }
+        if (tid == 0) {
+            s_carry = (found == QK_NONE) ? -1 : found;
+            uint64_t halo = 0;
+            uint32_t halo_mask = 0xFFFFFFFFu; // before the chunk: as good as resets
+            const uint32_t base = tile0 * QK_TILE;
+            if (base >= 32) {
+                const uint4 h0 = qk_load16(bytes, base - 32, n), h1 = qk_load16(bytes, base - 16, n);
+                halo = ((uint64_t)qk_codes16(h0) << 32) | qk_codes16(h1);
+                halo_mask = qk_resets16(h0) | (qk_resets16(h1) << 16);
+            }
+            s_codes[(tile0 & 1) ^ 1][QK_WORDS] = halo;
+            s_mask[(tile0 & 1) ^ 1][QK_WORDS] = halo_mask;
+        }
+    }
+
+    const qk_table_view tv = a.tv;
+    const uint32_t ord_mask = tv.ord_bits >= 32 ? 0xFFFFFFFFu : (1u << tv.ord_bits) - 1;
+    uint32_t n_emit = 0, n_hit = 0, n_ext = 0;
+    const uint32_t w = tid >> 1, half = tid & 1; // the word and the half of it this thread owns
+
+    uint4 cur = qk_load16(bytes, tile0 * QK_TILE + tid * 16, n);
+    for (uint32_t tile = tile0; tile < tile_end; ++tile) {
+        const uint32_t buf = tile & 1;
+        const uint32_t base = tile * QK_TILE;
+        __syncthreads();
+        const uint32_t my_codes = qk_codes16(cur);           // first base in the top pair
+        const uint32_t my_resets = qk_resets16(cur);
+        reinterpret_cast<uint32_t *>(s_codes[buf])[2 + (tid ^ 1)] = my_codes;
+        reinterpret_cast<uint16_t *>(s_mask[buf])[2 + tid] = (uint16_t)my_resets;
+        if (tid == 0) {
+            s_codes[buf][0] = s_codes[buf ^ 1][QK_WORDS];
+            s_mask[buf][0] = s_mask[buf ^ 1][QK_WORDS];
+        }
+        if (tile + 1 < tile_end) cur = qk_load16(bytes, base + QK_TILE + tid * 16, n); // prefetch
+        __syncthreads();
+        if (warp == 0) { // exclusive max-scan of the per-word last reset (needed for the 16-bit run counter only)
+            int carry = s_carry;
+#pragma unroll
+            for (int i = 0; i < QK_WORDS / 32; ++i) {
+                const uint32_t ww = i * 32 + lane;
+                const uint32_t m = s_mask[buf][ww + 1];
+                int incl = m ? (int)(base + ww * 32 + 31 - __clz(m)) : QK_NONE;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    int up = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl = max(incl, up);
+                }
+                int excl = __shfl_up_sync(0xffffffffu, incl, 1);
+                if (lane == 0) excl = QK_NONE;
+                s_last[buf][ww] = max(carry, excl);
+                carry = max(carry, __shfl_sync(0xffffffffu, incl, 31));
+            }
+            if (lane == 0) s_carry = carry;
+        }
+        __syncthreads();
+
+        // ---- which of my 16 positions end a 30-mer: no reset among the 30 bytes ending there ----
+        const uint64_t A = s_codes[buf][w], B = s_codes[buf][w + 1];
+        const uint64_t M64 = ((uint64_t)s_mask[buf][w + 1] << 32) | s_mask[buf][w];
+        uint64_t S = M64 | (M64 << 1);
+        S |= S << 2; S |= S << 4; S |= S << 8; S |= S << 14;   // bit p: a reset in [p-29, p]
+        const uint32_t sh0 = 32 + 16 * half;
+        uint32_t emit = ~(uint32_t)(S >> sh0) & 0xFFFFu;
+        if (emit == 0) continue;
+        const uint32_t p0 = base + 16 * tid;
+        {   // uint16 cur_chars (Q.c:402): positions whose run length mod 65,536 is below k emit nothing
+            const uint32_t lowhalf = s_mask[buf][w + 1] & 0xFFFFu;
+            const int last0 = (half && lowhalf) ? (int)(base + w * 32 + 31 - __clz(lowhalf)) : s_last[buf][w];
+            const uint32_t r0 = (uint32_t)((int)p0 - last0);
+            if (r0 + 15 >= 65536u) {
+                for (uint32_t j = 0; j < QK_RUN; ++j)
+                    if (((r0 + j) & 0xFFFFu) < 30u) emit &= ~(1u << j);
+                if (emit == 0) continue;
+            }
+        }
+        n_emit += __popc(emit);
+
+        auto key_at = [&](uint32_t j, bool *is_fwd) -> uint64_t {
+            const uint32_t sh = 2 * (31 - (16 * half + j));
+            const uint64_t x = ((B >> sh) | ((A << 1) << (63 - sh))) & QK_M60; // 30 bases ending at p0 + j
+            const uint64_t rc = (qk_rev_pairs(x) >> 4) ^ 0x0AAAAAAAAAAAAAAAull;
+            *is_fwd = x <= rc;
+            return min(x, rc);
+        };
+
+        // ---- anchor: the first emitting position ------------------------------------------------
+        const uint32_t ja = __ffs(emit) - 1;
+        bool a_fwd;
+        const qk_probe ap = qk_probe_prepare(tv, key_at(ja, &a_fwd));
+        const qk_bucket abk = qk_ld_bucket(ap.bp);
+        uint32_t a_strand = 0;
+        const uint32_t a_ord1 = qk_probe_resolve(tv, ap, abk, ord_mask, &a_strand);
+        uint32_t verified = 0;
+        bool plus = true;
+        if (a_ord1) {
+            ++n_hit;
+            const uint64_t oa = a_ord1 - 1;
+            atomicAdd(a.counters + oa, 1u);
+            const uint32_t nsteps = 15 - ja;
+            plus = (a_strand != 0) == a_fwd;
+            if (nsteps && (plus || oa >= 15)) {
+                // read bases of the steps, step i (position ja + i) in bits 2i-1:2i-2
+                uint32_t R = qk_rev16pairs(my_codes) >> (2 * (ja + 1));
+                uint32_t D, Cb;
+                if (plus) {
+                    D = qk_extract30(tv.ext_last, oa + 1);
+                    Cb = qk_extract15(tv.ext_cont, oa + 1);
+                } else {
+                    D = qk_rev16pairs(qk_extract30(tv.ext_first, oa - 15)) >> 2;
+                    Cb = __brev(qk_extract15(tv.ext_cont, oa - 14)) >> 17;
+                    R ^= 0xAAAAAAAAu;
+                }
+                const uint32_t X = D ^ R;
+                const uint32_t mism = (X | (X >> 1)) & 0x15555555u;
+                uint32_t len = mism ? (uint32_t)(__ffs(mism) - 1) >> 1 : 15u;
+                const uint32_t brk = ~Cb & 0x7FFFu;
+                if (brk) len = min(len, (uint32_t)__ffs(brk) - 1);
+                const uint32_t rs = (my_resets & 0xFFFFu) >> (ja + 1);
+                if (rs) len = min(len, (uint32_t)__ffs(rs) - 1);
+                len = min(len, nsteps);
+                verified = ((1u << len) - 1) << (ja + 1);
+            }
+            uint32_t ve = verified & emit;
+            n_hit += __popc(ve);
+            n_ext += __popc(ve);
+            while (ve) {
+                const uint32_t j = __ffs(ve) - 1;
+                ve &= ve - 1;
+                const uint64_t o = plus ? oa + (j - ja) : oa - (j - ja);
+                atomicAdd(a.counters + o, 1u);
+            }
+        }
+
+        // ---- everything else is probed on its own, four at a time --------------------------------
+        uint32_t todo = emit & ~verified & ~(1u << ja);
+        while (todo) {
+            qk_probe pr[4];
+            qk_bucket bk[4];
+            bool on[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                on[u] = todo != 0;
+                const uint32_t j = on[u] ? __ffs(todo) - 1 : 0;
+                todo &= todo - 1;
+                bool f;
+                pr[u] = qk_probe_prepare(tv, key_at(j, &f));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                bk[u].e[0] = bk[u].e[1] = bk[u].e[2] = bk[u].e[3] = 0;
+                if (on[u]) bk[u] = qk_ld_bucket(pr[u].bp);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (!on[u]) continue;
+                uint32_t st;
+                const uint32_t ord1 = qk_probe_resolve(tv, pr[u], bk[u], ord_mask, &st);
+                if (ord1) {
+                    ++n_hit;
+                    atomicAdd(a.counters + (ord1 - 1), 1u);
+                }
+            }
+        }
+    }
+
+    for (int o = 16; o; o >>= 1) {
+        n_emit += __shfl_xor_sync(0xffffffffu, n_emit, o);
+        n_hit += __shfl_xor_sync(0xffffffffu, n_hit, o);
+        n_ext += __shfl_xor_sync(0xffffffffu, n_ext, o);
+    }
+    if (lane == 0) {
+        atomicAdd(a.stats + 0, (unsigned long long)n_emit);
+        atomicAdd(a.stats + 1, (unsigned long long)n_hit);
+        atomicAdd(a.stats + 2, (unsigned long long)n_ext);
+    }
+}
+
 static int qk_table_view_of(qk_ctx *ctx, qk_table_view *tv)
 {
     if (ctx->dict_state != 2) return qk_fail(ctx, QK_ERR_STATE, "no dictionary built on this context");
@@ -305,6 +591,10 @@ static int qk_table_view_of(qk_ctx *ctx, qk_table_view *tv)
     tv->rem_bits = d->rem_bits;
     tv->ord_bits = d->ord_bits;
     tv->has_stash = d->stash_used != 0;
+    tv->ext_last = d->has_ext ? ctx->ext_last : NULL;
+    tv->ext_first = d->has_ext ? ctx->ext_first : NULL;
+    tv->ext_cont = d->has_ext ? ctx->ext_cont : NULL;
+    tv->n_kmers = d->n_kmers;
     return QK_OK;
 }
 
@@ -333,7 +623,10 @@ int qk_launch_count(qk_ctx *ctx, qk_slot *sl, const uint8_t *dev_bytes, size_t n
     rc = qk_ring_push(ctx, sl, 1, &tp);
     if (rc) return rc;
     QK_CUDA(ctx, cudaEventRecord(tp->a, sl->stream));
-    qk_count_kernel<<<grid, QK_THREADS, 0, sl->stream>>>(a);
+    static int classic = -1; // QK_CLASSIC_KERNEL=1: probe every position even when the extension arrays exist
+    if (classic < 0) classic = getenv("QK_CLASSIC_KERNEL") != NULL;
+    if (a.tv.ext_last && !classic) qk_count_ext_kernel<<<grid, QK_THREADS, 0, sl->stream>>>(a);
+    else qk_count_kernel<<<grid, QK_THREADS, 0, sl->stream>>>(a);
     QK_CUDA(ctx, cudaGetLastError());
     QK_CUDA(ctx, cudaEventRecord(tp->b, sl->stream));
     ctx->launches++;

@@ -120,6 +120,9 @@ extern "C" void qk_ctx_destroy(qk_ctx *ctx)
     cudaFree(ctx->raw_next);
     cudaFree(ctx->buckets);
     cudaFree(ctx->stash);
+    cudaFree(ctx->ext_last);
+    cudaFree(ctx->ext_first);
+    cudaFree(ctx->ext_cont);
     cudaFree(ctx->counters);
     cudaFree(ctx->stats);
     cudaFree(ctx->frame_stream);
@@ -208,6 +211,17 @@ extern "C" int qk_stats(qk_ctx *ctx, uint64_t *total_kmers, uint64_t *hits, uint
         QK_CUDA(ctx, cudaMemcpy(f, ctx->frame_stream, sizeof f, cudaMemcpyDeviceToHost));
         *lines = ctx->lines + f[1];
     }
+    return QK_OK;
+}
+
+extern "C" int qk_stats_ext(qk_ctx *ctx, uint64_t *verified_by_extension)
+{
+    if (!ctx || !verified_by_extension) return QK_ERR_ARG;
+    int rc = qk_sync(ctx);
+    if (rc) return rc;
+    unsigned long long h[4];
+    QK_CUDA(ctx, cudaMemcpy(h, ctx->stats, sizeof h, cudaMemcpyDeviceToHost));
+    *verified_by_extension = h[2];
     return QK_OK;
 }
 

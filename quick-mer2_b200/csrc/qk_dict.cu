@@ -21,6 +21,7 @@
 // rejected with QK_ERR_FORMAT.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "qk_common.cuh"
@@ -164,13 +165,13 @@ struct qk_build_params {
     uint32_t rem_bits, ord_bits;
 };
 
-__device__ __forceinline__ void qk_table_insert(const qk_build_params &bp, uint64_t key, uint64_t ord1,
+__device__ __forceinline__ void qk_table_insert(const qk_build_params &bp, uint64_t key, uint64_t ord1, uint32_t strand,
                                                 qk_build_info *info)
 {
     const uint64_t h = qk_mix60(key);
     const uint64_t bucket = h >> bp.rem_bits;
     const uint64_t rem = h & (((uint64_t)1 << bp.rem_bits) - 1);
-    const unsigned long long entry = (rem << bp.ord_bits) | ord1;
+    const unsigned long long entry = ((unsigned long long)strand << 63) | (rem << bp.ord_bits) | ord1;
     unsigned long long *e = bp.buckets[bucket].e;
 #pragma unroll
     for (int i = 0; i < QK_BUCKET_ENTRIES; ++i) {
@@ -182,15 +183,19 @@ __device__ __forceinline__ void qk_table_insert(const qk_build_params &bp, uint6
     uint64_t s = qk_mix_stash(key) & bp.stash_mask;
     for (;;) {
         unsigned long long old = atomicCAS(&bp.stash[s].key, 0ull, (unsigned long long)key);
-        if (old == 0ull) { bp.stash[s].ord1 = (uint32_t)ord1; return; }
+        if (old == 0ull) { bp.stash[s].ord1 = (uint32_t)ord1; bp.stash[s].pad = strand; return; }
         s = (s + 1) & bp.stash_mask;
     }
 }
 
-__global__ void qk_insert_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ next, uint64_t hash_size,
-                                 uint64_t n_split, uint32_t stride_log2, uint64_t first,
-                                 const unsigned long long *__restrict__ dist, const uint32_t *__restrict__ seg_len,
-                                 unsigned long long total, qk_build_params bp, qk_build_info *info)
+// Segment walk #2: every splitter hands out the ordinals of its segment and leaves the key of
+// ordinal o in kbo[o].  Bit 63 flags the ordinals that must never match: keys >= 2^60 (no read
+// can produce them) and the later copies of a duplicated key (Find_hash never reaches them).
+#define QK_KBO_SKIP 0x8000000000000000ull
+__global__ void qk_scatter_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ next, uint64_t hash_size,
+                                  uint64_t n_split, uint32_t stride_log2, uint64_t first,
+                                  const unsigned long long *__restrict__ dist, const uint32_t *__restrict__ seg_len,
+                                  unsigned long long total, unsigned long long *__restrict__ kbo, qk_build_info *info)
 {
     uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (id > n_split) return;
@@ -202,9 +207,90 @@ __global__ void qk_insert_kernel(const uint64_t *__restrict__ keys, const uint32
         uint64_t key = keys[c];
         uint64_t nx = next[c];
         if (key == 0) atomicOr(&info->flags, QK_FLAG_EMPTY_ON_CHAIN);
-        else if ((key >> QK_KEY_BITS) != 0 || !qk_is_primary(keys, hash_size, c, key)) atomicAdd(&info->skipped, 1ull);
-        else qk_table_insert(bp, key, ord + 1, info);
+        if ((key >> QK_KEY_BITS) != 0 || !qk_is_primary(keys, hash_size, c, key)) {
+            atomicAdd(&info->skipped, 1ull);
+            key |= QK_KBO_SKIP;
+        }
+        kbo[ord] = key;
         c = nx;
+    }
+}
+
+// reverse complement of a 30-mer in the reference's encoding (A=0 C=1 T=2 G=3, complement = ^2)
+__device__ __forceinline__ uint64_t qk_rc30(uint64_t x)
+{
+    uint64_t z = __brevll(x);
+    z = ((z & 0x5555555555555555ull) << 1) | ((z >> 1) & 0x5555555555555555ull);
+    return (z >> 4) ^ 0x0AAAAAAAAAAAAAAAull;
+}
+
+// Orientation pass + table insert, in ordinal order.  The dictionary in chain order is a
+// sequence of overlapping k-mers (consecutive reference positions) broken wherever a k-mer
+// was not unique.  For k = 30 (canonical key = min(fwd, rc), both true 30-mers) choose for
+// every ordinal o an orientation F_o in {K_o, rc(K_o)} and record
+//     cont[o]  = 1 iff F_o is F_{o-1} shifted by one base  (F_o >> 2 == F_{o-1} & (2^58-1))
+//     last[o]  = last base of F_o,  first[o] = first base of F_o,  strand[o] = (F_o == K_o)
+// so that the count kernel can walk from one verified k-mer of a read to its neighbours without
+// probing the table (qk_count_ext_kernel).  These are statements about the KEYS alone, so the
+// walk is exact whatever produced the dictionary.  One thread per QK_EXT_BLOCK ordinals; the
+// first ordinal of a block never continues (the price of not chaining the blocks).
+#define QK_EXT_BLOCK 256
+__global__ void qk_orient_insert_kernel(const unsigned long long *__restrict__ kbo, uint64_t n, int with_ext, qk_build_params bp,
+                                        uint32_t *__restrict__ ext_last, uint32_t *__restrict__ ext_first,
+                                        uint32_t *__restrict__ ext_cont, qk_build_info *info)
+{
+    const uint64_t blk = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t begin = blk * QK_EXT_BLOCK;
+    if (begin >= n) return;
+    const uint64_t end = begin + QK_EXT_BLOCK < n ? begin + QK_EXT_BLOCK : n;
+    const uint64_t M58 = ((uint64_t)1 << 58) - 1;
+    bool have_prev = false;
+    uint64_t prevF = 0;
+    uint32_t wl = 0, wf = 0, wc = 0;
+    for (uint64_t o = begin; o < end; ++o) {
+        const uint64_t raw = kbo[o];
+        const uint64_t K = raw & ~QK_KBO_SKIP;
+        uint32_t cont = 0, strand = 1;
+        uint64_t F = K;
+        if (raw & QK_KBO_SKIP) {
+            have_prev = false;
+        } else {
+            if (with_ext) {
+                const uint64_t Kr = qk_rc30(K);
+                if (have_prev) {
+                    const uint64_t want = prevF & M58;
+                    if ((K >> 2) == want) { F = K; cont = 1; }
+                    else if ((Kr >> 2) == want) { F = Kr; cont = 1; }
+                }
+                if (!cont && o + 1 < n) { // a run starts here: face the way the next k-mer continues
+                    const uint64_t nraw = kbo[o + 1];
+                    if (!(nraw & QK_KBO_SKIP)) {
+                        const uint64_t nK = nraw, nKr = qk_rc30(nraw);
+                        if ((nK >> 2) == (K & M58) || (nKr >> 2) == (K & M58)) F = K;
+                        else if ((nK >> 2) == (Kr & M58) || (nKr >> 2) == (Kr & M58)) F = Kr;
+                    }
+                }
+                strand = F == K;
+                prevF = F;
+                have_prev = true;
+            }
+            qk_table_insert(bp, K, o + 1, strand, info);
+        }
+        if (with_ext) {
+            const uint32_t i = (uint32_t)(o - begin);
+            wl |= (uint32_t)(F & 3) << (2 * (i & 15));
+            wf |= (uint32_t)((F >> 58) & 3) << (2 * (i & 15));
+            wc |= cont << (i & 31);
+            if ((i & 15) == 15 || o + 1 == end) {
+                ext_last[o >> 4] = wl;
+                ext_first[o >> 4] = wf;
+                wl = wf = 0;
+            }
+            if ((i & 31) == 31 || o + 1 == end) {
+                ext_cont[o >> 5] = wc;
+                wc = 0;
+            }
+        }
     }
 }
 
@@ -216,15 +302,16 @@ static uint32_t qk_bits_for(uint64_t v) // smallest b with v < 2^b
     return b;
 }
 
-// Geometry for n chain entries: buckets = smallest power of two with <= 2.8 keys per
-// 4-entry bucket on average; the stash is sized from the Poisson overflow expectation.
+// Geometry for n chain entries: buckets = smallest power of two with <= 2.1 keys per
+// 4-entry bucket on average (<= 4 % of the keys overflow into the stash); the stash is sized
+// from the Poisson overflow expectation.
 static void qk_geometry(uint64_t n, uint32_t k, uint64_t stash_slots_min, qk_table_desc *d)
 {
     memset(d, 0, sizeof *d);
     d->n_kmers = n;
     d->k = k;
     uint64_t nb = 1;
-    while ((double)n / (double)nb > 2.8) nb <<= 1;
+    while ((double)n / (double)nb > 2.1) nb <<= 1;
     if (nb < 64) nb = 64;
     d->n_buckets = nb;
     d->bucket_bits = qk_bits_for(nb - 1);
@@ -251,6 +338,11 @@ static void qk_geometry(uint64_t n, uint32_t k, uint64_t stash_slots_min, qk_tab
     d->stash_slots = ss;
     d->table_bytes = nb * sizeof(qk_bucket);
     d->stash_bytes = ss * sizeof(qk_stash_entry);
+    // dictionary-order extension arrays (k = 30 only: for other k the reference's canonical key
+    // mixes a k-mer with a 30-base reverse complement, Q.c:415-420, and is not a walkable k-mer)
+    d->has_ext = (k == 30 && getenv("QK_NO_EXT") == NULL) ? 1 : 0;
+    d->ext_bytes = d->has_ext ? ((n + 15) / 16 + 4) * sizeof(uint32_t) : 0;   // 2 bits per ordinal, padded
+    d->cont_bytes = d->has_ext ? ((n + 31) / 32 + 4) * sizeof(uint32_t) : 0;  // 1 bit per ordinal, padded
 }
 
 static int qk_alloc_table(qk_ctx *ctx, const qk_table_desc *d)
@@ -258,9 +350,21 @@ static int qk_alloc_table(qk_ctx *ctx, const qk_table_desc *d)
     cudaFree(ctx->buckets);
     cudaFree(ctx->stash);
     cudaFree(ctx->counters);
+    cudaFree(ctx->ext_last);
+    cudaFree(ctx->ext_first);
+    cudaFree(ctx->ext_cont);
     ctx->buckets = NULL; ctx->stash = NULL; ctx->counters = NULL;
+    ctx->ext_last = ctx->ext_first = ctx->ext_cont = NULL;
     QK_CUDA(ctx, cudaMalloc((void **)&ctx->buckets, d->table_bytes));
     QK_CUDA(ctx, cudaMalloc((void **)&ctx->stash, d->stash_bytes));
+    if (d->has_ext) {
+        QK_CUDA(ctx, cudaMalloc((void **)&ctx->ext_last, d->ext_bytes));
+        QK_CUDA(ctx, cudaMalloc((void **)&ctx->ext_first, d->ext_bytes));
+        QK_CUDA(ctx, cudaMalloc((void **)&ctx->ext_cont, d->cont_bytes));
+        QK_CUDA(ctx, cudaMemset(ctx->ext_last, 0, d->ext_bytes));
+        QK_CUDA(ctx, cudaMemset(ctx->ext_first, 0, d->ext_bytes));
+        QK_CUDA(ctx, cudaMemset(ctx->ext_cont, 0, d->cont_bytes));
+    }
     QK_CUDA(ctx, cudaMalloc((void **)&ctx->counters, (d->n_kmers + 1) * sizeof(uint32_t)));
     QK_CUDA(ctx, cudaMemset(ctx->counters, 0, (d->n_kmers + 1) * sizeof(uint32_t)));
     QK_CUDA(ctx, cudaMemset(ctx->stats, 0, 4 * sizeof(unsigned long long))); // a new dictionary starts a new count
@@ -298,7 +402,8 @@ extern "C" int qk_dict_build(qk_ctx *ctx, uint64_t *n_kmers_out)
     qk_table_desc d;
     unsigned long long total = 0;
     int cur = 0;
-    uint64_t stash_min = 0;
+    uint64_t stash_min = 0, skipped = 0;
+    unsigned long long *kbo = NULL;
 
     QK_TRY(cudaMalloc((void **)&info, sizeof(qk_build_info)));
     QK_TRY(cudaMemset(info, 0, sizeof(qk_build_info)));
@@ -331,6 +436,23 @@ extern "C" int qk_dict_build(qk_ctx *ctx, uint64_t *n_kmers_out)
         goto done;
     }
 
+    // keys in ordinal order; after this the raw QM11 arrays are no longer needed
+    QK_TRY(cudaMalloc((void **)&kbo, (total + 1) * sizeof(unsigned long long)));
+    QK_TRY(cudaMemset(info, 0, sizeof(qk_build_info)));
+    qk_scatter_kernel<<<(unsigned)((n_split + 1 + 127) / 128), 128>>>(ctx->raw_keys, ctx->raw_next, H, n_split, stride_log2, first,
+                                                                      dist[cur], seg_len, total, kbo, info);
+    QK_TRY(cudaGetLastError());
+    QK_TRY(cudaMemcpy(&hinfo, info, sizeof hinfo, cudaMemcpyDeviceToHost));
+    if (hinfo.flags & QK_FLAG_EMPTY_ON_CHAIN) {
+        rc = qk_fail(ctx, QK_ERR_FORMAT, "the chain passes through an empty slot: not a QM11 chain");
+        goto done;
+    }
+    skipped = hinfo.skipped;
+    cudaFree(ctx->raw_keys);
+    cudaFree(ctx->raw_next);
+    ctx->raw_keys = NULL;
+    ctx->raw_next = NULL;
+
     for (int attempt = 0; attempt < 4; ++attempt) {
         qk_geometry(total, ctx->k, stash_min, &d);
         if (d.rem_bits + d.ord_bits > 63 || d.ord_bits > 32) {
@@ -349,25 +471,23 @@ extern "C" int qk_dict_build(qk_ctx *ctx, uint64_t *n_kmers_out)
         bp.stash_limit = d.stash_slots / 2;
         bp.rem_bits = d.rem_bits;
         bp.ord_bits = d.ord_bits;
-        qk_insert_kernel<<<(unsigned)((n_split + 1 + 127) / 128), 128>>>(ctx->raw_keys, ctx->raw_next, H, n_split, stride_log2,
-                                                                         first, dist[cur], seg_len, total, bp, info);
+        const uint64_t n_blocks = (total + QK_EXT_BLOCK - 1) / QK_EXT_BLOCK;
+        qk_orient_insert_kernel<<<(unsigned)((n_blocks + 63) / 64), 64>>>(kbo, total, (int)d.has_ext, bp, ctx->ext_last,
+                                                                          ctx->ext_first, ctx->ext_cont, info);
         QK_TRY(cudaGetLastError());
         QK_TRY(cudaMemcpy(&hinfo, info, sizeof hinfo, cudaMemcpyDeviceToHost));
-        if (hinfo.flags & QK_FLAG_EMPTY_ON_CHAIN) {
-            rc = qk_fail(ctx, QK_ERR_FORMAT, "the chain passes through an empty slot: not a QM11 chain");
-            goto done;
-        }
         if (!(hinfo.flags & QK_FLAG_STASH_FULL)) break;
         stash_min = hinfo.stash_used + 1024; // retry with a stash that holds what was needed
         if (attempt == 3) { rc = qk_fail(ctx, QK_ERR_NOMEM, "stash overflow after 4 attempts"); goto done; }
     }
     d.stash_used = hinfo.stash_used;
-    d.skipped_keys = hinfo.skipped;
+    d.skipped_keys = skipped;
     ctx->desc = d;
     ctx->dict_state = 2;
     if (n_kmers_out) *n_kmers_out = total;
 
 done:
+    cudaFree(kbo);
     cudaFree(info);
     cudaFree(succ[0]); cudaFree(succ[1]);
     cudaFree(dist[0]); cudaFree(dist[1]);
@@ -395,7 +515,8 @@ extern "C" int qk_dict_adopt(qk_ctx *ctx, const qk_table_desc *desc)
     if (desc->n_buckets == 0 || (desc->n_buckets & (desc->n_buckets - 1)) || desc->stash_slots == 0 ||
         (desc->stash_slots & (desc->stash_slots - 1)) || desc->table_bytes != desc->n_buckets * sizeof(qk_bucket) ||
         desc->stash_bytes != desc->stash_slots * sizeof(qk_stash_entry) || desc->rem_bits + desc->ord_bits > 63 ||
-        desc->ord_bits > 32 ||
+        desc->ord_bits > 32 || (desc->has_ext && (desc->k != 30 || desc->ext_bytes < (desc->n_kmers + 15) / 16 * 4 + 16 ||
+                                                  desc->cont_bytes < (desc->n_kmers + 31) / 32 * 4 + 16)) ||
         desc->rem_bits + desc->bucket_bits != QK_KEY_BITS || desc->k < 1 || desc->k > 32)
         return qk_fail(ctx, QK_ERR_ARG, "inconsistent table descriptor");
     QK_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -404,6 +525,16 @@ extern "C" int qk_dict_adopt(qk_ctx *ctx, const qk_table_desc *desc)
     ctx->desc = *desc;
     ctx->k = (uint8_t)desc->k;
     ctx->dict_state = 2;
+    return QK_OK;
+}
+
+extern "C" int qk_dict_ext_ptrs(const qk_ctx *ctx, void **last, void **first, void **cont)
+{
+    if (!ctx) return QK_ERR_ARG;
+    if (ctx->dict_state != 2) return QK_ERR_STATE;
+    if (last) *last = ctx->ext_last;
+    if (first) *first = ctx->ext_first;
+    if (cont) *cont = ctx->ext_cont;
     return QK_OK;
 }
 

@@ -99,7 +99,7 @@ def count_sharded(plan: dict, rank: int, world: int, count_fn, reset_fn, all_gat
 # ---- device side (needs torch + a CUDA context per rank) -------------------------------------
 def replicate_dictionary(qk, ctx, rank: int, device: int, dist) -> int:
     """Rank 0 holds a built table; every other rank adopts its geometry and receives the image
-    (table + stash) by broadcast over NCCL.  Returns n_kmers."""
+    (table, stash, extension arrays) by broadcast over NCCL.  Returns n_kmers."""
     import torch
 
     desc = ctx.table_desc() if rank == 0 else qk.TableDesc()
@@ -108,8 +108,7 @@ def replicate_dictionary(qk, ctx, rank: int, device: int, dist) -> int:
     if rank != 0:
         desc = qk.TableDesc.from_buffer_copy(raw.cpu().numpy().tobytes())
         ctx.adopt(desc)
-    tptr, sptr = ctx.table_device_ptrs()
-    for ptr, nbytes in ((tptr, int(desc.table_bytes)), (sptr, int(desc.stash_bytes))):
+    for ptr, nbytes in ctx.table_images():              # table, stash, extension arrays
         dist.broadcast(torch.as_tensor(DevMem(ptr, nbytes), device=f"cuda:{device}"), 0)
     torch.cuda.synchronize()
     return int(desc.n_kmers)

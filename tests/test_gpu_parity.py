@@ -230,6 +230,66 @@ def test_corrupt_chain_is_rejected(qk, oracle, gpu_ctx):
     assert gpu_ctx.load_dictionary_arrays(30, keys, nxt, first) == order.size   # and the intact one loads
 
 
+# ------------------------------------------------------------------ dictionary-order extension
+def test_extension_path_is_exercised_and_exact(mid_dict, qk, oracle, synth, tmp_path):
+    """k = 30: most hits must come from walking the dictionary order (both strands: odd reads
+    are reverse complements), and the result must equal the oracle's and the classic kernel's."""
+    synth("reads", "--ref", mid_dict / "ref.fa", "--out", tmp_path / "clean.fa", "--n", 100000, "--len", 150, "--seed", 5,
+          "--err-ppm", 0)
+    synth("reads", "--ref", mid_dict / "ref.fa", "--out", tmp_path / "noisy.fa", "--n", 100000, "--len", 150, "--seed", 6,
+          "--err-ppm", 50000)                               # 5 % substitutions: every read breaks the walk several times
+    for name, min_frac in (("clean.fa", 0.85), ("noisy.fa", 0.05)):
+        want, ost = oracle.count_bin(mid_dict / "ref.fa.qm", tmp_path / name)
+        with qk.Context(n_slots=2, chunk_capacity=4 << 20) as ctx:
+            ctx.load_dictionary(mid_dict / "ref.fa.qm")
+            assert ctx.table_desc().has_ext == 1
+            ctx.count_file(tmp_path / name)
+            st = ctx.stats()
+            assert np.array_equal(ctx.finish(), want), name
+            assert st["total_kmers"] == ost["total_kmers"] and st["hits"] == ost["hits"]
+            assert st["ext_verified"] >= min_frac * st["hits"], (name, st)
+    # the classic kernel (every position probes) on the same input, in a process of its own
+    code = ("import sys; sys.path.insert(0, %r); from conftest import load_package; qk = load_package();"
+            "st = qk.count(%r, %r, %r); print(st['hits'])" % (str(GOLDEN.parent), str(mid_dict / "ref.fa"), str(tmp_path / "noisy.fa"),
+                                                          str(tmp_path / "classic")))
+    for env_extra in ({"QK_CLASSIC_KERNEL": "1"}, {"QK_NO_EXT": "1"}):
+        res = subprocess.run(["python", "-c", code], env=dict(os.environ, **env_extra), capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr
+        assert np.array_equal(np.fromfile(tmp_path / "classic.bin", dtype=np.uint16), want)
+
+
+def test_extension_on_chimeric_and_repetitive_reads(mid_dict, qk, oracle, tmp_path):
+    """Reads that jump between loci and strands mid-read, carry N, or sit in tandem repeats: the
+    walk must stop exactly where the dictionary order stops describing the read."""
+    rng = np.random.default_rng(3)
+    seq = "".join(l.strip() for l in open(mid_dict / "ref.fa") if not l.startswith(">"))
+    comp = str.maketrans("ACGTN", "TGCAN")
+    reads = []
+    for i in range(20000):
+        parts = []
+        for _ in range(int(rng.integers(1, 4))):
+            a = int(rng.integers(0, len(seq) - 200))
+            piece = seq[a:a + int(rng.integers(20, 120))]
+            if rng.integers(0, 2):
+                piece = piece.translate(comp)[::-1]
+            parts.append(piece)
+        r = "".join(parts)
+        if i % 7 == 0:
+            r = r[:40] + "N" + r[41:]
+        if i % 11 == 0:
+            unit = seq[a:a + int(rng.integers(1, 9))]
+            r = r[:50] + unit * 12 + r[50:]
+        reads.append(r)
+    (tmp_path / "c.fa").write_text("".join(f">c{i}\n{r}\n" for i, r in enumerate(reads)))
+    want, ost = oracle.count_bin(mid_dict / "ref.fa.qm", tmp_path / "c.fa")
+    with qk.Context(n_slots=2, chunk_capacity=1 << 20) as ctx:
+        ctx.load_dictionary(mid_dict / "ref.fa.qm")
+        ctx.count_file(tmp_path / "c.fa")
+        st = ctx.stats()
+        assert np.array_equal(ctx.finish(), want)
+        assert st["hits"] == ost["hits"] and st["ext_verified"] > 0
+
+
 # ------------------------------------------------------------------ device framing ---------
 def weird_stream(rng, seq, fastq_like, n_lines):
     """Lines in arbitrary order -- not a valid FASTA/FASTQ -- so that the reference's line state
