@@ -370,136 +370,131 @@ __device__ __forceinline__ uint32_t qk_probe_resolve(const qk_table_view &tv, co
     return ord1;
 }
 
+// Work decomposition: a WARP owns a span of 512-byte sub-tiles and walks it on its own -- no
+// CTA-wide barrier anywhere, so a warp waiting for DRAM never holds up its neighbours (with
+// CTA-wide tiles ncu showed as many cycles stalled on the barrier as on memory).  Lane l owns
+// bytes [16 l, 16 l + 16) of the sub-tile.  Probes that the walk cannot avoid are pooled in a
+// per-warp queue and issued 64 at a time with every lane busy, and the depth increments are made
+// position-parallel from a per-warp ordinal array, so that a warp's REDs fall on consecutive
+// counters (one or two 128-byte lines per instruction).
+#define QK_SUB 512
+#define QK_SUB_WORDS (QK_SUB / 32)
+#define QK_WARPS (QK_THREADS / 32)
+
+struct qk_warp_smem {
+    uint64_t codes[QK_SUB_WORDS + 1]; // [0] = halo: the 32 bases before the sub-tile
+    uint32_t mask[QK_SUB_WORDS + 1];  // reset flags; [0] = halo word
+    uint32_t pad;
+    uint32_t ord[QK_SUB];             // ordinal + 1 per position of the sub-tile (0 = no hit)
+    uint16_t queue[QK_SUB];           // positions that need a probe of their own
+};
+
 __global__ void __launch_bounds__(QK_THREADS, 4) qk_count_ext_kernel(const qk_count_args a)
 {
-    __shared__ uint64_t s_codes[2][QK_WORDS + 1]; // [0] = halo: the 32 bases before the tile
-    __shared__ uint32_t s_mask[2][QK_WORDS + 1];  // reset flags; [0] = halo word
-    __shared__ int s_last[2][QK_WORDS];           // last reset before word w (chunk position)
-    __shared__ int s_red[QK_THREADS / 32];
-    __shared__ int s_carry;
+    __shared__ __align__(16) qk_warp_smem s_all[QK_WARPS];
+    const uint32_t lane = threadIdx.x & 31;
+    qk_warp_smem &sm = s_all[threadIdx.x >> 5];
+    const uint32_t FULL = 0xffffffffu;
 
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t tile0 = blockIdx.x * a.tiles_per_cta;
-    if (tile0 >= a.n_tiles) return;
-    const uint32_t tile_end = min(tile0 + a.tiles_per_cta, a.n_tiles);
-    const uint8_t *__restrict__ bytes = a.bytes;
     const uint32_t n = a.n_bytes;
+    const uint32_t n_subs = (n + QK_SUB - 1) / QK_SUB;
+    const uint32_t subs_per_warp = a.tiles_per_cta * (QK_TILE / QK_SUB) / QK_WARPS; // = tiles_per_cta: 8 sub-tiles per tile, 8 warps
+    const uint32_t sub0 = (blockIdx.x * QK_WARPS + (threadIdx.x >> 5)) * subs_per_warp;
+    if (sub0 >= n_subs) return;
+    const uint32_t sub_end = min(sub0 + subs_per_warp, n_subs);
+    const uint8_t *__restrict__ bytes = a.bytes;
 
-    // ---- span start: last reset before the span, halo codes and halo reset bits --------------
+    // ---- span start: last reset before the span (for the 16-bit run counter), halo -------------
+    int carry_last;
+    uint64_t halo_c = 0;
+    uint32_t halo_m = 0xFFFFFFFFu; // before the chunk: as good as resets
     {
         int found = QK_NONE;
-        uint32_t pos = tile0 * QK_TILE;
+        uint32_t pos = sub0 * QK_SUB;
         while (pos > 0 && found == QK_NONE) {
-            pos -= QK_TILE;
-            const uint32_t at = pos + tid * 16;
+            pos -= QK_SUB;
+            const uint32_t at = pos + lane * 16;
             const uint32_t m = qk_resets16(qk_load16(bytes, at, n));
-            int own = m ? (int)(at + 31 - __clz(m)) : QK_NONE;
-            for (int o = 16; o; o >>= 1) own = max(own, __shfl_xor_sync(0xffffffffu, own, o));
-            if (lane == 0) s_red[warp] = own;
-            __syncthreads();
-            found = s_red[0];
-#pragma unroll
-            for (int w = 1; w < QK_THREADS / 32; ++w) found = max(found, s_red[w]);
-            __syncthreads();
+            found = __reduce_max_sync(FULL, m ? (int)(at + 31 - __clz(m)) : QK_NONE);
         }
-        if (tid == 0) {
-            s_carry = (found == QK_NONE) ? -1 : found;
-            uint64_t halo = 0;
-            uint32_t halo_mask = 0xFFFFFFFFu; // before the chunk: as good as resets
-            const uint32_t base = tile0 * QK_TILE;
-            if (base >= 32) {
-                const uint4 h0 = qk_load16(bytes, base - 32, n), h1 = qk_load16(bytes, base - 16, n);
-                halo = ((uint64_t)qk_codes16(h0) << 32) | qk_codes16(h1);
-                halo_mask = qk_resets16(h0) | (qk_resets16(h1) << 16);
-            }
-            s_codes[(tile0 & 1) ^ 1][QK_WORDS] = halo;
-            s_mask[(tile0 & 1) ^ 1][QK_WORDS] = halo_mask;
+        carry_last = (found == QK_NONE) ? -1 : found;
+        const uint32_t base = sub0 * QK_SUB;
+        if (base >= 32) {
+            const uint4 h0 = qk_load16(bytes, base - 32, n), h1 = qk_load16(bytes, base - 16, n);
+            halo_c = ((uint64_t)qk_codes16(h0) << 32) | qk_codes16(h1);
+            halo_m = qk_resets16(h0) | (qk_resets16(h1) << 16);
         }
     }
 
     const qk_table_view tv = a.tv;
     const uint32_t ord_mask = tv.ord_bits >= 32 ? 0xFFFFFFFFu : (1u << tv.ord_bits) - 1;
     uint32_t n_emit = 0, n_hit = 0, n_ext = 0;
-    const uint32_t w = tid >> 1, half = tid & 1; // the word and the half of it this thread owns
+    const uint32_t w = lane >> 1, half = lane & 1; // the word and the half of it this lane owns
 
-    uint4 cur = qk_load16(bytes, tile0 * QK_TILE + tid * 16, n);
-    for (uint32_t tile = tile0; tile < tile_end; ++tile) {
-        const uint32_t buf = tile & 1;
-        const uint32_t base = tile * QK_TILE;
-        __syncthreads();
-        const uint32_t my_codes = qk_codes16(cur);           // first base in the top pair
+    auto key_at = [&](uint32_t idx, bool *is_fwd) -> uint64_t { // canonical 30-mer ending at position idx of the sub-tile
+        const uint64_t A = sm.codes[idx >> 5], B = sm.codes[(idx >> 5) + 1];
+        const uint32_t sh = 2 * (31 - (idx & 31));
+        const uint64_t x = ((B >> sh) | ((A << 1) << (63 - sh))) & QK_M60;
+        const uint64_t rc = (qk_rev_pairs(x) >> 4) ^ 0x0AAAAAAAAAAAAAAAull;
+        *is_fwd = x <= rc;
+        return min(x, rc);
+    };
+
+    uint4 cur = qk_load16(bytes, sub0 * QK_SUB + lane * 16, n);
+    for (uint32_t sub = sub0; sub < sub_end; ++sub) {
+        const uint32_t base = sub * QK_SUB;
+        __syncwarp(); // everybody is done reading the previous sub-tile
+        const uint32_t my_codes = qk_codes16(cur); // first base in the top pair
         const uint32_t my_resets = qk_resets16(cur);
-        reinterpret_cast<uint32_t *>(s_codes[buf])[2 + (tid ^ 1)] = my_codes;
-        reinterpret_cast<uint16_t *>(s_mask[buf])[2 + tid] = (uint16_t)my_resets;
-        if (tid == 0) {
-            s_codes[buf][0] = s_codes[buf ^ 1][QK_WORDS];
-            s_mask[buf][0] = s_mask[buf ^ 1][QK_WORDS];
+        reinterpret_cast<uint32_t *>(sm.codes)[2 + (lane ^ 1)] = my_codes;
+        reinterpret_cast<uint16_t *>(sm.mask)[2 + lane] = (uint16_t)my_resets;
+        if (lane == 0) {
+            sm.codes[0] = halo_c;
+            sm.mask[0] = halo_m;
         }
-        if (tile + 1 < tile_end) cur = qk_load16(bytes, base + QK_TILE + tid * 16, n); // prefetch
-        __syncthreads();
-        if (warp == 0) { // exclusive max-scan of the per-word last reset (needed for the 16-bit run counter only)
-            int carry = s_carry;
-#pragma unroll
-            for (int i = 0; i < QK_WORDS / 32; ++i) {
-                const uint32_t ww = i * 32 + lane;
-                const uint32_t m = s_mask[buf][ww + 1];
-                int incl = m ? (int)(base + ww * 32 + 31 - __clz(m)) : QK_NONE;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    int up = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl = max(incl, up);
-                }
-                int excl = __shfl_up_sync(0xffffffffu, incl, 1);
-                if (lane == 0) excl = QK_NONE;
-                s_last[buf][ww] = max(carry, excl);
-                carry = max(carry, __shfl_sync(0xffffffffu, incl, 31));
-            }
-            if (lane == 0) s_carry = carry;
-        }
-        __syncthreads();
+        if (sub + 1 < sub_end) cur = qk_load16(bytes, base + QK_SUB + lane * 16, n); // prefetch
+        __syncwarp();
 
         // ---- which of my 16 positions end a 30-mer: no reset among the 30 bytes ending there ----
-        const uint64_t A = s_codes[buf][w], B = s_codes[buf][w + 1];
-        const uint64_t M64 = ((uint64_t)s_mask[buf][w + 1] << 32) | s_mask[buf][w];
+        const uint64_t M64 = ((uint64_t)sm.mask[w + 1] << 32) | sm.mask[w];
         uint64_t S = M64 | (M64 << 1);
-        S |= S << 2; S |= S << 4; S |= S << 8; S |= S << 14;   // bit p: a reset in [p-29, p]
-        const uint32_t sh0 = 32 + 16 * half;
-        uint32_t emit = ~(uint32_t)(S >> sh0) & 0xFFFFu;
-        if (emit == 0) continue;
-        const uint32_t p0 = base + 16 * tid;
-        {   // uint16 cur_chars (Q.c:402): positions whose run length mod 65,536 is below k emit nothing
-            const uint32_t lowhalf = s_mask[buf][w + 1] & 0xFFFFu;
-            const int last0 = (half && lowhalf) ? (int)(base + w * 32 + 31 - __clz(lowhalf)) : s_last[buf][w];
-            const uint32_t r0 = (uint32_t)((int)p0 - last0);
-            if (r0 + 15 >= 65536u) {
-                for (uint32_t j = 0; j < QK_RUN; ++j)
-                    if (((r0 + j) & 0xFFFFu) < 30u) emit &= ~(1u << j);
-                if (emit == 0) continue;
+        S |= S << 2; S |= S << 4; S |= S << 8; S |= S << 14; // bit p: a reset in [p-29, p]
+        uint32_t emit = ~(uint32_t)(S >> (32 + 16 * half)) & 0xFFFFu;
+        const uint32_t p0 = base + 16 * lane;
+        if (emit && p0 + 15 - (uint32_t)carry_last >= 65536u) {
+            // uint16 cur_chars (Q.c:402): a position whose run length mod 65,536 is below k emits
+            // nothing.  Only lines longer than 65 k get here: find the exact last reset before p0.
+            int last0 = carry_last;
+            for (int ww = (int)w; ww >= 0 && last0 == carry_last; --ww) {
+                uint32_t m = sm.mask[ww + 1];
+                if ((uint32_t)ww == w) m &= half ? 0xFFFFu : 0u;
+                if (m) last0 = (int)(base + ww * 32 + 31 - __clz(m));
             }
+            const uint32_t r0 = (uint32_t)((int)p0 - last0);
+            for (uint32_t j = 0; j < QK_RUN; ++j)
+                if (((r0 + j) & 0xFFFFu) < 30u) emit &= ~(1u << j);
+        }
+        {   // last reset seen so far, for the next sub-tile
+            const int own = my_resets ? (int)(p0 + 31 - __clz(my_resets)) : QK_NONE;
+            carry_last = max(carry_last, __reduce_max_sync(FULL, own));
         }
         n_emit += __popc(emit);
 
-        auto key_at = [&](uint32_t j, bool *is_fwd) -> uint64_t {
-            const uint32_t sh = 2 * (31 - (16 * half + j));
-            const uint64_t x = ((B >> sh) | ((A << 1) << (63 - sh))) & QK_M60; // 30 bases ending at p0 + j
-            const uint64_t rc = (qk_rev_pairs(x) >> 4) ^ 0x0AAAAAAAAAAAAAAAull;
-            *is_fwd = x <= rc;
-            return min(x, rc);
-        };
-
-        // ---- anchor: the first emitting position ------------------------------------------------
-        const uint32_t ja = __ffs(emit) - 1;
-        bool a_fwd;
-        const qk_probe ap = qk_probe_prepare(tv, key_at(ja, &a_fwd));
-        const qk_bucket abk = qk_ld_bucket(ap.bp);
-        uint32_t a_strand = 0;
-        const uint32_t a_ord1 = qk_probe_resolve(tv, ap, abk, ord_mask, &a_strand);
-        uint32_t verified = 0;
+        // ---- anchor: my first emitting position; walk the dictionary order from it ---------------
+        const uint32_t ja = emit ? __ffs(emit) - 1 : 0;
+        bool a_fwd = false;
+        qk_probe ap;
+        qk_bucket abk;
+        abk.e[0] = abk.e[1] = abk.e[2] = abk.e[3] = 0;
+        if (emit) {
+            ap = qk_probe_prepare(tv, key_at(16 * lane + ja, &a_fwd));
+            abk = qk_ld_bucket(ap.bp);
+        }
+        uint32_t a_strand = 0, a_ord1 = 0, verified = 0;
         bool plus = true;
+        if (emit) a_ord1 = qk_probe_resolve(tv, ap, abk, ord_mask, &a_strand);
+        const uint64_t oa = a_ord1 ? a_ord1 - 1 : 0;
         if (a_ord1) {
-            ++n_hit;
-            const uint64_t oa = a_ord1 - 1;
-            atomicAdd(a.counters + oa, 1u);
             const uint32_t nsteps = 15 - ja;
             plus = (a_strand != 0) == a_fwd;
             if (nsteps && (plus || oa >= 15)) {
@@ -524,53 +519,84 @@ __global__ void __launch_bounds__(QK_THREADS, 4) qk_count_ext_kernel(const qk_co
                 len = min(len, nsteps);
                 verified = ((1u << len) - 1) << (ja + 1);
             }
-            uint32_t ve = verified & emit;
-            n_hit += __popc(ve);
-            n_ext += __popc(ve);
-            while (ve) {
-                const uint32_t j = __ffs(ve) - 1;
-                ve &= ve - 1;
-                const uint64_t o = plus ? oa + (j - ja) : oa - (j - ja);
-                atomicAdd(a.counters + o, 1u);
+        }
+        const uint32_t ve = verified & emit;
+        n_ext += __popc(ve);
+        {   // ordinal + 1 of my 16 positions as far as known now
+            uint32_t o[QK_RUN];
+#pragma unroll
+            for (uint32_t j = 0; j < QK_RUN; ++j) {
+                const uint32_t step = j - ja;
+                const uint32_t walked = (uint32_t)(plus ? oa + step : oa - step) + 1;
+                o[j] = (ve >> j) & 1u ? walked : (j == ja ? a_ord1 : 0u);
             }
+            uint4 *dst = reinterpret_cast<uint4 *>(sm.ord + 16 * lane);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) dst[v] = make_uint4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
         }
 
-        // ---- everything else is probed on its own, four at a time --------------------------------
-        uint32_t todo = emit & ~verified & ~(1u << ja);
-        while (todo) {
-            qk_probe pr[4];
-            qk_bucket bk[4];
-            bool on[4];
+        // ---- positions the walk could not settle: pool them over the warp ------------------------
+        uint32_t todo = emit & ~verified;
+        if (emit) todo &= ~(1u << ja);
+        const uint32_t cnt = __popc(todo);
+        uint32_t incl = cnt;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                on[u] = todo != 0;
-                const uint32_t j = on[u] ? __ffs(todo) - 1 : 0;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(FULL, incl, o);
+            if (lane >= (uint32_t)o) incl += up;
+        }
+        const uint32_t total = __shfl_sync(FULL, incl, 31);
+        {
+            uint32_t off = incl - cnt;
+            while (todo) {
+                sm.queue[off++] = (uint16_t)(16 * lane + __ffs(todo) - 1);
                 todo &= todo - 1;
-                bool f;
-                pr[u] = qk_probe_prepare(tv, key_at(j, &f));
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                bk[u].e[0] = bk[u].e[1] = bk[u].e[2] = bk[u].e[3] = 0;
-                if (on[u]) bk[u] = qk_ld_bucket(pr[u].bp);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (!on[u]) continue;
-                uint32_t st;
-                const uint32_t ord1 = qk_probe_resolve(tv, pr[u], bk[u], ord_mask, &st);
-                if (ord1) {
-                    ++n_hit;
-                    atomicAdd(a.counters + (ord1 - 1), 1u);
-                }
             }
         }
+        __syncwarp();
+        for (uint32_t q0 = 0; q0 < total; q0 += 64) {
+            qk_probe pr[2];
+            qk_bucket bk[2];
+            uint32_t idx[2];
+            bool on[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const uint32_t e = q0 + 32 * u + lane;
+                on[u] = e < total;
+                idx[u] = on[u] ? sm.queue[e] : 0;
+                bool f;
+                pr[u] = qk_probe_prepare(tv, key_at(idx[u], &f));
+                bk[u].e[0] = bk[u].e[1] = bk[u].e[2] = bk[u].e[3] = 0;
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                if (on[u]) bk[u] = qk_ld_bucket(pr[u].bp);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (!on[u]) continue;
+                uint32_t st;
+                sm.ord[idx[u]] = qk_probe_resolve(tv, pr[u], bk[u], ord_mask, &st);
+            }
+        }
+        __syncwarp();
+
+        // ---- depth increments, position-parallel: consecutive lanes, consecutive counters --------
+#pragma unroll 4
+        for (uint32_t it = 0; it < QK_SUB / 32; ++it) {
+            const uint32_t o1 = sm.ord[it * 32 + lane];
+            if (o1) {
+                ++n_hit;
+                atomicAdd(a.counters + (o1 - 1), 1u);
+            }
+        }
+        halo_c = sm.codes[QK_SUB_WORDS];
+        halo_m = sm.mask[QK_SUB_WORDS];
     }
 
     for (int o = 16; o; o >>= 1) {
-        n_emit += __shfl_xor_sync(0xffffffffu, n_emit, o);
-        n_hit += __shfl_xor_sync(0xffffffffu, n_hit, o);
-        n_ext += __shfl_xor_sync(0xffffffffu, n_ext, o);
+        n_emit += __shfl_xor_sync(FULL, n_emit, o);
+        n_hit += __shfl_xor_sync(FULL, n_hit, o);
+        n_ext += __shfl_xor_sync(FULL, n_ext, o);
     }
     if (lane == 0) {
         atomicAdd(a.stats + 0, (unsigned long long)n_emit);
