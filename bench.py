@@ -368,7 +368,7 @@ def gpu_arm(args):
     d, ref, reads = prepare(args.workload, cdir, rank)
 
     chunk_cap = args.chunk_mib << 20
-    ctx = qk.Context(device=local, n_slots=8, chunk_capacity=chunk_cap)
+    ctx = qk.Context(device=local, n_slots=args.slots, chunk_capacity=chunk_cap)
     t0 = time.perf_counter()
     if rank == 0:
         n_kmers = ctx.load_dictionary(ref.with_suffix(".fa.qm"))
@@ -591,7 +591,8 @@ def main():
     ap.add_argument("--cache-dir", default=None)
     ap.add_argument("--chunk-mib", type=int, default=64)
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--reader-threads", type=int, default=8)
+    ap.add_argument("--reader-threads", type=int, default=12)
+    ap.add_argument("--slots", type=int, default=12)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--kernel-only", action="store_true",
                     help="device-resident leg only (no e2e, micro-benchmarks or CPU leg): for ncu and quick iteration")

@@ -17,7 +17,7 @@ extern "C" {
 #endif
 
 #define QK_ERR_IO 6 /* file cannot be opened / short read */
-#define QK_HOST_MAX_SLOTS 8
+#define QK_HOST_MAX_SLOTS 16
 
 /* ---- QM11 dictionary file: written at Q.c:1284-1299, read at Q.c:345-359 and 483 ---- */
 typedef struct qk_qm_header {

@@ -42,7 +42,7 @@ const char *qk_version(void);
 int qk_device_count(void);
 
 /*
- * Create a context on CUDA device `device` with `n_slots` (1..8) chunk slots of
+ * Create a context on CUDA device `device` with `n_slots` (1..16) chunk slots of
  * `chunk_capacity` bytes each.  Every slot owns a pinned host buffer, a device buffer, a
  * stream and two events -- the replacement for the reference's per-worker double FIFO
  * (struct FIFO_arg_struc, Q.c:34-41; thread pool set-up Q.c:368-384).

@@ -20,7 +20,7 @@
 
 #define QK_TILE 4096          // bytes (= positions) per tile
 #define QK_THREADS 256        // threads per CTA of the count kernel
-#define QK_MAX_SLOTS 8
+#define QK_MAX_SLOTS 16
 #define QK_TIMING_RING 64
 #define QK_KEY_BITS 60
 #define QK_BUCKET_ENTRIES 4

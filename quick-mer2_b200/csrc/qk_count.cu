@@ -94,6 +94,17 @@ __device__ __forceinline__ uint4 qk_load16(const uint8_t *__restrict__ bytes, ui
     return v;
 }
 
+// the same load with an L2 fetch-size hint of 64 B: a missing sector then costs 64 B of DRAM
+// traffic instead of the default 128 B (measured, profiles/r1_gather_probe_ncu.txt)
+__device__ __forceinline__ qk_bucket qk_ld_bucket64(const qk_bucket *p)
+{
+    qk_bucket v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(v.e[0]), "=l"(v.e[1]), "=l"(v.e[2]), "=l"(v.e[3])
+                 : "l"(p));
+    return v;
+}
+
 __device__ __forceinline__ qk_bucket qk_ld_bucket(const qk_bucket *p)
 {
     qk_bucket v;
@@ -389,7 +400,8 @@ struct qk_warp_smem {
     uint16_t queue[QK_SUB];           // positions that need a probe of their own
 };
 
-__global__ void __launch_bounds__(QK_THREADS, 4) qk_count_ext_kernel(const qk_count_args a)
+template <int MINB, bool L64>
+__global__ void __launch_bounds__(QK_THREADS, MINB) qk_count_ext_kernel(const qk_count_args a)
 {
     __shared__ __align__(16) qk_warp_smem s_all[QK_WARPS];
     const uint32_t lane = threadIdx.x & 31;
@@ -488,7 +500,7 @@ __global__ void __launch_bounds__(QK_THREADS, 4) qk_count_ext_kernel(const qk_co
         abk.e[0] = abk.e[1] = abk.e[2] = abk.e[3] = 0;
         if (emit) {
             ap = qk_probe_prepare(tv, key_at(16 * lane + ja, &a_fwd));
-            abk = qk_ld_bucket(ap.bp);
+            abk = L64 ? qk_ld_bucket64(ap.bp) : qk_ld_bucket(ap.bp);
         }
         uint32_t a_strand = 0, a_ord1 = 0, verified = 0;
         bool plus = true;
@@ -570,7 +582,7 @@ __global__ void __launch_bounds__(QK_THREADS, 4) qk_count_ext_kernel(const qk_co
             }
 #pragma unroll
             for (int u = 0; u < 2; ++u)
-                if (on[u]) bk[u] = qk_ld_bucket(pr[u].bp);
+                if (on[u]) bk[u] = L64 ? qk_ld_bucket64(pr[u].bp) : qk_ld_bucket(pr[u].bp);
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 if (!on[u]) continue;
@@ -637,7 +649,9 @@ int qk_launch_count(qk_ctx *ctx, qk_slot *sl, const uint8_t *dev_bytes, size_t n
         const char *e = getenv("QK_TILES_PER_CTA");
         tiles_env = e ? atoi(e) : 0;
     }
-    uint32_t target_ctas = (uint32_t)ctx->sm_count * 3 * 4;
+    // classic kernel: 3 CTAs/SM, 4 waves; extension kernel: 4 CTAs/SM, 2 waves (longer warp spans
+    // amortise the span-start search; measured +3 %)
+    uint32_t target_ctas = (uint32_t)ctx->sm_count * (a.tv.ext_last ? 8 : 12);
     uint32_t tpc = (a.n_tiles + target_ctas - 1) / target_ctas;
     if (tpc < 4) tpc = 4;
     if (tiles_env > 0) tpc = (uint32_t)tiles_env;
@@ -651,8 +665,21 @@ int qk_launch_count(qk_ctx *ctx, qk_slot *sl, const uint8_t *dev_bytes, size_t n
     QK_CUDA(ctx, cudaEventRecord(tp->a, sl->stream));
     static int classic = -1; // QK_CLASSIC_KERNEL=1: probe every position even when the extension arrays exist
     if (classic < 0) classic = getenv("QK_CLASSIC_KERNEL") != NULL;
-    if (a.tv.ext_last && !classic) qk_count_ext_kernel<<<grid, QK_THREADS, 0, sl->stream>>>(a);
-    else qk_count_kernel<<<grid, QK_THREADS, 0, sl->stream>>>(a);
+    static int variant = -1; // QK_EXT_VARIANT = 10 * min CTAs per SM (4..6) + L2::64B hint (0/1); tuning knob
+    if (variant < 0) {
+        const char *e = getenv("QK_EXT_VARIANT");
+        variant = e ? atoi(e) : 41;
+    }
+    if (a.tv.ext_last && !classic) {
+        switch (variant) {
+        case 40: qk_count_ext_kernel<4, false><<<grid, QK_THREADS, 0, sl->stream>>>(a); break;
+        case 50: qk_count_ext_kernel<5, false><<<grid, QK_THREADS, 0, sl->stream>>>(a); break;
+        case 51: qk_count_ext_kernel<5, true><<<grid, QK_THREADS, 0, sl->stream>>>(a); break;
+        case 60: qk_count_ext_kernel<6, false><<<grid, QK_THREADS, 0, sl->stream>>>(a); break;
+        case 61: qk_count_ext_kernel<6, true><<<grid, QK_THREADS, 0, sl->stream>>>(a); break;
+        default: qk_count_ext_kernel<4, true><<<grid, QK_THREADS, 0, sl->stream>>>(a); break;
+        }
+    } else qk_count_kernel<<<grid, QK_THREADS, 0, sl->stream>>>(a);
     QK_CUDA(ctx, cudaGetLastError());
     QK_CUDA(ctx, cudaEventRecord(tp->b, sl->stream));
     ctx->launches++;
