@@ -524,11 +524,18 @@ def gpu_arm(args):
     else:
         gather = ctx.bench_gather(int(desc.table_bytes), gran=32, loads_in_flight=8, n_gathers=1 << 30)
         h2d = ctx.bench_h2d(min(chunk_cap, 64 << 20), repeats=16)
+    ext = bool(desc.has_ext) and not os.environ.get("QK_CLASSIC_KERNEL")
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of
+    # `bench.py --kernel-only` on this workload (profiles/r1_count_ext_kernel_ncu_full_summary.csv); null elsewhere
+    traffic = 1249798000 + 194004224 if (args.workload == "config2" and ext and args.chunk_mib == 64) else None
     roofline = {
-        "bound": "hbm", "kernel": "qk_count_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "peak_source": peak_src, "traffic": None,
+        "bound": "hbm", "kernel": "qk_count_ext_kernel<4,1>" if ext else "qk_count_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "peak_source": peak_src, "traffic": traffic,
+        "traffic_source": "ncu --set full, profiles/r1_count_ext_kernel_ncu_full_summary.csv" if traffic else None,
         "algorithmic_bytes_per_launch": alg_bytes_step / max(1, launches),
-        "bytes_model": "32 B bucket sector per emitted k-mer + 4 B counter per hit + 1 B per input byte",
+        "bytes_model": "SURVEY 8(d): 32 B bucket sector per emitted k-mer + 4 B counter per hit + 1 B per input byte"
+                       + (" (the extension kernel derives most hits from dictionary order and probes far fewer sectors, so measured DRAM traffic is BELOW this figure)" if ext else ""),
+        "probes_avoided_fraction": (stats.get("ext_verified", 0) / max(1, step_kmers)),
         "avg_launch_ms": avg_launch_ms, "launches_per_step": launches,
         "kernel_share_of_step": tm["kernel_ms"] / ms_per_step if world == 1 else None,
         "gather_peak_gbs": gather, "gather_peak_how": f"random 32 B sector loads over a {int(desc.table_bytes) >> 20} MiB table, 8 in flight/thread (qk_bench_gather)",
