@@ -606,10 +606,18 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         log("note: the timing rules ask for >= 3 warm-up steps")
+    # stdout carries exactly one JSON line: libraries that print there (NCCL's version banner
+    # does when NCCL_DEBUG is set) are sent to stderr for the duration
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    real_stdout = os.fdopen(saved, "w")
+    sys.stdout = real_stdout
     if args.impl == "reference":
         reference_arm(args)
     else:
         gpu_arm(args)
+    real_stdout.flush()
 
 
 if __name__ == "__main__":

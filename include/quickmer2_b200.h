@@ -67,6 +67,10 @@ int qk_dict_begin(qk_ctx *ctx, uint8_t k, uint64_t hash_size, uint64_t first_idx
  * are host pointers (pinned or pageable); the call returns when they may be reused. */
 int qk_dict_upload_keys(qk_ctx *ctx, uint64_t slot_offset, const uint64_t *keys, uint64_t count);
 int qk_dict_upload_chain(qk_ctx *ctx, uint64_t slot_offset, const uint32_t *next, uint64_t count);
+/* The same from the pinned buffer of `slot` (qk_slot_host_buffer), asynchronously on the
+ * slot's stream; kind 0 = keys (u64), 1 = chain (u32); qk_wait_slot(slot) tells when the buffer
+ * may be refilled.  Lets several reader threads fill slots while copies are in flight. */
+int qk_dict_upload_from_slot(qk_ctx *ctx, uint32_t slot, int kind, uint64_t elem_offset, uint64_t count);
 /* Rank the chain, build the table, release the raw arrays, zero the counters. */
 int qk_dict_build(qk_ctx *ctx, uint64_t *n_kmers_out);
 

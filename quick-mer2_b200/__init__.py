@@ -98,6 +98,7 @@ SIGNATURES = {
     "qk_dict_begin": (C.c_int, [_P, C.c_uint8, C.c_uint64, C.c_uint64]),
     "qk_dict_upload_keys": (C.c_int, [_P, C.c_uint64, _P, C.c_uint64]),
     "qk_dict_upload_chain": (C.c_int, [_P, C.c_uint64, _P, C.c_uint64]),
+    "qk_dict_upload_from_slot": (C.c_int, [_P, C.c_uint32, C.c_int, C.c_uint64, C.c_uint64]),
     "qk_dict_build": (C.c_int, [_P, _U64P]),
     "qk_dict_describe": (C.c_int, [_P, C.POINTER(TableDesc)]),
     "qk_dict_adopt": (C.c_int, [_P, C.POINTER(TableDesc)]),

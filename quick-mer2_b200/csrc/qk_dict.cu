@@ -84,6 +84,24 @@ extern "C" int qk_dict_upload_chain(qk_ctx *ctx, uint64_t slot_offset, const uin
     return QK_OK;
 }
 
+// Asynchronous variant: the data already sits in the pinned buffer of `slot`; the copy is
+// enqueued on the slot's stream and qk_wait_slot(slot) tells when the buffer may be refilled.
+// kind 0 = keys (count x u64 at element offset `elem_offset`), 1 = chain (u32).
+extern "C" int qk_dict_upload_from_slot(qk_ctx *ctx, uint32_t slot, int kind, uint64_t elem_offset, uint64_t count)
+{
+    if (!ctx || slot >= ctx->n_slots) return QK_ERR_ARG;
+    if (ctx->dict_state != 1) return qk_fail(ctx, QK_ERR_STATE, "qk_dict_begin not called");
+    const size_t esz = kind ? sizeof(uint32_t) : sizeof(uint64_t);
+    if (elem_offset + count > ctx->hash_size || count * esz > ctx->chunk_capacity)
+        return qk_fail(ctx, QK_ERR_ARG, "upload range outside the table or larger than a slot");
+    QK_CUDA(ctx, cudaSetDevice(ctx->device));
+    qk_slot *sl = &ctx->slots[slot];
+    void *dst = kind ? (void *)(ctx->raw_next + elem_offset) : (void *)(ctx->raw_keys + elem_offset);
+    QK_CUDA(ctx, cudaMemcpyAsync(dst, sl->host, count * esz, cudaMemcpyHostToDevice, sl->stream));
+    QK_CUDA(ctx, cudaEventRecord(sl->h2d_done, sl->stream));
+    return QK_OK;
+}
+
 // ---- kernels ---------------------------------------------------------------------------
 __global__ void qk_count_occupied(const uint64_t *__restrict__ keys, uint64_t n, qk_build_info *info)
 {
@@ -381,6 +399,7 @@ extern "C" int qk_dict_build(qk_ctx *ctx, uint64_t *n_kmers_out)
     if (!ctx) return QK_ERR_ARG;
     if (ctx->dict_state != 1) return qk_fail(ctx, QK_ERR_STATE, "qk_dict_begin/upload not called");
     QK_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (uint32_t s = 0; s < ctx->n_slots; ++s) QK_CUDA(ctx, cudaStreamSynchronize(ctx->slots[s].stream)); // async uploads
     const uint64_t H = ctx->hash_size, first = ctx->first_idx;
     // stride: about 2^19 walkers or more, segments of 16..512 slots
     uint32_t stride_log2 = 4;

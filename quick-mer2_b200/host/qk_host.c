@@ -33,6 +33,12 @@ int qk_qm_read_header(const char *qm_path, qk_qm_header *hdr)
     return QK_OK;
 }
 
+static uint32_t reader_threads_default(void);
+/* One array of the .qm (keys: 8-byte elements at file offset 24; chain: 4-byte elements after
+ * the keys) -> device, through the slots' pinned buffers: reader threads pread() pieces in
+ * parallel, this thread enqueues the H2D copies in order. */
+static int qm_upload_array(qk_ctx *ctx, int fd, uint64_t file_off, uint64_t n_elems, int kind, uint32_t threads);
+
 int qk_qm_load(qk_ctx *ctx, const char *qm_path, qk_qm_header *hdr_out, uint64_t *n_kmers_out)
 {
     qk_qm_header hdr;
@@ -41,34 +47,20 @@ int qk_qm_load(qk_ctx *ctx, const char *qm_path, qk_qm_header *hdr_out, uint64_t
     if (hdr_out) *hdr_out = hdr;
     rc = qk_dict_begin(ctx, hdr.k, hdr.hash_size, hdr.first_idx);
     if (rc) return rc;
-    FILE *f = fopen(qm_path, "rb");
-    if (!f) return QK_ERR_IO;
-    const size_t piece = (size_t)64 << 20;
-    void *buf = malloc(piece);
-    if (!buf) { fclose(f); return QK_ERR_NOMEM; }
-    rc = QK_OK;
-    if (fseeko(f, 24, SEEK_SET) != 0) rc = QK_ERR_IO;
-    for (uint64_t at = 0; !rc && at < hdr.hash_size;) {       /* keys, Q.c:359 */
-        uint64_t m = hdr.hash_size - at;
-        if (m > piece / 8) m = piece / 8;
-        if (fread(buf, 8, m, f) != m) { rc = QK_ERR_IO; break; }
-        rc = qk_dict_upload_keys(ctx, at, (const uint64_t *)buf, m);
-        at += m;
-    }
-    for (uint64_t at = 0; !rc && at < hdr.hash_size;) {       /* chain, Q.c:483 */
-        uint64_t m = hdr.hash_size - at;
-        if (m > piece / 4) m = piece / 4;
-        if (fread(buf, 4, m, f) != m) { rc = QK_ERR_IO; break; }
-        rc = qk_dict_upload_chain(ctx, at, (const uint32_t *)buf, m);
-        at += m;
-    }
-    free(buf);
-    fclose(f);
+    int fd = open(qm_path, O_RDONLY);
+    if (fd < 0) return QK_ERR_IO;
+    struct stat sb;
+    if (fstat(fd, &sb) != 0 || (uint64_t)sb.st_size < 24 + hdr.hash_size * 12) { close(fd); return QK_ERR_IO; } /* short file */
+    const uint32_t threads = reader_threads_default();
+    rc = qm_upload_array(ctx, fd, 24, hdr.hash_size, 0, threads);                           /* keys, Q.c:359 */
+    if (!rc) rc = qm_upload_array(ctx, fd, 24 + hdr.hash_size * 8, hdr.hash_size, 1, threads); /* chain, Q.c:483 */
+    close(fd);
     if (rc) return rc;
     return qk_dict_build(ctx, n_kmers_out);
 }
 
 /* ------------------------------------------------------------------ framer ----------- */
+
 struct qk_framer {
     int fd;             /* -1 for in-memory input */
     int seekable;
@@ -552,6 +544,7 @@ typedef struct {
     uint64_t submitted;          /* pieces the submitting thread is done with */
     uint64_t filled[QK_HOST_MAX_SLOTS]; /* piece index + 1 sitting in each slot, 0 = none */
     size_t filled_len[QK_HOST_MAX_SLOTS];
+    size_t head;                 /* bytes of headroom in front of each piece */
     int err;
 } qk_ingest;
 
@@ -567,7 +560,7 @@ static void *ingest_reader(void *arg)
         pthread_mutex_unlock(&g->mu);
         const uint32_t slot = (uint32_t)(i % g->n_slots);
         int rc = qk_wait_slot(g->ctx, slot);     /* its last H2D has left the pinned buffer */
-        uint8_t *host = qk_slot_host_buffer(g->ctx, slot) + QK_HEAD;
+        uint8_t *host = qk_slot_host_buffer(g->ctx, slot) + g->head;
         const uint64_t at = g->begin + i * g->body;
         const size_t want = g->end - at > g->body ? g->body : (size_t)(g->end - at);
         size_t have = 0;
@@ -598,6 +591,7 @@ static int count_range_mt(qk_ctx *ctx, int fd, uint64_t begin, uint64_t end, uin
     g.fd = fd;
     g.begin = begin;
     g.end = end;
+    g.head = QK_HEAD;
     g.body = cap - QK_HEAD - 1;
     g.n_pieces = (end - begin + g.body - 1) / g.body;
     pthread_mutex_init(&g.mu, NULL);
@@ -646,6 +640,54 @@ static int count_range_mt(qk_ctx *ctx, int fd, uint64_t begin, uint64_t end, uin
     pthread_mutex_unlock(&g.mu);
     for (uint32_t t = 0; t < started; ++t) pthread_join(th[t], NULL);
     free(tail);
+    pthread_mutex_destroy(&g.mu);
+    pthread_cond_destroy(&g.cv);
+    return rc ? rc : g.err;
+}
+
+static int qm_upload_array(qk_ctx *ctx, int fd, uint64_t file_off, uint64_t n_elems, int kind, uint32_t threads)
+{
+    qk_ingest g;
+    memset(&g, 0, sizeof g);
+    size_t cap = 0;
+    int rc = qk_ctx_info(ctx, &g.n_slots, &cap);
+    if (rc) return rc;
+    const size_t esz = kind ? 4 : 8;
+    g.ctx = ctx;
+    g.fd = fd;
+    g.begin = file_off;
+    g.end = file_off + n_elems * esz;
+    g.head = 0;
+    g.body = cap / 8 * 8;                     /* whole elements per piece */
+    g.n_pieces = (g.end - g.begin + g.body - 1) / g.body;
+    pthread_mutex_init(&g.mu, NULL);
+    pthread_cond_init(&g.cv, NULL);
+    if (threads > g.n_slots) threads = g.n_slots;
+    if (threads < 1) threads = 1;
+    pthread_t th[QK_HOST_MAX_SLOTS];
+    uint32_t started = 0;
+    for (; started < threads; ++started)
+        if (pthread_create(&th[started], NULL, ingest_reader, &g) != 0) break;
+    if (started == 0) rc = QK_ERR_NOMEM;
+    for (uint64_t i = 0; !rc && i < g.n_pieces; ++i) {
+        const uint32_t slot = (uint32_t)(i % g.n_slots);
+        pthread_mutex_lock(&g.mu);
+        while (!g.err && g.filled[slot] != i + 1) pthread_cond_wait(&g.cv, &g.mu);
+        rc = g.err;
+        const size_t have = g.filled_len[slot];
+        pthread_mutex_unlock(&g.mu);
+        if (rc) break;
+        rc = qk_dict_upload_from_slot(ctx, slot, kind, i * (g.body / esz), have / esz);
+        pthread_mutex_lock(&g.mu);
+        g.submitted = i + 1;
+        pthread_cond_broadcast(&g.cv);
+        pthread_mutex_unlock(&g.mu);
+    }
+    pthread_mutex_lock(&g.mu);
+    if (rc && !g.err) g.err = rc;
+    pthread_cond_broadcast(&g.cv);
+    pthread_mutex_unlock(&g.mu);
+    for (uint32_t t = 0; t < started; ++t) pthread_join(th[t], NULL);
     pthread_mutex_destroy(&g.mu);
     pthread_cond_destroy(&g.cv);
     return rc ? rc : g.err;
