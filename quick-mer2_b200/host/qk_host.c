@@ -52,11 +52,22 @@ int qk_qm_load(qk_ctx *ctx, const char *qm_path, qk_qm_header *hdr_out, uint64_t
     struct stat sb;
     if (fstat(fd, &sb) != 0 || (uint64_t)sb.st_size < 24 + hdr.hash_size * 12) { close(fd); return QK_ERR_IO; } /* short file */
     const uint32_t threads = reader_threads_default();
+    const int verbose = getenv("QK_TIMING") != NULL;
+    struct timespec t0, t1, t2;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
     rc = qm_upload_array(ctx, fd, 24, hdr.hash_size, 0, threads);                           /* keys, Q.c:359 */
     if (!rc) rc = qm_upload_array(ctx, fd, 24 + hdr.hash_size * 8, hdr.hash_size, 1, threads); /* chain, Q.c:483 */
     close(fd);
     if (rc) return rc;
-    return qk_dict_build(ctx, n_kmers_out);
+    if (verbose) { qk_sync(ctx); clock_gettime(CLOCK_MONOTONIC, &t1); }
+    rc = qk_dict_build(ctx, n_kmers_out);
+    if (verbose) {
+        clock_gettime(CLOCK_MONOTONIC, &t2);
+        fprintf(stderr, "[qk] .qm upload %.3f s (%u readers), table build %.3f s\n",
+                (t1.tv_sec - t0.tv_sec) + (t1.tv_nsec - t0.tv_nsec) * 1e-9, threads,
+                (t2.tv_sec - t1.tv_sec) + (t2.tv_nsec - t1.tv_nsec) * 1e-9);
+    }
+    return rc;
 }
 
 /* ------------------------------------------------------------------ framer ----------- */
