@@ -31,6 +31,14 @@
 // 2^20 steps is unreachable for a valid dictionary placed by hashing.
 #define QK_WALK_CAP (1u << 20)
 
+#include <time.h>
+static double qk_now(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + ts.tv_nsec * 1e-9;
+}
+
 enum { QK_FLAG_WALK_CAP = 1, QK_FLAG_EMPTY_ON_CHAIN = 2, QK_FLAG_STASH_FULL = 4 };
 
 struct qk_build_info {
@@ -408,6 +416,8 @@ extern "C" int qk_dict_build(qk_ctx *ctx, uint64_t *n_kmers_out)
     const uint64_t n_split = H >> stride_log2;
     const uint64_t n_nodes = n_split + 2;
 
+    const int verbose = getenv("QK_TIMING") != NULL;
+    double tm0 = qk_now(), tm1 = tm0, tm2 = tm0, tm3 = tm0;
     qk_build_info *info = NULL;
     uint32_t *succ[2] = {NULL, NULL}, *seg_len = NULL;
     unsigned long long *dist[2] = {NULL, NULL};
@@ -455,6 +465,7 @@ extern "C" int qk_dict_build(qk_ctx *ctx, uint64_t *n_kmers_out)
         goto done;
     }
 
+    tm1 = qk_now(); // chain ranked
     // keys in ordinal order; after this the raw QM11 arrays are no longer needed
     QK_TRY(cudaMalloc((void **)&kbo, (total + 1) * sizeof(unsigned long long)));
     QK_TRY(cudaMemset(info, 0, sizeof(qk_build_info)));
@@ -467,6 +478,7 @@ extern "C" int qk_dict_build(qk_ctx *ctx, uint64_t *n_kmers_out)
         goto done;
     }
     skipped = hinfo.skipped;
+    tm2 = qk_now(); // keys scattered by ordinal
     cudaFree(ctx->raw_keys);
     cudaFree(ctx->raw_next);
     ctx->raw_keys = NULL;
@@ -499,6 +511,10 @@ extern "C" int qk_dict_build(qk_ctx *ctx, uint64_t *n_kmers_out)
         stash_min = hinfo.stash_used + 1024; // retry with a stash that holds what was needed
         if (attempt == 3) { rc = qk_fail(ctx, QK_ERR_NOMEM, "stash overflow after 4 attempts"); goto done; }
     }
+    tm3 = qk_now(); // table built
+    if (verbose)
+        fprintf(stderr, "[qk] build: rank %.3f s, scatter %.3f s, alloc+orient+insert %.3f s (%llu k-mers, %llu buckets)\n", tm1 - tm0,
+                tm2 - tm1, tm3 - tm2, total, (unsigned long long)d.n_buckets);
     d.stash_used = hinfo.stash_used;
     d.skipped_keys = skipped;
     ctx->desc = d;

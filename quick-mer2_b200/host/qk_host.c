@@ -808,6 +808,7 @@ int qk_count_main(int argc, char **argv)
         return 1;
     }
     uint64_t n_kmers = 0;
+    if (getenv("QK_TIMING")) fprintf(stderr, "[qk] context (pinned + device slots) %.3f s\n", now_sec() - t0);
     rc = qk_qm_load(ctx, path, NULL, &n_kmers);
     if (rc) {
         printf("Dictionary load failed: %s\n", rc == QK_ERR_IO ? "short read" : qk_last_error(ctx));

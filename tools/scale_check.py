@@ -43,8 +43,11 @@ def main():
     out["dict"] = json.loads(res.stdout.strip().splitlines()[-1])
     _, out["gen_reads_s"] = run([SYNTH, "reads", "--ref", "ref.fa", "--out", "reads.fq", "--n", args.reads, "--len", 150, "--seed", 9,
                                  "--fastq"], d)
-    res, out["ours_wall_s"] = run([CLI, "count", "-t", 12, "ref.fa", "reads.fq", "ours"], d)
+    import os
+    res, out["ours_wall_s"] = run([CLI, "count", "-t", 12, "ref.fa", "reads.fq", "ours"], d,
+                                  env=dict(os.environ, QK_TIMING="1", QK_READER_THREADS="8"))
     out["ours"] = json.loads(res.stderr.strip().splitlines()[-1])
+    out["ours_timing"] = [l for l in res.stderr.splitlines() if l.startswith("[qk]")]
     res, out["reference_wall_s"] = run([REF, "count", "-t", args.ref_threads, "ref.fa", "reads.fq", "theirs"], d)
     out["reference_stdout"] = [l for l in res.stdout.splitlines() if "elapse" in l or "depth" in l]
     out["bin_identical"] = (d / "ours.bin").read_bytes() == (d / "theirs.bin").read_bytes()
