@@ -404,12 +404,20 @@ def gpu_arm(args):
     dev_base, host_base = dev.data_ptr(), framed.data_ptr()
     n_framed = sum(sizes)
 
+    stream0 = torch.cuda.ExternalStream(ctx.slot_stream(0), device=f"cuda:{local}")
+
     def job_device():
-        # one stream: launches run back to back, so the per-launch event times are not inflated
-        # by two kernels sharing the SMs and the kernel's share of the step is meaningful
-        ctx.reset()
+        # one stream (slot 0): launches run back to back, so the per-launch event times are not
+        # inflated by two kernels sharing the SMs and the kernel's share of the step is meaningful.
+        # Nothing here waits on the host: reset, kernels and (N > 1) the reduce are stream-ordered.
+        ctx.reset_async()
         for o, s in zip(offs, sizes):
             ctx.submit_device(dev_base + o, s, slot=0)
+
+    def finish_device_step():
+        if world > 1:
+            with torch.cuda.stream(stream0):      # NCCL orders itself after slot 0's work and slot 0 after it
+                dist.reduce(counters_t, 0, op=dist.ReduceOp.SUM)
 
     def job_preframed():
         ctx.reset()
@@ -436,20 +444,21 @@ def gpu_arm(args):
 
     # ---- value: inputs resident in HBM ---------------------------------------------------
     for _ in range(args.warmup):
-        job_device(); finish_step()
+        job_device(); finish_device_step()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     ctx.reset()                                   # zero the library's kernel/launch accounting
     t_wall0 = time.time()
     ctx.span_begin()
     for _ in range(args.steps):
-        job_device(); finish_step()
+        job_device(); finish_device_step()
     span_ms = ctx.span_end()
     barrier()
     t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
-    tm = ctx.timing()                             # kernel_ms / launches of the LAST step (reset() zeroes them per step)
-    stats = ctx.stats()
+    tm = ctx.timing()                             # kernel_ms / launches summed over the K timed steps
+    tm = {"kernel_ms": tm["kernel_ms"] / args.steps, "h2d_ms": tm["h2d_ms"] / args.steps, "launches": tm["launches"] // args.steps}
+    stats = ctx.stats()                           # device totals of the last step (each step zeroes them)
     step_kmers, step_hits = stats["total_kmers"], stats["hits"]
     if world > 1:
         t = torch.tensor([span_ms], dtype=torch.float64, device=f"cuda:{local}")

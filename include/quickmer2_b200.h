@@ -141,6 +141,9 @@ int qk_submit_raw(qk_ctx *ctx, uint32_t slot, const uint8_t *bytes, size_t n_byt
 int qk_raw_stats(qk_ctx *ctx, uint64_t *read_lines, uint64_t *bases, uint64_t *raw_lines);
 /* 1 if `p` is page-locked host memory known to CUDA (async copies from it are true DMA). */
 int qk_host_is_pinned(const void *p);
+/* The cudaStream_t of a slot (as void *), so that a caller can order its own device work --
+ * e.g. an NCCL reduce of the counters -- against the slot's work without a host sync. */
+void *qk_slot_stream(qk_ctx *ctx, uint32_t slot);
 /* Block until the host buffer last submitted on `slot` may be overwritten. */
 int qk_wait_slot(qk_ctx *ctx, uint32_t slot);
 /* Block until every enqueued chunk has been counted. */
@@ -157,6 +160,8 @@ int qk_stats_ext(qk_ctx *ctx, uint64_t *verified_by_extension);
  * reduce across GPUs; the low 16 bits are the reference's uint16 depth (Q.c:23,291). */
 int qk_counters_device_ptr(const qk_ctx *ctx, uint32_t **counters, uint64_t *n_kmers);
 int qk_reset_counters(qk_ctx *ctx);
+/* The same, stream-ordered (no host synchronisation): for jobs run back to back. */
+int qk_reset_counters_async(qk_ctx *ctx);
 /* Copy `count` raw uint32 counters starting at ordinal `offset` to host memory (syncs). */
 int qk_counters_download(qk_ctx *ctx, uint64_t offset, uint32_t *out, uint64_t count);
 

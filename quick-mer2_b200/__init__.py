@@ -119,6 +119,8 @@ SIGNATURES = {
     "qk_stats_ext": (C.c_int, [_P, _U64P]),
     "qk_counters_device_ptr": (C.c_int, [_P, C.POINTER(_P), _U64P]),
     "qk_reset_counters": (C.c_int, [_P]),
+    "qk_reset_counters_async": (C.c_int, [_P]),
+    "qk_slot_stream": (_P, [_P, C.c_uint32]),
     "qk_counters_download": (C.c_int, [_P, C.c_uint64, _P, C.c_uint64]),
     "qk_finish": (C.c_int, [_P, _P, C.c_uint64]),
     "qk_gc_curve": (C.c_int, [_P, _P, C.c_uint64, _P, _P, _P]),
@@ -321,6 +323,14 @@ class Context:
 
     def reset(self):
         self._check(self._lib.qk_reset_counters(self._h))
+
+    def reset_async(self):
+        """Stream-ordered reset (no host sync) for jobs run back to back."""
+        self._check(self._lib.qk_reset_counters_async(self._h))
+
+    def slot_stream(self, slot: int = 0) -> int:
+        """cudaStream_t of a slot as an integer (e.g. for torch.cuda.ExternalStream)."""
+        return int(self._lib.qk_slot_stream(self._h, slot) or 0)
 
     def stats(self) -> dict:
         t, h, l = C.c_uint64(), C.c_uint64(), C.c_uint64()

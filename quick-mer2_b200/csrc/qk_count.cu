@@ -742,6 +742,28 @@ extern "C" int qk_reset_counters(qk_ctx *ctx)
     return QK_OK;
 }
 
+// Stream-ordered reset for back-to-back jobs: zeroes the counters and the device totals on
+// slot 0's stream after joining every other slot stream into it, and makes the other slots
+// wait for it -- no host synchronisation.  (Host-side timing accumulators keep running.)
+extern "C" int qk_reset_counters_async(qk_ctx *ctx)
+{
+    if (!ctx) return QK_ERR_ARG;
+    if (ctx->dict_state != 2) return QK_ERR_STATE;
+    QK_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s0 = ctx->slots[0].stream;
+    for (uint32_t s = 1; s < ctx->n_slots; ++s) {
+        QK_CUDA(ctx, cudaEventRecord(ctx->span_join, ctx->slots[s].stream));
+        QK_CUDA(ctx, cudaStreamWaitEvent(s0, ctx->span_join, 0));
+    }
+    QK_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, (ctx->desc.n_kmers + 1) * sizeof(uint32_t), s0));
+    QK_CUDA(ctx, cudaMemsetAsync(ctx->stats, 0, 4 * sizeof(unsigned long long), s0));
+    QK_CUDA(ctx, cudaMemsetAsync(ctx->frame_stream + 1, 0, 3 * sizeof(unsigned long long), s0));
+    QK_CUDA(ctx, cudaEventRecord(ctx->span_join, s0));
+    for (uint32_t s = 1; s < ctx->n_slots; ++s) QK_CUDA(ctx, cudaStreamWaitEvent(ctx->slots[s].stream, ctx->span_join, 0));
+    ctx->lines = 0;
+    return QK_OK;
+}
+
 extern "C" int qk_counters_download(qk_ctx *ctx, uint64_t offset, uint32_t *out, uint64_t count)
 {
     if (!ctx || !out) return QK_ERR_ARG;

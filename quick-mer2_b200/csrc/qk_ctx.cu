@@ -183,6 +183,12 @@ int qk_ring_drain(qk_ctx *ctx)
     return QK_OK;
 }
 
+extern "C" void *qk_slot_stream(qk_ctx *ctx, uint32_t slot)
+{
+    if (!ctx || slot >= ctx->n_slots) return NULL;
+    return (void *)ctx->slots[slot].stream;
+}
+
 extern "C" int qk_wait_slot(qk_ctx *ctx, uint32_t slot)
 {
     if (!ctx || slot >= ctx->n_slots) return QK_ERR_ARG;
