@@ -160,6 +160,10 @@ int qk_stats_ext(qk_ctx *ctx, uint64_t *verified_by_extension);
  * reduce across GPUs; the low 16 bits are the reference's uint16 depth (Q.c:23,291). */
 int qk_counters_device_ptr(const qk_ctx *ctx, uint32_t **counters, uint64_t *n_kmers);
 int qk_reset_counters(qk_ctx *ctx);
+/* Two counter buffers (0 = default, 1 = allocated on first use): later launches, resets,
+ * qk_counters_device_ptr, qk_finish ... use the selected one, so the reduce / download of one
+ * job can overlap the counting of the next. */
+int qk_counters_select(qk_ctx *ctx, uint32_t which);
 /* The same, stream-ordered (no host synchronisation): for jobs run back to back. */
 int qk_reset_counters_async(qk_ctx *ctx);
 /* Copy `count` raw uint32 counters starting at ordinal `offset` to host memory (syncs). */

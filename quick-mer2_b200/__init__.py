@@ -120,6 +120,7 @@ SIGNATURES = {
     "qk_counters_device_ptr": (C.c_int, [_P, C.POINTER(_P), _U64P]),
     "qk_reset_counters": (C.c_int, [_P]),
     "qk_reset_counters_async": (C.c_int, [_P]),
+    "qk_counters_select": (C.c_int, [_P, C.c_uint32]),
     "qk_slot_stream": (_P, [_P, C.c_uint32]),
     "qk_counters_download": (C.c_int, [_P, C.c_uint64, _P, C.c_uint64]),
     "qk_finish": (C.c_int, [_P, _P, C.c_uint64]),
@@ -323,6 +324,10 @@ class Context:
 
     def reset(self):
         self._check(self._lib.qk_reset_counters(self._h))
+
+    def select_counters(self, which: int):
+        """Use counter buffer 0 or 1 for what is issued from now on."""
+        self._check(self._lib.qk_counters_select(self._h, which))
 
     def reset_async(self):
         """Stream-ordered reset (no host sync) for jobs run back to back."""

@@ -75,7 +75,8 @@ struct qk_ctx {
     uint32_t *ext_last, *ext_first, *ext_cont; // dictionary-order extension arrays (k = 30), else NULL
     qk_table_desc desc;
 
-    uint32_t *counters;       // n_kmers x u32, indexed by ordinal
+    uint32_t *counters;       // n_kmers x u32, indexed by ordinal: the buffer jobs currently count into
+    uint32_t *counters_buf[2]; // [0] always allocated with the table; [1] on first qk_counters_select(1)
     unsigned long long *stats; // device: [0] emitted k-mers, [1] hits
     uint64_t lines;
 

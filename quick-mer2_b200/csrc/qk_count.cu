@@ -742,6 +742,23 @@ extern "C" int qk_reset_counters(qk_ctx *ctx)
     return QK_OK;
 }
 
+// Two counter buffers, so that the reduce / download of one job overlaps the counting of the
+// next (samples run back to back against one dictionary).  Selecting a buffer affects the
+// launches, resets and downloads issued AFTER the call; work already enqueued keeps its buffer.
+extern "C" int qk_counters_select(qk_ctx *ctx, uint32_t which)
+{
+    if (!ctx || which > 1) return QK_ERR_ARG;
+    if (ctx->dict_state != 2) return QK_ERR_STATE;
+    if (!ctx->counters_buf[which]) {
+        QK_CUDA(ctx, cudaSetDevice(ctx->device));
+        QK_CUDA(ctx, cudaMalloc((void **)&ctx->counters_buf[which], (ctx->desc.n_kmers + 1) * sizeof(uint32_t)));
+        QK_CUDA(ctx, cudaMemset(ctx->counters_buf[which], 0, (ctx->desc.n_kmers + 1) * sizeof(uint32_t)));
+        QK_CUDA(ctx, cudaDeviceSynchronize());
+    }
+    ctx->counters = ctx->counters_buf[which];
+    return QK_OK;
+}
+
 // Stream-ordered reset for back-to-back jobs: zeroes the counters and the device totals on
 // slot 0's stream after joining every other slot stream into it, and makes the other slots
 // wait for it -- no host synchronisation.  (Host-side timing accumulators keep running.)

@@ -123,7 +123,8 @@ extern "C" void qk_ctx_destroy(qk_ctx *ctx)
     cudaFree(ctx->ext_last);
     cudaFree(ctx->ext_first);
     cudaFree(ctx->ext_cont);
-    cudaFree(ctx->counters);
+    cudaFree(ctx->counters_buf[0]);
+    cudaFree(ctx->counters_buf[1]);
     cudaFree(ctx->stats);
     cudaFree(ctx->frame_stream);
     cudaFree(ctx->frame_elems);

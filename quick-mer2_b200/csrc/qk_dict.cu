@@ -62,8 +62,10 @@ extern "C" int qk_dict_begin(qk_ctx *ctx, uint8_t k, uint64_t hash_size, uint64_
     cudaFree(ctx->raw_next);
     cudaFree(ctx->buckets);
     cudaFree(ctx->stash);
-    cudaFree(ctx->counters);
+    cudaFree(ctx->counters_buf[0]);
+    cudaFree(ctx->counters_buf[1]);
     ctx->raw_keys = NULL; ctx->raw_next = NULL; ctx->buckets = NULL; ctx->stash = NULL; ctx->counters = NULL;
+    ctx->counters_buf[0] = ctx->counters_buf[1] = NULL;
     ctx->dict_state = 0;
     QK_CUDA(ctx, cudaMalloc((void **)&ctx->raw_keys, hash_size * sizeof(uint64_t)));
     QK_CUDA(ctx, cudaMalloc((void **)&ctx->raw_next, hash_size * sizeof(uint32_t)));
@@ -375,7 +377,9 @@ static int qk_alloc_table(qk_ctx *ctx, const qk_table_desc *d)
 {
     cudaFree(ctx->buckets);
     cudaFree(ctx->stash);
-    cudaFree(ctx->counters);
+    cudaFree(ctx->counters_buf[0]);
+    cudaFree(ctx->counters_buf[1]);
+    ctx->counters_buf[0] = ctx->counters_buf[1] = NULL;
     cudaFree(ctx->ext_last);
     cudaFree(ctx->ext_first);
     cudaFree(ctx->ext_cont);
@@ -391,7 +395,8 @@ static int qk_alloc_table(qk_ctx *ctx, const qk_table_desc *d)
         QK_CUDA(ctx, cudaMemset(ctx->ext_first, 0, d->ext_bytes));
         QK_CUDA(ctx, cudaMemset(ctx->ext_cont, 0, d->cont_bytes));
     }
-    QK_CUDA(ctx, cudaMalloc((void **)&ctx->counters, (d->n_kmers + 1) * sizeof(uint32_t)));
+    QK_CUDA(ctx, cudaMalloc((void **)&ctx->counters_buf[0], (d->n_kmers + 1) * sizeof(uint32_t)));
+    ctx->counters = ctx->counters_buf[0];
     QK_CUDA(ctx, cudaMemset(ctx->counters, 0, (d->n_kmers + 1) * sizeof(uint32_t)));
     QK_CUDA(ctx, cudaMemset(ctx->stats, 0, 4 * sizeof(unsigned long long))); // a new dictionary starts a new count
     QK_CUDA(ctx, cudaMemset(ctx->frame_stream, 0, 4 * sizeof(unsigned long long)));

@@ -465,6 +465,25 @@ def test_properties_at_size(qk, synth, tmp_path):
         assert np.array_equal(ctx2.finish().astype(np.int64), b)
 
 
+def test_two_counter_buffers_and_async_reset(qk, oracle, gpu_ctx):
+    """Back-to-back jobs: buffer 1 takes a job while buffer 0 keeps the previous result."""
+    d = GOLDEN / "k30_fasta_t0"
+    want = np.fromfile(d / "expect.bin", dtype=np.uint16)
+    gpu_ctx.load_dictionary(d / "ref.fa.qm")
+    gpu_ctx.count_file(d / "reads.fa")
+    gpu_ctx.select_counters(1)
+    assert not gpu_ctx.finish().any()                       # a fresh buffer
+    gpu_ctx.count_file(d / "reads.fa")
+    gpu_ctx.count_file(d / "reads.fa")
+    assert np.array_equal(gpu_ctx.finish().astype(np.int64), 2 * want.astype(np.int64))
+    gpu_ctx.reset_async()                                   # stream-ordered: no host sync needed before the next job
+    gpu_ctx.count_file(d / "reads.fa")
+    assert np.array_equal(gpu_ctx.finish(), want)
+    gpu_ctx.select_counters(0)
+    assert np.array_equal(gpu_ctx.finish(), want)           # untouched by the jobs on buffer 1
+    assert gpu_ctx.slot_stream(0) != 0
+
+
 def test_depth_wraps_like_uint16(qk, oracle, gpu_ctx, tmp_path):
     """T12: one 30-mer seen 70,000 times reads 70,000 mod 65,536 = 4,464 (no saturation)."""
     kmer = "ACGTTGCATGCCGATAGGCTAACGTTAGCC"
