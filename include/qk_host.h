@@ -105,9 +105,15 @@ int qk_shard_bounds(const char *reads_path, uint32_t rank, uint32_t world, uint6
 int qk_fastq_state_guess(const uint8_t *window, size_t n, uint32_t *line_state);
 int qk_count_raw_range(qk_ctx *ctx, const char *reads_path, uint64_t begin, uint64_t end, int fastq, uint32_t line_state,
                        qk_framer_stats *st, uint32_t *final_state);
+int qk_count_raw_range_mt(qk_ctx *ctx, const char *reads_path, uint64_t begin, uint64_t end, int fastq, uint32_t line_state,
+                          uint32_t threads, qk_framer_stats *st, uint32_t *final_state);
+/* The whole file over the GPUs of a qk_multi, one shard and `threads_per_gpu` readers per GPU,
+ * with the guess / verify / recount loop described above done here in C.  A pipe is counted by
+ * context 0 alone.  Call qk_multi_reduce afterwards. */
+int qk_count_file_multi(qk_multi *m, const char *reads_path, uint32_t threads_per_gpu, qk_framer_stats *st);
 
 /* ---- the command: main_count, Q.c:304-545 -----------------------------------------------
- * quicKmer2 count [-h] [-t N] [-g device] ref_prefix reads out_prefix
+ * quicKmer2 count [-h] [-t N] [-g device[,device...]] ref_prefix reads out_prefix
  * Same positional-from-the-end convention, same stdout lines, same files. */
 int qk_count_main(int argc, char **argv);
 

@@ -180,6 +180,22 @@ int qk_finish(qk_ctx *ctx, uint16_t *counts_out, uint64_t n_kmers);
 int qk_gc_curve(qk_ctx *ctx, const uint16_t *qgc, uint64_t n_kmers, uint64_t sum[QK_GC_BINS],
                 int64_t sumsq[QK_GC_BINS], uint64_t count[QK_GC_BINS]);
 
+/* ------------------------------------------------------------------ several GPUs -----
+ * One process, one context per device: the dictionary built on context 0 is
+ * replicated with ncclBroadcast, every context counts its share of the reads, the u32 counters
+ * are added into context 0 with ncclReduce; qk_finish / qk_gc_curve then run on context 0.
+ * NCCL (libnccl.so.2) is bound at run time and only when n > 1.  For one process PER GPU
+ * (torchrun) use qk_dict_describe / adopt / device_ptrs with the launcher's own collectives
+ * instead (quick-mer2_b200/dist.py). */
+typedef struct qk_multi qk_multi;
+int qk_multi_create(qk_multi **out, const int *devices, uint32_t n, uint32_t n_slots, size_t chunk_capacity);
+void qk_multi_destroy(qk_multi *m);
+const char *qk_multi_last_error(const qk_multi *m);
+uint32_t qk_multi_size(const qk_multi *m);
+qk_ctx *qk_multi_ctx(qk_multi *m, uint32_t i);
+int qk_multi_replicate(qk_multi *m); /* dictionary of context 0 -> all */
+int qk_multi_reduce(qk_multi *m);    /* counters of all -> context 0 (syncs) */
+
 /* ------------------------------------------------------------------ measurement -----
  * Device time (ms) spent in count kernels / H2D copies on all slots since the last
  * qk_reset_counters, from CUDA events recorded on the slots' streams, and the number of

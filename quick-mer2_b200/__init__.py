@@ -130,6 +130,13 @@ SIGNATURES = {
     "qk_span_end": (C.c_int, [_P, C.POINTER(C.c_double)]),
     "qk_bench_gather": (C.c_int, [_P, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(C.c_double)]),
     "qk_bench_h2d": (C.c_int, [_P, C.c_size_t, C.c_int, C.POINTER(C.c_double)]),
+    "qk_multi_create": (C.c_int, [C.POINTER(_P), C.POINTER(C.c_int), C.c_uint32, C.c_uint32, C.c_size_t]),
+    "qk_multi_destroy": (None, [_P]),
+    "qk_multi_last_error": (C.c_char_p, [_P]),
+    "qk_multi_size": (C.c_uint32, [_P]),
+    "qk_multi_ctx": (_P, [_P, C.c_uint32]),
+    "qk_multi_replicate": (C.c_int, [_P]),
+    "qk_multi_reduce": (C.c_int, [_P]),
     # qk_host.h
     "qk_qm_read_header": (C.c_int, [C.c_char_p, C.POINTER(QmHeader)]),
     "qk_qm_load": (C.c_int, [_P, C.c_char_p, C.POINTER(QmHeader), _U64P]),
@@ -151,6 +158,9 @@ SIGNATURES = {
     "qk_count_raw_range": (C.c_int, [_P, C.c_char_p, C.c_uint64, C.c_uint64, C.c_int, C.c_uint32, C.POINTER(FramerStats),
                                      C.POINTER(C.c_uint32)]),
     "qk_count_raw_file_mt": (C.c_int, [_P, C.c_char_p, C.c_uint32, C.POINTER(FramerStats)]),
+    "qk_count_raw_range_mt": (C.c_int, [_P, C.c_char_p, C.c_uint64, C.c_uint64, C.c_int, C.c_uint32, C.c_uint32,
+                                        C.POINTER(FramerStats), C.POINTER(C.c_uint32)]),
+    "qk_count_file_multi": (C.c_int, [_P, C.c_char_p, C.c_uint32, C.POINTER(FramerStats)]),
     "qk_count_main": (C.c_int, [C.c_int, C.POINTER(C.c_char_p)]),
 }
 

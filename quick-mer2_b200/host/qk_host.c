@@ -485,8 +485,18 @@ int qk_fastq_state_guess(const uint8_t *window, size_t n, uint32_t *line_state)
     return QK_ERR_FORMAT;
 }
 
+static int count_range_mt(qk_ctx *ctx, int fd, uint64_t begin, uint64_t end, uint32_t threads, uint64_t *unterminated);
+static uint32_t reader_threads_default(void);
+#define QK_HEAD ((size_t)128 << 10) /* >= the longest line the reference reads (100,000 bytes) */
+
 int qk_count_raw_range(qk_ctx *ctx, const char *reads_path, uint64_t begin, uint64_t end, int fastq, uint32_t line_state,
                        qk_framer_stats *st, uint32_t *final_state)
+{
+    return qk_count_raw_range_mt(ctx, reads_path, begin, end, fastq, line_state, 0, st, final_state);
+}
+
+int qk_count_raw_range_mt(qk_ctx *ctx, const char *reads_path, uint64_t begin, uint64_t end, int fastq, uint32_t line_state,
+                          uint32_t threads, qk_framer_stats *st, uint32_t *final_state)
 {
     uint32_t n_slots = 0;
     size_t cap = 0;
@@ -497,6 +507,10 @@ int qk_count_raw_range(qk_ctx *ctx, const char *reads_path, uint64_t begin, uint
     rc = qk_raw_begin_state(ctx, fastq, line_state);
     uint64_t unterminated = 0, pos = begin;
     uint32_t slot = 0;
+    if (!rc && cap >= 4 * QK_HEAD && end > begin) {      /* reader threads fill the pinned slots in parallel */
+        rc = count_range_mt(ctx, fd, begin, end, threads ? threads : reader_threads_default(), &unterminated);
+        pos = end;
+    }
     while (!rc && pos < end) {
         rc = qk_wait_slot(ctx, slot);
         if (rc) break;
@@ -540,8 +554,6 @@ int qk_count_raw_range(qk_ctx *ctx, const char *reads_path, uint64_t begin, uint
  * pinned buffers (at offset QK_HEAD), the submitting thread takes the pieces in order, puts
  * the partial last line of the previous piece in front (that is what the QK_HEAD bytes of
  * headroom are for), cuts at the last '\n' and enqueues H2D + framing + counting. */
-#define QK_HEAD ((size_t)128 << 10) /* >= the longest line the reference reads (100,000 bytes) */
-
 typedef struct {
     qk_ctx *ctx;
     int fd;
@@ -744,13 +756,102 @@ int qk_count_raw_file(qk_ctx *ctx, const char *reads_path, qk_framer_stats *st)
     return qk_count_raw_file_mt(ctx, reads_path, 0, st);
 }
 
+/* ---- one reads file over the GPUs of a qk_multi ---------------------------------------------
+ * Shard r = the line-aligned r-th part of the file (qk_shard_bounds), counted by context r with
+ * its own reader threads.  FASTA shards start in line state 0; FASTQ shards start in the state
+ * guessed from their first lines, all at once, and afterwards every assumed state is checked
+ * against the state its predecessor really ended in -- a shard whose guess was wrong (malformed
+ * FASTQ only) is zeroed and recounted from the true state, then the check repeats. */
+typedef struct {
+    qk_ctx *ctx;
+    const char *path;
+    uint64_t begin, end;
+    int fastq;
+    uint32_t state, final_state, threads;
+    qk_framer_stats st;
+    int rc, todo;
+} shard_job;
+
+static void *shard_worker(void *arg)
+{
+    shard_job *j = arg;
+    j->rc = qk_count_raw_range_mt(j->ctx, j->path, j->begin, j->end, j->fastq, j->state, j->threads, &j->st, &j->final_state);
+    return NULL;
+}
+
+int qk_count_file_multi(qk_multi *m, const char *reads_path, uint32_t threads_per_gpu, qk_framer_stats *st)
+{
+    const uint32_t n = qk_multi_size(m);
+    if (!m || n == 0 || !reads_path) return QK_ERR_ARG;
+    struct stat sb;
+    if (n == 1 || stat(reads_path, &sb) != 0 || !S_ISREG(sb.st_mode) || sb.st_size == 0)
+        return qk_count_raw_file_mt(qk_multi_ctx(m, 0), reads_path, threads_per_gpu, st); /* pipes: one GPU */
+    int fd = open(reads_path, O_RDONLY);
+    if (fd < 0) return QK_ERR_IO;
+    uint8_t first = 0;
+    if (pread(fd, &first, 1, 0) != 1) { close(fd); return QK_ERR_IO; }
+    const int fastq = first == '@';
+    shard_job job[QK_HOST_MAX_SLOTS];
+    memset(job, 0, sizeof job);
+    uint8_t *window = malloc(1 << 20);
+    int rc = window ? QK_OK : QK_ERR_NOMEM;
+    for (uint32_t r = 0; !rc && r < n; ++r) {
+        shard_job *j = &job[r];
+        j->ctx = qk_multi_ctx(m, r);
+        j->path = reads_path;
+        j->fastq = fastq;
+        j->threads = threads_per_gpu;
+        j->todo = 1;
+        rc = qk_shard_bounds(reads_path, r, n, &j->begin, &j->end);
+        if (rc) break;
+        if (r == 0) j->state = fastq ? 3 : 0;            /* the first line of a FASTQ is consumed (Q.c:393-395) */
+        else if (fastq) {
+            ssize_t got = pread(fd, window, 1 << 20, (off_t)j->begin);
+            qk_fastq_state_guess(window, got > 0 ? (size_t)got : 0, &j->state);
+        }
+    }
+    free(window);
+    close(fd);
+    for (uint32_t round = 0; !rc && round <= n; ++round) {
+        pthread_t th[QK_HOST_MAX_SLOTS];
+        for (uint32_t r = 0; r < n; ++r)
+            if (job[r].todo && pthread_create(&th[r], NULL, shard_worker, &job[r]) != 0) { job[r].rc = QK_ERR_NOMEM; job[r].todo = 2; }
+        for (uint32_t r = 0; r < n; ++r) {
+            if (job[r].todo == 1) pthread_join(th[r], NULL);
+            if (job[r].todo && job[r].rc) rc = job[r].rc;
+            job[r].todo = 0;
+        }
+        if (rc) break;
+        uint32_t carry = job[0].state, bad = n;
+        for (uint32_t r = 0; r < n; ++r) {               /* the first shard whose assumed state was wrong */
+            if (job[r].end == job[r].begin) continue;
+            if (r > 0 && job[r].state != carry) { bad = r; break; }
+            carry = job[r].final_state;
+        }
+        if (bad == n) break;
+        job[bad].state = carry;
+        job[bad].todo = 1;
+        rc = qk_reset_counters(job[bad].ctx);
+    }
+    if (rc || !st) return rc;
+    memset(st, 0, sizeof *st);
+    st->fastq = fastq;
+    for (uint32_t r = 0; r < n; ++r) {
+        st->lines += job[r].st.lines;
+        st->bases += job[r].st.bases;
+        st->raw_bytes += job[r].st.raw_bytes;
+        st->unterminated += job[r].st.unterminated;
+    }
+    return QK_OK;
+}
+
 /* ------------------------------------------------------------------ command ---------- */
 static void help_count(void)
 {
     puts("\nquicKmer2 count [Options] ref.fa sample.fast[a/q] Out_prefix\n\nOptions:");
     puts("-h\t\tShow this help information");
     puts("-t [num]\tNumber of threads reading the input into pinned memory (counting runs on the GPU)");
-    puts("-g [num]\tCUDA device index (default 0)");
+    puts("-g [list]\tCUDA device index, or a comma-separated list to shard the reads over several GPUs (default 0)");
 }
 
 static double now_sec(void)
@@ -762,7 +863,8 @@ static double now_sec(void)
 
 int qk_count_main(int argc, char **argv)
 {
-    int device = 0;
+    int devices[QK_HOST_MAX_SLOTS] = {0};
+    uint32_t n_dev = 1;
     unsigned threads = 0;
     if (argc < 2) { help_count(); return 1; }          /* Q.c:309-312 */
     int opt;
@@ -774,7 +876,16 @@ int qk_count_main(int argc, char **argv)
             threads = (uint8_t)atoi(optarg);            /* uint8_t thread_count, Q.c:306 */
             printf("[Option] Set %u threads\n", threads);
             break;
-        case 'g': device = atoi(optarg); break;
+        case 'g':                                       /* one device or a comma-separated list */
+            n_dev = 0;
+            for (const char *p = optarg; *p && n_dev < QK_HOST_MAX_SLOTS;) {
+                devices[n_dev++] = atoi(p);
+                p = strchr(p, ',');
+                if (!p) break;
+                ++p;
+            }
+            if (n_dev == 0) { puts("Option error, check help"); help_count(); return 1; }
+            break;
         case '?': puts("Option error, check help"); help_count(); return 1;
         default: return 1;
         }
@@ -790,32 +901,37 @@ int qk_count_main(int argc, char **argv)
     }
     const int host_framer = getenv("QK_HOST_FRAMER") != NULL; /* default: the device frames the raw stream */
     qk_framer *fr = NULL;
-    int reads_fd = -1, reads_seekable = 0;
     if (host_framer) fr = qk_framer_open(reads);
     else {
-        reads_fd = open(reads, O_RDONLY);
-        reads_seekable = reads_fd >= 0 && lseek(reads_fd, 0, SEEK_CUR) != (off_t)-1;
+        int probe = open(reads, O_RDONLY);              /* only to fail early; the drivers reopen it */
+        if (probe < 0) { puts("Input open fail"); return 1; } /* Q.c:339-341 (the reference goes on and crashes) */
+        if (lseek(probe, 0, SEEK_CUR) != (off_t)-1) close(probe);
+        else reads = NULL, fr = NULL, devices[QK_HOST_MAX_SLOTS - 1] = probe; /* a pipe: keep the descriptor */
     }
-    if (!fr && reads_fd < 0) { puts("Input open fail"); return 1; } /* Q.c:339-341 (the reference goes on and crashes) */
+    const int pipe_fd = reads ? -1 : devices[QK_HOST_MAX_SLOTS - 1];
+    if (host_framer && !fr) { puts("Input open fail"); return 1; }
     printf("Hash Size: 0x%lX\nFirst location: 0x%lX\n", (unsigned long)hdr.hash_size, (unsigned long)hdr.first_idx);
 
     double t0 = now_sec();
-    qk_ctx *ctx = NULL;
-    int rc = qk_ctx_create(&ctx, device, 8, (size_t)32 << 20);
+    qk_multi *m = NULL;
+    int rc = qk_multi_create(&m, devices, n_dev, 8, (size_t)32 << 20);
     if (rc) {
-        printf("GPU context failed: %s\n", ctx ? qk_last_error(ctx) : "no CUDA device");
-        qk_ctx_destroy(ctx);
+        printf("GPU context failed: %s\n", m ? qk_multi_last_error(m) : "no CUDA device");
+        qk_multi_destroy(m);
         return 1;
     }
+    qk_ctx *ctx = qk_multi_ctx(m, 0);
     uint64_t n_kmers = 0;
-    if (getenv("QK_TIMING")) fprintf(stderr, "[qk] context (pinned + device slots) %.3f s\n", now_sec() - t0);
+    if (getenv("QK_TIMING")) fprintf(stderr, "[qk] contexts (pinned + device slots) %.3f s\n", now_sec() - t0);
     rc = qk_qm_load(ctx, path, NULL, &n_kmers);
     if (rc) {
         printf("Dictionary load failed: %s\n", rc == QK_ERR_IO ? "short read" : qk_last_error(ctx));
         if (rc == QK_ERR_NOMEM) puts("Memory allocation failed"); /* Q.c:355,362 */
-        qk_ctx_destroy(ctx);
+        qk_multi_destroy(m);
         return 1;
     }
+    rc = qk_multi_replicate(m);                          /* ncclBroadcast of the table to the other GPUs */
+    if (rc) { printf("Dictionary broadcast failed: %s\n", qk_multi_last_error(m)); qk_multi_destroy(m); return 1; }
     printf("Read 0x%lX hash\n", (unsigned long)hdr.hash_size);            /* Q.c:359 */
     double t1 = now_sec();
     time_t start_time, end_time;
@@ -824,25 +940,32 @@ int qk_count_main(int argc, char **argv)
     if (host_framer) {
         rc = qk_count_framer(ctx, fr, &st);
         qk_framer_close(fr);
+    } else if (pipe_fd >= 0) {
+        rc = qk_count_raw_fd(ctx, pipe_fd, 0, &st);      /* a pipe feeds one GPU */
+        close(pipe_fd);
     } else {
-        close(reads_fd);
-        (void)reads_seekable;
-        rc = qk_count_raw_file_mt(ctx, reads, threads, &st); /* -t N: reader threads (0 = default) */
+        rc = qk_count_file_multi(m, reads, threads, &st); /* -t N: reader threads per GPU (0 = default) */
     }
     uint64_t total = 0, hits = 0;
-    if (!rc) rc = qk_stats(ctx, &total, &hits, NULL);
-    if (rc) { printf("Counting failed: %s\n", qk_last_error(ctx)); qk_ctx_destroy(ctx); return 1; }
+    for (uint32_t i = 0; !rc && i < n_dev; ++i) {
+        uint64_t t = 0, h = 0;
+        rc = qk_stats(qk_multi_ctx(m, i), &t, &h, NULL);
+        total += t;
+        hits += h;
+    }
+    if (!rc) rc = qk_multi_reduce(m);                    /* ncclReduce of the counters into GPU 0 */
+    if (rc) { printf("Counting failed: %s / %s\n", qk_last_error(ctx), qk_multi_last_error(m)); qk_multi_destroy(m); return 1; }
     time(&end_time);
     double t2 = now_sec();
     printf("Counting elapse %u sec, total %lu kmers\n", (unsigned)(end_time - start_time), (unsigned long)total); /* Q.c:481 */
     printf("Pileup finish\nRead chain file %lu entries\n", (unsigned long)hdr.hash_size);                         /* Q.c:483 */
 
     uint16_t *counts = malloc((n_kmers ? n_kmers : 1) * sizeof(uint16_t));
-    if (!counts) { puts("Memory allocation failed"); qk_ctx_destroy(ctx); return 1; }
+    if (!counts) { puts("Memory allocation failed"); qk_multi_destroy(m); return 1; }
     rc = qk_finish(ctx, counts, n_kmers);
-    if (rc) { printf("Result download failed: %s\n", qk_last_error(ctx)); free(counts); qk_ctx_destroy(ctx); return 1; }
+    if (rc) { printf("Result download failed: %s\n", qk_last_error(ctx)); free(counts); qk_multi_destroy(m); return 1; }
     snprintf(path, sizeof path, "%s.bin", out_prefix);
-    if (qk_write_bin(path, counts, n_kmers)) { printf("Cannot write %s\n", path); free(counts); qk_ctx_destroy(ctx); return 1; }
+    if (qk_write_bin(path, counts, n_kmers)) { printf("Cannot write %s\n", path); free(counts); qk_multi_destroy(m); return 1; }
     free(counts);
 
     snprintf(path, sizeof path, "%s.qgc", ref_prefix);                     /* Q.c:484-488 */
@@ -850,7 +973,7 @@ int qk_count_main(int argc, char **argv)
     if (!gc) printf("GC control file %s absent. Continue without GC correction!\n", path);
     else {
         uint16_t *qgc = calloc(n_kmers ? n_kmers : 1, sizeof(uint16_t));
-        if (!qgc) { puts("Memory allocation failed"); fclose(gc); qk_ctx_destroy(ctx); return 1; }
+        if (!qgc) { puts("Memory allocation failed"); fclose(gc); qk_multi_destroy(m); return 1; }
         size_t got = fread(qgc, sizeof(uint16_t), n_kmers, gc);
         (void)got;
         fclose(gc);
@@ -858,24 +981,24 @@ int qk_count_main(int argc, char **argv)
         int64_t sq[QK_GC_BINS];
         rc = qk_gc_curve(ctx, qgc, n_kmers, sum, sq, cnt);
         free(qgc);
-        if (rc) { printf("GC curve failed: %s\n", qk_last_error(ctx)); qk_ctx_destroy(ctx); return 1; }
+        if (rc) { printf("GC curve failed: %s\n", qk_last_error(ctx)); qk_multi_destroy(m); return 1; }
         double mean = 0;
         snprintf(path, sizeof path, "%s.txt", out_prefix);                 /* Q.c:523-525 */
-        if (qk_write_gc_txt(path, sum, sq, cnt, &mean)) { printf("Cannot write %s\n", path); qk_ctx_destroy(ctx); return 1; }
+        if (qk_write_gc_txt(path, sum, sq, cnt, &mean)) { printf("Cannot write %s\n", path); qk_multi_destroy(m); return 1; }
         printf("Mean sequencing depth: %.2f\n", mean);                     /* Q.c:540 */
     }
     double t3 = now_sec();
     double kms = 0, hms = 0;
     uint64_t launches = 0;
     qk_timing(ctx, &kms, &hms, &launches);
-    qk_ctx_destroy(ctx);
+    qk_multi_destroy(m);
     puts("Exit quicK-mer2 count");                                          /* Q.c:543 */
     fprintf(stderr,
             "{\"total_kmers\": %llu, \"hits\": %llu, \"lines\": %llu, \"bases\": %llu, \"fastq\": %d, "
-            "\"n_kmers\": %llu, \"load_s\": %.3f, \"count_s\": %.3f, \"dump_s\": %.3f, \"kernel_ms\": %.3f, "
+            "\"n_kmers\": %llu, \"gpus\": %u, \"load_s\": %.3f, \"count_s\": %.3f, \"dump_s\": %.3f, \"kernel_ms\": %.3f, "
             "\"h2d_ms\": %.3f, \"launches\": %llu, \"threads_option\": %u}\n",
             (unsigned long long)total, (unsigned long long)hits, (unsigned long long)st.lines,
-            (unsigned long long)st.bases, st.fastq, (unsigned long long)n_kmers, t1 - t0, t2 - t1, t3 - t2, kms, hms,
+            (unsigned long long)st.bases, st.fastq, (unsigned long long)n_kmers, n_dev, t1 - t0, t2 - t1, t3 - t2, kms, hms,
             (unsigned long long)launches, threads);
     return 0;
 }

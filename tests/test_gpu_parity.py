@@ -430,6 +430,47 @@ def test_sharded_file_equals_whole_file(kind, world, mid_dict, qk, oracle, synth
             c.close()
 
 
+def _n_gpus(qk):
+    return qk.lib().qk_device_count()
+
+
+@pytest.mark.parametrize("kind", ["fastq", "fasta", "fastq_out_of_phase", "golden"])
+def test_cli_on_several_gpus(kind, mid_dict, qk, oracle, synth, tmp_path):
+    """`quicKmer2_b200 count -g 0,1[,2,3]`: one process, NCCL broadcast of the dictionary, one
+    shard per GPU, NCCL reduce of the counters -- same .bin / .txt as one GPU and the reference."""
+    n = _n_gpus(qk)
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs (gpurun --gpus 2)")
+    gpus = ",".join(str(i) for i in range(min(n, 4)))
+    if kind == "golden":
+        d = GOLDEN / "k30_fastq_t3"
+        ref, reads = d / "ref.fa", d / "reads.fq"
+        want_bin, want_txt = (d / "expect.bin").read_bytes(), (d / "expect.txt").read_bytes()
+    else:
+        ref = mid_dict / "ref.fa"
+        reads = tmp_path / ("r.fa" if kind == "fasta" else "r.fq")
+        synth("reads", "--ref", ref, "--out", reads, "--n", 200000, "--len", 150, "--seed", 21,
+              *(["--fastq", "--rand-qual"] if kind != "fasta" else []))
+        if kind == "fastq_out_of_phase":
+            data = reads.read_bytes()
+            cut = data.index(b"\n@", len(data) // 10) + 1
+            reads.write_bytes(data[:cut] + b"@odd\n>not a read\n+\nIIII\n" + data[cut:])
+        oracle.count(ref, reads, tmp_path / "want")
+        want_bin, want_txt = (tmp_path / "want.bin").read_bytes(), (tmp_path / "want.txt").read_bytes()
+    res = qk.run_cli(["count", "-t", "4", "-g", gpus, ref, reads, tmp_path / "multi"])
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert (tmp_path / "multi.bin").read_bytes() == want_bin
+    assert (tmp_path / "multi.txt").read_bytes() == want_txt
+    import json
+    info = json.loads(res.stderr.strip().splitlines()[-1])
+    assert info["gpus"] == min(n, 4)
+    res1 = qk.run_cli(["count", "-g", "0", ref, reads, tmp_path / "single"])
+    assert res1.returncode == 0
+    assert json.loads(res1.stderr.strip().splitlines()[-1])["total_kmers"] == info["total_kmers"]
+    assert [l for l in res.stdout.splitlines() if "total" in l][0].split("total")[1] == \
+           [l for l in res1.stdout.splitlines() if "total" in l][0].split("total")[1]
+
+
 # ------------------------------------------------------------------ properties at size -----
 def test_properties_at_size(qk, synth, tmp_path):
     """16 Mb dictionary, 2 M reads (~240 M k-mers): too slow for the oracle in a unit test, so
