@@ -901,14 +901,14 @@ int qk_count_main(int argc, char **argv)
     }
     const int host_framer = getenv("QK_HOST_FRAMER") != NULL; /* default: the device frames the raw stream */
     qk_framer *fr = NULL;
+    int pipe_fd = -1;                                   /* >= 0: the input is not seekable (README.md:89-90) */
     if (host_framer) fr = qk_framer_open(reads);
     else {
-        int probe = open(reads, O_RDONLY);              /* only to fail early; the drivers reopen it */
+        int probe = open(reads, O_RDONLY);
         if (probe < 0) { puts("Input open fail"); return 1; } /* Q.c:339-341 (the reference goes on and crashes) */
-        if (lseek(probe, 0, SEEK_CUR) != (off_t)-1) close(probe);
-        else reads = NULL, fr = NULL, devices[QK_HOST_MAX_SLOTS - 1] = probe; /* a pipe: keep the descriptor */
+        if (lseek(probe, 0, SEEK_CUR) != (off_t)-1) close(probe); /* regular file: the drivers reopen it */
+        else pipe_fd = probe;                           /* a pipe can be opened only once: keep it */
     }
-    const int pipe_fd = reads ? -1 : devices[QK_HOST_MAX_SLOTS - 1];
     if (host_framer && !fr) { puts("Input open fail"); return 1; }
     printf("Hash Size: 0x%lX\nFirst location: 0x%lX\n", (unsigned long)hdr.hash_size, (unsigned long)hdr.first_idx);
 
