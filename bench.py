@@ -280,8 +280,11 @@ def cpu_threads():
 
 
 def cpu_baseline(name, cdir, threads=None):
-    d, ref, sample = prepare(name, cdir, sample=True)
     w = WORKLOADS[name]
+    if not REF_BIN.exists():      # only the single-threaded port is here: keep its sample to ~10-20 s of CPU work
+        w = dict(w, sample_reads=max(1000, w["sample_reads"] // 8))
+        WORKLOADS[name] = w
+    d, ref, sample = prepare(name, cdir, sample=True)
     t, ncpu = cpu_threads()
     t = threads or t
     if REF_BIN.exists():
