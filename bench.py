@@ -351,8 +351,15 @@ def gpu_arm(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the count path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
-    if world > 1:
+    if os.environ.get("QK_BENCH_PREALLOC_MB"):       # diagnostic: shift where later allocations land in HBM
+        _shift = torch.empty(int(os.environ["QK_BENCH_PREALLOC_MB"]) << 20, dtype=torch.uint8, device=f"cuda:{local}")
+    if world > 1 or os.environ.get("QK_BENCH_FORCE_DIST"):
+        if world == 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29577")
+            os.environ.setdefault("RANK", "0"); os.environ.setdefault("WORLD_SIZE", "1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if world == 1:
+            _t = torch.ones(1 << 20, device=f"cuda:{local}"); dist.all_reduce(_t); torch.cuda.synchronize()
     qk = load_package()
     import importlib
     qd = importlib.import_module("quickmer2_b200.dist")
