@@ -379,9 +379,13 @@ def gpu_arm(args):
 
     chunk_cap = args.chunk_mib << 20
     ctx = qk.Context(device=local, n_slots=args.slots, chunk_capacity=chunk_cap)
+    if os.environ.get("QK_BENCH_PREALLOC_AFTER_CTX_MB"):
+        _shift2 = torch.empty(int(os.environ["QK_BENCH_PREALLOC_AFTER_CTX_MB"]) << 20, dtype=torch.uint8, device=f"cuda:{local}")
     t0 = time.perf_counter()
     if rank == 0:
         n_kmers = ctx.load_dictionary(ref.with_suffix(".fa.qm"))
+    if os.environ.get("QK_BENCH_PREALLOC_AFTER_DICT_MB"):
+        _shift3 = torch.empty(int(os.environ["QK_BENCH_PREALLOC_AFTER_DICT_MB"]) << 20, dtype=torch.uint8, device=f"cuda:{local}")
     load_s = time.perf_counter() - t0
     bcast_s = 0.0
     if world > 1:
