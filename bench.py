@@ -351,8 +351,22 @@ def gpu_arm(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the count path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
-    if os.environ.get("QK_BENCH_PREALLOC_MB"):       # diagnostic: shift where later allocations land in HBM
+    qk = load_package()
+    import importlib
+    qd = importlib.import_module("quickmer2_b200.dist")
+    if rank == 0:
+        qk.build()
+    else:
+        while not (qk.LIB_PATH.exists() and qk.SYNTH_PATH.exists()):
+            time.sleep(0.5)
+        time.sleep(1.0)                              # rank 0's make may still be writing
+    if os.environ.get("QK_BENCH_PREALLOC_MB"):       # diagnostic: another CUDA allocation before the context
         _shift = torch.empty(int(os.environ["QK_BENCH_PREALLOC_MB"]) << 20, dtype=torch.uint8, device=f"cuda:{local}")
+    # The context goes first: with any other CUDA allocation made before it (a 64 MB torch tensor, or
+    # NCCL's buffers at init) the count kernels run 6-7 % slower -- measured, cause not established
+    # (profiles/README.md) -- so the process group is initialised after it.
+    chunk_cap = args.chunk_mib << 20
+    ctx = qk.Context(device=local, n_slots=args.slots, chunk_capacity=chunk_cap)
     if world > 1 or os.environ.get("QK_BENCH_FORCE_DIST"):
         if world == 1:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29577")
@@ -360,11 +374,6 @@ def gpu_arm(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         if world == 1:
             _t = torch.ones(1 << 20, device=f"cuda:{local}"); dist.all_reduce(_t); torch.cuda.synchronize()
-    qk = load_package()
-    import importlib
-    qd = importlib.import_module("quickmer2_b200.dist")
-    if rank == 0:
-        qk.build()
     if world > 1:
         dist.barrier()
     cdir = cache_dir(args.cache_dir)
@@ -377,8 +386,6 @@ def gpu_arm(args):
         dist.barrier()
     d, ref, reads = prepare(args.workload, cdir, rank)
 
-    chunk_cap = args.chunk_mib << 20
-    ctx = qk.Context(device=local, n_slots=args.slots, chunk_capacity=chunk_cap)
     if os.environ.get("QK_BENCH_PREALLOC_AFTER_CTX_MB"):
         _shift2 = torch.empty(int(os.environ["QK_BENCH_PREALLOC_AFTER_CTX_MB"]) << 20, dtype=torch.uint8, device=f"cuda:{local}")
     t0 = time.perf_counter()
