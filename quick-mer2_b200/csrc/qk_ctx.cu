@@ -63,14 +63,6 @@ extern "C" int qk_ctx_create(qk_ctx **out, int device, uint32_t n_slots, size_t 
     *out = ctx; // returned even on failure below so the caller can read the message
     QK_CUDA(ctx, cudaSetDevice(device));
     QK_CUDA(ctx, cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
-    {   // The probe reads one random 32-byte sector per k-mer; ask L2 not to widen the DRAM fetch
-        // beyond what QK_L2_FETCH_GRANULARITY (32/64/128, default 32; 0 = leave the driver default) says.  A hint: see DESIGN.md.
-        const char *e = getenv("QK_L2_FETCH_GRANULARITY");
-        size_t g = e ? (size_t)atoi(e) : 32;
-        if (g == 32 || g == 64 || g == 128) {
-            if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, g) != cudaSuccess) cudaGetLastError();
-        }
-    }
     for (uint32_t s = 0; s < n_slots; ++s) {
         qk_slot *sl = &ctx->slots[s];
         QK_CUDA(ctx, cudaHostAlloc((void **)&sl->host, ctx->chunk_capacity, cudaHostAllocDefault));

@@ -1,7 +1,6 @@
 #!/usr/bin/env python
 """Roofline denominators on the box: random-sector gather GB/s (qk_bench_gather) for sector
-sizes 32/64/128 B, loads in flight 1..8, table sizes 1..32 GiB, under each L2 fetch-granularity
-hint; and pinned H2D GB/s.  One JSON object per line on stdout.  (Measurement tooling: the
+sizes 32/64/128 B, loads in flight 1..8, table sizes 1..32 GiB; and pinned H2D GB/s.  One JSON object per line on stdout.  (Measurement tooling: the
 product reads QK_L2_FETCH_GRANULARITY itself.)"""
 import json
 import os
@@ -21,11 +20,9 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
             for gran in (32, 64, 128):
                 for mlp in (1, 2, 4, 8):
                     g = ctx.bench_gather(gib << 30, gran=gran, loads_in_flight=mlp, n_gathers=1 << 29)
-                    print(json.dumps({"l2_fetch": os.environ.get("QK_L2_FETCH_GRANULARITY"), "table_GiB": gib, "gran": gran,
+                    print(json.dumps({"table_GiB": gib, "gran": gran,
                                       "in_flight": mlp, "GBs": round(g, 1), "G_per_s": round(g / gran, 2)}), flush=True)
         print(json.dumps({"h2d_GBs": round(ctx.bench_h2d(64 << 20, 16), 2)}), flush=True)
 else:
     sizes = sys.argv[1] if len(sys.argv) > 1 else "1,32"
-    for g in ("0", "32", "64", "128"):
-        env = dict(os.environ, QK_L2_FETCH_GRANULARITY=g)
-        subprocess.run([sys.executable, __file__, "child", sizes], env=env, check=True)
+    subprocess.run([sys.executable, __file__, "child", sizes], check=True)
