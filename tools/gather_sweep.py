@@ -1,7 +1,6 @@
 #!/usr/bin/env python
 """Roofline denominators on the box: random-sector gather GB/s (qk_bench_gather) for sector
-sizes 32/64/128 B, loads in flight 1..8, table sizes 1..32 GiB; and pinned H2D GB/s.  One JSON object per line on stdout.  (Measurement tooling: the
-product reads QK_L2_FETCH_GRANULARITY itself.)"""
+sizes 32/64/128 B, loads in flight 1..8, table sizes 1..32 GiB; and pinned H2D GB/s.  One JSON object per line on stdout.  (Measurement tooling.)"""
 import json
 import os
 import subprocess
