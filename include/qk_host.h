@@ -71,6 +71,8 @@ void qk_framer_close(qk_framer *f);
 
 /* ---- writers: Q.c:498-518 (.bin) and Q.c:522-542 (.txt) -------------------------------- */
 int qk_write_bin(const char *path, const uint16_t *counts, uint64_t n);
+/* Device -> .bin without a host copy of the whole array (qk_finish_pieces + fwrite). */
+int qk_write_bin_from_device(qk_ctx *ctx, const char *path);
 /* 401 lines "%.2f\t%f\t%i\t%f\n" of bin/4, mean, count, variance; *mean_depth receives the
  * figure printed as "Mean sequencing depth" (Q.c:539-540). */
 int qk_write_gc_txt(const char *path, const uint64_t sum[QK_GC_BINS], const int64_t sumsq[QK_GC_BINS],

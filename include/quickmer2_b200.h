@@ -174,6 +174,12 @@ int qk_counters_download(qk_ctx *ctx, uint64_t offset, uint32_t *out, uint64_t c
  * chain, already in .bin order, wrapped to 16 bits exactly as uint16_t Kmer_depth does.
  */
 int qk_finish(qk_ctx *ctx, uint16_t *counts_out, uint64_t n_kmers);
+/* The same in pieces, in order, without a full-size host array: `consume` gets `count` depths
+ * starting at .bin index `offset` (pinned memory, valid until it returns; non-zero aborts) while
+ * the next piece is still on its way -- e.g. to write the .bin as it arrives (Q.c:510-513
+ * flushes per 1 Mi entries). */
+typedef int (*qk_piece_fn)(void *user, const uint16_t *piece, uint64_t offset, uint64_t count);
+int qk_finish_pieces(qk_ctx *ctx, qk_piece_fn consume, void *user);
 /* GC control curve sums of Q.c:501-508 from the final depths and the .qgc flags
  * (host array of n_kmers uint16): sum[b] = sum of depth, sumsq[b] = sum of the int
  * product depth*depth, count[b] = entries, for control k-mers of GC bin b. */

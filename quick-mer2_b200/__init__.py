@@ -124,6 +124,7 @@ SIGNATURES = {
     "qk_slot_stream": (_P, [_P, C.c_uint32]),
     "qk_counters_download": (C.c_int, [_P, C.c_uint64, _P, C.c_uint64]),
     "qk_finish": (C.c_int, [_P, _P, C.c_uint64]),
+    "qk_finish_pieces": (C.c_int, [_P, _P, _P]),
     "qk_gc_curve": (C.c_int, [_P, _P, C.c_uint64, _P, _P, _P]),
     "qk_timing": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), _U64P]),
     "qk_span_begin": (C.c_int, [_P]),
@@ -147,6 +148,7 @@ SIGNATURES = {
     "qk_framer_get_stats": (None, [_P, C.POINTER(FramerStats)]),
     "qk_framer_close": (None, [_P]),
     "qk_write_bin": (C.c_int, [C.c_char_p, _P, C.c_uint64]),
+    "qk_write_bin_from_device": (C.c_int, [_P, C.c_char_p]),
     "qk_write_gc_txt": (C.c_int, [C.c_char_p, _P, _P, _P, C.POINTER(C.c_double)]),
     "qk_count_file": (C.c_int, [_P, C.c_char_p, C.POINTER(FramerStats)]),
     "qk_count_framer": (C.c_int, [_P, _P, C.POINTER(FramerStats)]),
@@ -368,6 +370,13 @@ class Context:
         assert out.dtype == np.uint16 and out.size == self.n_kmers and out.flags.c_contiguous
         self._check(self._lib.qk_finish(self._h, _np_ptr(out), self.n_kmers))
         return out
+
+    def write_bin(self, path):
+        """Depths straight from the device to a .bin file, piece by piece."""
+        rc = self._lib.qk_write_bin_from_device(self._h, os.fsencode(str(path)))
+        if rc == 6:
+            raise QkError(rc, f"cannot write {path}")
+        self._check(rc)
 
     def gc_curve(self, qgc: np.ndarray):
         qgc = np.ascontiguousarray(qgc, dtype=np.uint16)

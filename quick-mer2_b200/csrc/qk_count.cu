@@ -801,51 +801,77 @@ __global__ void qk_narrow_kernel(const uint32_t *__restrict__ counters, uint16_t
         out[i] = (uint16_t)(counters[i] & 0xFFFFu);
 }
 
-// D2H of the depths.  Pageable destinations go through two pinned staging buffers so the PCIe
-// copy of piece i+1 overlaps the host memcpy of piece i (a direct pageable cudaMemcpy runs at a
-// few GB/s); a destination that is already pinned is written directly.
+// D2H of the depths, piece by piece: narrow on the device, copy into one of two pinned staging
+// buffers, hand the piece to the consumer while the next one is in flight (a direct pageable
+// cudaMemcpy runs at a few GB/s).  qk_finish with a pinned destination skips the staging.
 #define QK_FINISH_PIECE ((uint64_t)4 << 20) // entries per staged piece (8 MiB)
-extern "C" int qk_finish(qk_ctx *ctx, uint16_t *counts_out, uint64_t n_kmers)
+extern "C" int qk_finish_pieces(qk_ctx *ctx, qk_piece_fn consume, void *user)
 {
-    if (!ctx || !counts_out) return QK_ERR_ARG;
+    if (!ctx || !consume) return QK_ERR_ARG;
     if (ctx->dict_state != 2) return qk_fail(ctx, QK_ERR_STATE, "no dictionary built on this context");
-    if (n_kmers != ctx->desc.n_kmers) return qk_fail(ctx, QK_ERR_ARG, "n_kmers does not match the dictionary");
+    const uint64_t n_kmers = ctx->desc.n_kmers;
     int rc = qk_sync(ctx);
     if (rc) return rc;
     QK_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->slots[0].stream;
-    cudaPointerAttributes attr;
-    bool pinned = cudaPointerGetAttributes(&attr, counts_out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-    cudaGetLastError();
     if (!ctx->narrow_dev) QK_CUDA(ctx, cudaMalloc((void **)&ctx->narrow_dev, 2 * QK_FINISH_PIECE * sizeof(uint16_t)));
-    if (!pinned && !ctx->narrow_host)
+    if (!ctx->narrow_host)
         QK_CUDA(ctx, cudaHostAlloc((void **)&ctx->narrow_host, 2 * QK_FINISH_PIECE * sizeof(uint16_t), cudaHostAllocDefault));
     cudaEvent_t done[2];
     QK_CUDA(ctx, cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming));
     QK_CUDA(ctx, cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
     cudaError_t e = cudaSuccess;
     uint64_t prev_at = 0, prev_m = 0;
-    int b = 0;
-    for (uint64_t at = 0; at < n_kmers && e == cudaSuccess; at += QK_FINISH_PIECE, b ^= 1) {
+    int b = 0, crc = 0;
+    for (uint64_t at = 0; at < n_kmers && e == cudaSuccess && !crc; at += QK_FINISH_PIECE, b ^= 1) {
         const uint64_t m = n_kmers - at < QK_FINISH_PIECE ? n_kmers - at : QK_FINISH_PIECE;
         uint16_t *dev = ctx->narrow_dev + (uint64_t)b * QK_FINISH_PIECE;
         qk_narrow_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->counters + at, dev, m);
-        uint16_t *dst = pinned ? counts_out + at : ctx->narrow_host + (uint64_t)b * QK_FINISH_PIECE;
-        e = cudaMemcpyAsync(dst, dev, m * sizeof(uint16_t), cudaMemcpyDeviceToHost, st);
+        e = cudaMemcpyAsync(ctx->narrow_host + (uint64_t)b * QK_FINISH_PIECE, dev, m * sizeof(uint16_t), cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaEventRecord(done[b], st);
-        if (!pinned && prev_m && e == cudaSuccess) { // drain the other buffer while this piece is in flight
+        if (prev_m && e == cudaSuccess) { // consume the other buffer while this piece is in flight
             e = cudaEventSynchronize(done[b ^ 1]);
-            memcpy(counts_out + prev_at, ctx->narrow_host + (uint64_t)(b ^ 1) * QK_FINISH_PIECE, prev_m * sizeof(uint16_t));
+            if (e == cudaSuccess) crc = consume(user, ctx->narrow_host + (uint64_t)(b ^ 1) * QK_FINISH_PIECE, prev_at, prev_m);
         }
         prev_at = at;
         prev_m = m;
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (!pinned && prev_m && e == cudaSuccess)
-        memcpy(counts_out + prev_at, ctx->narrow_host + (uint64_t)(b ^ 1) * QK_FINISH_PIECE, prev_m * sizeof(uint16_t));
+    if (prev_m && e == cudaSuccess && !crc) crc = consume(user, ctx->narrow_host + (uint64_t)(b ^ 1) * QK_FINISH_PIECE, prev_at, prev_m);
     cudaEventDestroy(done[0]);
     cudaEventDestroy(done[1]);
     if (e != cudaSuccess) return qk_cuda_fail(ctx, e, "D2H of counts");
+    return crc;
+}
+
+static int qk_finish_copy(void *user, const uint16_t *piece, uint64_t offset, uint64_t count)
+{
+    memcpy((uint16_t *)user + offset, piece, count * sizeof(uint16_t));
+    return QK_OK;
+}
+
+extern "C" int qk_finish(qk_ctx *ctx, uint16_t *counts_out, uint64_t n_kmers)
+{
+    if (!ctx || !counts_out) return QK_ERR_ARG;
+    if (ctx->dict_state != 2) return qk_fail(ctx, QK_ERR_STATE, "no dictionary built on this context");
+    if (n_kmers != ctx->desc.n_kmers) return qk_fail(ctx, QK_ERR_ARG, "n_kmers does not match the dictionary");
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, counts_out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (!pinned) return qk_finish_pieces(ctx, qk_finish_copy, counts_out);
+    int rc = qk_sync(ctx);
+    if (rc) return rc;
+    QK_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->slots[0].stream;
+    if (!ctx->narrow_dev) QK_CUDA(ctx, cudaMalloc((void **)&ctx->narrow_dev, 2 * QK_FINISH_PIECE * sizeof(uint16_t)));
+    int b = 0;
+    for (uint64_t at = 0; at < n_kmers; at += QK_FINISH_PIECE, b ^= 1) { // stream order keeps the two device buffers safe
+        const uint64_t m = n_kmers - at < QK_FINISH_PIECE ? n_kmers - at : QK_FINISH_PIECE;
+        uint16_t *dev = ctx->narrow_dev + (uint64_t)b * QK_FINISH_PIECE;
+        qk_narrow_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->counters + at, dev, m);
+        QK_CUDA(ctx, cudaMemcpyAsync(counts_out + at, dev, m * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
+    }
+    QK_CUDA(ctx, cudaStreamSynchronize(st));
     return QK_OK;
 }
 

@@ -238,6 +238,22 @@ int qk_write_bin(const char *path, const uint16_t *counts, uint64_t n)
     return rc;
 }
 
+static int write_piece(void *user, const uint16_t *piece, uint64_t offset, uint64_t count)
+{
+    (void)offset;                                      /* pieces arrive in order */
+    return fwrite(piece, sizeof(uint16_t), count, (FILE *)user) == count ? QK_OK : QK_ERR_IO;
+}
+
+int qk_write_bin_from_device(qk_ctx *ctx, const char *path)
+{
+    FILE *f = fopen(path, "wb");
+    if (!f) return QK_ERR_IO;
+    setvbuf(f, NULL, _IONBF, 0);                       /* 8 MiB pieces: no point in a stdio copy */
+    int rc = qk_finish_pieces(ctx, write_piece, f);
+    if (fclose(f) != 0 && !rc) rc = QK_ERR_IO;
+    return rc;
+}
+
 int qk_write_gc_txt(const char *path, const uint64_t sum[QK_GC_BINS], const int64_t sumsq[QK_GC_BINS],
                     const uint64_t count[QK_GC_BINS], double *mean_depth)
 {
@@ -854,6 +870,26 @@ static void help_count(void)
     puts("-g [list]\tCUDA device index, or a comma-separated list to shard the reads over several GPUs (default 0)");
 }
 
+typedef struct {
+    char path[65536];
+    uint64_t n;
+    uint16_t *data;      /* n entries, zero where the file is short; NULL if the allocation failed */
+    int opened;
+} qgc_prefetch;
+
+static void *qgc_reader(void *arg)
+{
+    qgc_prefetch *j = arg;
+    j->data = calloc(j->n ? j->n : 1, sizeof(uint16_t));
+    FILE *f = j->data ? fopen(j->path, "rb") : NULL;
+    if (f) {
+        size_t got = fread(j->data, sizeof(uint16_t), j->n, f);
+        (void)got;
+        fclose(f);
+    }
+    return NULL;
+}
+
 static double now_sec(void)
 {
     struct timespec ts;
@@ -933,6 +969,18 @@ int qk_count_main(int argc, char **argv)
     rc = qk_multi_replicate(m);                          /* ncclBroadcast of the table to the other GPUs */
     if (rc) { printf("Dictionary broadcast failed: %s\n", qk_multi_last_error(m)); qk_multi_destroy(m); return 1; }
     printf("Read 0x%lX hash\n", (unsigned long)hdr.hash_size);            /* Q.c:359 */
+    /* Q.c:484-488: the reference opens ref.qgc after counting; here a thread reads it meanwhile */
+    qgc_prefetch qgc_job = {0};
+    pthread_t qgc_thread;
+    snprintf(qgc_job.path, sizeof qgc_job.path, "%s.qgc", ref_prefix);
+    qgc_job.n = n_kmers;
+    {
+        FILE *probe = fopen(qgc_job.path, "rb");
+        if (probe) {
+            fclose(probe);
+            qgc_job.opened = pthread_create(&qgc_thread, NULL, qgc_reader, &qgc_job) == 0;
+        }
+    }
     double t1 = now_sec();
     time_t start_time, end_time;
     time(&start_time);                                                     /* Q.c:387 */
@@ -954,34 +1002,37 @@ int qk_count_main(int argc, char **argv)
         hits += h;
     }
     if (!rc) rc = qk_multi_reduce(m);                    /* ncclReduce of the counters into GPU 0 */
-    if (rc) { printf("Counting failed: %s / %s\n", qk_last_error(ctx), qk_multi_last_error(m)); qk_multi_destroy(m); return 1; }
+    if (rc) {
+        printf("Counting failed: %s / %s\n", qk_last_error(ctx), qk_multi_last_error(m));
+        if (qgc_job.opened) { pthread_join(qgc_thread, NULL); free(qgc_job.data); }
+        qk_multi_destroy(m);
+        return 1;
+    }
     time(&end_time);
     double t2 = now_sec();
     printf("Counting elapse %u sec, total %lu kmers\n", (unsigned)(end_time - start_time), (unsigned long)total); /* Q.c:481 */
     printf("Pileup finish\nRead chain file %lu entries\n", (unsigned long)hdr.hash_size);                         /* Q.c:483 */
 
-    uint16_t *counts = malloc((n_kmers ? n_kmers : 1) * sizeof(uint16_t));
-    if (!counts) { puts("Memory allocation failed"); qk_multi_destroy(m); return 1; }
-    rc = qk_finish(ctx, counts, n_kmers);
-    if (rc) { printf("Result download failed: %s\n", qk_last_error(ctx)); free(counts); qk_multi_destroy(m); return 1; }
-    snprintf(path, sizeof path, "%s.bin", out_prefix);
-    if (qk_write_bin(path, counts, n_kmers)) { printf("Cannot write %s\n", path); free(counts); qk_multi_destroy(m); return 1; }
-    free(counts);
+    snprintf(path, sizeof path, "%s.bin", out_prefix);                     /* Q.c:498-518, written as the pieces arrive */
+    rc = qk_write_bin_from_device(ctx, path);
+    if (rc) {
+        printf("Cannot write %s: %s\n", path, rc == QK_ERR_IO ? "I/O error" : qk_last_error(ctx));
+        if (qgc_job.opened) { pthread_join(qgc_thread, NULL); free(qgc_job.data); }
+        qk_multi_destroy(m);
+        return 1;
+    }
 
     snprintf(path, sizeof path, "%s.qgc", ref_prefix);                     /* Q.c:484-488 */
-    FILE *gc = fopen(path, "rb");
-    if (!gc) printf("GC control file %s absent. Continue without GC correction!\n", path);
+    if (!qgc_job.opened) printf("GC control file %s absent. Continue without GC correction!\n", path);
     else {
-        uint16_t *qgc = calloc(n_kmers ? n_kmers : 1, sizeof(uint16_t));
-        if (!qgc) { puts("Memory allocation failed"); fclose(gc); qk_multi_destroy(m); return 1; }
-        size_t got = fread(qgc, sizeof(uint16_t), n_kmers, gc);
-        (void)got;
-        fclose(gc);
+        pthread_join(qgc_thread, NULL);                 /* the .qgc was read while the reads were counted */
+        uint16_t *qgc = qgc_job.data;
+        if (!qgc) { puts("Memory allocation failed"); qk_multi_destroy(m); return 1; }
         uint64_t sum[QK_GC_BINS], cnt[QK_GC_BINS];
         int64_t sq[QK_GC_BINS];
         rc = qk_gc_curve(ctx, qgc, n_kmers, sum, sq, cnt);
         free(qgc);
-        if (rc) { printf("GC curve failed: %s\n", qk_last_error(ctx)); qk_multi_destroy(m); return 1; }
+        if (rc) { printf("GC curve failed: %s\n", qk_last_error(ctx)); qk_multi_destroy(m); return 1; } /* qgc freed above */
         double mean = 0;
         snprintf(path, sizeof path, "%s.txt", out_prefix);                 /* Q.c:523-525 */
         if (qk_write_gc_txt(path, sum, sq, cnt, &mean)) { printf("Cannot write %s\n", path); qk_multi_destroy(m); return 1; }

@@ -525,6 +525,16 @@ def test_two_counter_buffers_and_async_reset(qk, oracle, gpu_ctx):
     assert gpu_ctx.slot_stream(0) != 0
 
 
+def test_bin_streamed_from_device(qk, gpu_ctx, tmp_path):
+    d = GOLDEN / "k30_fastq_t3"
+    gpu_ctx.load_dictionary(d / "ref.fa.qm")
+    gpu_ctx.count_file(d / "reads.fq")
+    gpu_ctx.write_bin(tmp_path / "s.bin")
+    assert (tmp_path / "s.bin").read_bytes() == (d / "expect.bin").read_bytes()
+    with pytest.raises(qk.QkError):
+        gpu_ctx.write_bin("/nonexistent/dir/s.bin")
+
+
 def test_depth_wraps_like_uint16(qk, oracle, gpu_ctx, tmp_path):
     """T12: one 30-mer seen 70,000 times reads 70,000 mod 65,536 = 4,464 (no saturation)."""
     kmer = "ACGTTGCATGCCGATAGGCTAACGTTAGCC"
