@@ -388,6 +388,9 @@ __device__ __forceinline__ uint32_t qk_probe_resolve(const qk_table_view &tv, co
 // per-warp queue and issued 64 at a time with every lane busy, and the depth increments are made
 // position-parallel from a per-warp ordinal array, so that a warp's REDs fall on consecutive
 // counters (one or two 128-byte lines per instruction).
+#ifndef QK_POOL_UNROLL
+#define QK_POOL_UNROLL 2 // pooled probes per lane per round
+#endif
 #define QK_SUB 512
 #define QK_SUB_WORDS (QK_SUB / 32)
 #define QK_WARPS (QK_THREADS / 32)
@@ -566,13 +569,13 @@ __global__ void __launch_bounds__(QK_THREADS, MINB) qk_count_ext_kernel(const qk
             }
         }
         __syncwarp();
-        for (uint32_t q0 = 0; q0 < total; q0 += 64) {
-            qk_probe pr[2];
-            qk_bucket bk[2];
-            uint32_t idx[2];
-            bool on[2];
+        for (uint32_t q0 = 0; q0 < total; q0 += 32 * QK_POOL_UNROLL) {
+            qk_probe pr[QK_POOL_UNROLL];
+            qk_bucket bk[QK_POOL_UNROLL];
+            uint32_t idx[QK_POOL_UNROLL];
+            bool on[QK_POOL_UNROLL];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < QK_POOL_UNROLL; ++u) {
                 const uint32_t e = q0 + 32 * u + lane;
                 on[u] = e < total;
                 idx[u] = on[u] ? sm.queue[e] : 0;
@@ -581,10 +584,10 @@ __global__ void __launch_bounds__(QK_THREADS, MINB) qk_count_ext_kernel(const qk
                 bk[u].e[0] = bk[u].e[1] = bk[u].e[2] = bk[u].e[3] = 0;
             }
 #pragma unroll
-            for (int u = 0; u < 2; ++u)
+            for (int u = 0; u < QK_POOL_UNROLL; ++u)
                 if (on[u]) bk[u] = L64 ? qk_ld_bucket64(pr[u].bp) : qk_ld_bucket(pr[u].bp);
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < QK_POOL_UNROLL; ++u) {
                 if (!on[u]) continue;
                 uint32_t st;
                 sm.ord[idx[u]] = qk_probe_resolve(tv, pr[u], bk[u], ord_mask, &st);
