@@ -668,20 +668,12 @@ int qk_launch_count(qk_ctx *ctx, qk_slot *sl, const uint8_t *dev_bytes, size_t n
     QK_CUDA(ctx, cudaEventRecord(tp->a, sl->stream));
     static int classic = -1; // QK_CLASSIC_KERNEL=1: probe every position even when the extension arrays exist
     if (classic < 0) classic = getenv("QK_CLASSIC_KERNEL") != NULL;
-    static int variant = -1; // QK_EXT_VARIANT = 10 * min CTAs per SM (4..6) + L2::64B hint (0/1); tuning knob
-    if (variant < 0) {
-        const char *e = getenv("QK_EXT_VARIANT");
-        variant = e ? atoi(e) : 41;
-    }
+    static int plain_loads = -1; // QK_EXT_PLAIN_LOADS=1: bucket loads without the .L2::64B hint (A/B knob, -2 %)
+    if (plain_loads < 0) plain_loads = getenv("QK_EXT_PLAIN_LOADS") != NULL;
     if (a.tv.ext_last && !classic) {
-        switch (variant) {
-        case 40: qk_count_ext_kernel<4, false><<<grid, QK_THREADS, 0, sl->stream>>>(a); break;
-        case 50: qk_count_ext_kernel<5, false><<<grid, QK_THREADS, 0, sl->stream>>>(a); break;
-        case 51: qk_count_ext_kernel<5, true><<<grid, QK_THREADS, 0, sl->stream>>>(a); break;
-        case 60: qk_count_ext_kernel<6, false><<<grid, QK_THREADS, 0, sl->stream>>>(a); break;
-        case 61: qk_count_ext_kernel<6, true><<<grid, QK_THREADS, 0, sl->stream>>>(a); break;
-        default: qk_count_ext_kernel<4, true><<<grid, QK_THREADS, 0, sl->stream>>>(a); break;
-        }
+        // 4 CTAs/SM at 64 registers: 5 and 6 CTAs/SM spill and measured 2-5 % slower (profiles/README.md)
+        if (plain_loads) qk_count_ext_kernel<4, false><<<grid, QK_THREADS, 0, sl->stream>>>(a);
+        else qk_count_ext_kernel<4, true><<<grid, QK_THREADS, 0, sl->stream>>>(a);
     } else qk_count_kernel<<<grid, QK_THREADS, 0, sl->stream>>>(a);
     QK_CUDA(ctx, cudaGetLastError());
     QK_CUDA(ctx, cudaEventRecord(tp->b, sl->stream));
