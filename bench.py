@@ -636,7 +636,8 @@ def gpu_arm(args):
                          if n_framed + int(desc.table_bytes) > (256 << 20) else "working set fits L2: HBM term does not bind"},
         "bases_per_s": bases_step * world / (ms_per_step * 1e-3),
         "e2e": {"value": job_kmers / raw_s, "unit": "k-mers/s", "h2d_bytes_per_step": int(raw_np.size), "d2h_bytes_per_step": 2 * n_kmers + 64,
-                "h2d_gbs": raw_np.size / raw_s / 1e9,
+                "h2d_gbs": raw_np.size / raw_s / 1e9, "frac_of_h2d_peak": (raw_np.size / raw_s / 1e9) / h2d if h2d == h2d else None,
+                "bases_per_s": bases_step * world / raw_s,
                 "path": "raw FASTA/FASTQ bytes in pinned host memory -> qk_count_raw_mem (cut at line ends, H2D, device framing, count kernels) -> qk_finish (uint16 depths D2H)",
                 "steps": e2e_steps, "raw_bytes_per_step": int(raw_np.size)},
         "e2e_preframed": {"value": job_kmers / pre_s, "unit": "k-mers/s", "h2d_gbs": n_framed / pre_s / 1e9,
