@@ -95,6 +95,8 @@ typedef struct qk_table_desc {
 } qk_table_desc;
 
 int qk_dict_describe(const qk_ctx *ctx, qk_table_desc *desc);
+/* The geometry qk_dict_build will choose for n_kmers chain entries (no device needed). */
+int qk_table_geometry(uint64_t n_kmers, uint32_t k, qk_table_desc *desc);
 /* Allocate an (uninitialised) replica with the geometry of `desc` on this context; the
  * host then fills it, e.g. with an NCCL broadcast into the pointers below. */
 int qk_dict_adopt(qk_ctx *ctx, const qk_table_desc *desc);

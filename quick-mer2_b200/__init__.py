@@ -100,6 +100,7 @@ SIGNATURES = {
     "qk_dict_upload_chain": (C.c_int, [_P, C.c_uint64, _P, C.c_uint64]),
     "qk_dict_upload_from_slot": (C.c_int, [_P, C.c_uint32, C.c_int, C.c_uint64, C.c_uint64]),
     "qk_dict_build": (C.c_int, [_P, _U64P]),
+    "qk_table_geometry": (C.c_int, [C.c_uint64, C.c_uint32, C.POINTER(TableDesc)]),
     "qk_dict_describe": (C.c_int, [_P, C.POINTER(TableDesc)]),
     "qk_dict_adopt": (C.c_int, [_P, C.POINTER(TableDesc)]),
     "qk_dict_device_ptrs": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),

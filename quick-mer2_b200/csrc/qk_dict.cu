@@ -373,6 +373,15 @@ static void qk_geometry(uint64_t n, uint32_t k, uint64_t stash_slots_min, qk_tab
     d->cont_bytes = d->has_ext ? ((n + 31) / 32 + 4) * sizeof(uint32_t) : 0;  // 1 bit per ordinal, padded
 }
 
+// Geometry a dictionary of n k-mers will get, without a device: lets a host size the job
+// (table_bytes + stash_bytes + 2 x ext_bytes + cont_bytes + 4 (n + 1) bytes of counters).
+extern "C" int qk_table_geometry(uint64_t n_kmers, uint32_t k, qk_table_desc *desc)
+{
+    if (!desc || n_kmers == 0 || n_kmers >= ((uint64_t)1 << 32) || k < 1 || k > 32) return QK_ERR_ARG;
+    qk_geometry(n_kmers, k, 0, desc);
+    return QK_OK;
+}
+
 static int qk_alloc_table(qk_ctx *ctx, const qk_table_desc *d)
 {
     cudaFree(ctx->buckets);

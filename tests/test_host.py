@@ -204,3 +204,43 @@ def test_cli_usage_and_missing_inputs(qk, tmp_path):
     assert res.returncode == 1 and "open fail" in res.stdout       # the reference segfaults here (Q.c:345)
     res = qk.run_cli(["est"])
     assert res.returncode == 1
+
+
+# ---------------------------------------------------------------------------- geometry ---
+@pytest.mark.parametrize("n", [1, 5, 1000, 5873, 999971, 58217593, 499708597, 1487556863, 2200000000, (1 << 32) - 1])
+@pytest.mark.parametrize("k", [3, 30, 31])
+def test_table_geometry_invariants(n, k, qk):
+    """What the probe relies on: power-of-two buckets, <= 2.1 keys per 4-entry bucket, an entry
+    (remainder + ordinal) that leaves bit 63 free, ordinals in 32 bits, padded extension arrays."""
+    d = qk.TableDesc()
+    assert qk.lib().qk_table_geometry(n, k, C.byref(d)) == 0
+    assert d.n_kmers == n and d.k == k
+    assert d.n_buckets & (d.n_buckets - 1) == 0 and d.n_buckets >= 64
+    assert n / d.n_buckets <= 2.1
+    assert d.rem_bits + d.bucket_bits == 60 and (1 << d.bucket_bits) == d.n_buckets
+    assert (1 << d.ord_bits) > n and d.ord_bits <= 32            # holds ordinal + 1
+    assert d.rem_bits + d.ord_bits <= 63
+    assert d.table_bytes == d.n_buckets * 32
+    assert d.stash_slots & (d.stash_slots - 1) == 0 and d.stash_bytes == d.stash_slots * 16
+    assert d.has_ext == (1 if k == 30 else 0)
+    if d.has_ext:
+        assert d.ext_bytes >= (n + 15) // 16 * 4 + 16 and d.cont_bytes >= (n + 31) // 32 * 4 + 16
+    else:
+        assert d.ext_bytes == 0 and d.cont_bytes == 0
+
+
+def test_table_geometry_rejects_nonsense(qk):
+    d = qk.TableDesc()
+    for n, k in ((0, 30), (1 << 32, 30), (10, 0), (10, 33)):
+        assert qk.lib().qk_table_geometry(n, k, C.byref(d)) == 2
+
+
+def test_human_scale_fits_one_gpu(qk):
+    """2.2 G k-mers (2^32-slot .qm).  Peak device memory = build transients + table."""
+    d = qk.TableDesc()
+    n = 2_200_000_000
+    qk.lib().qk_table_geometry(n, 30, C.byref(d))
+    resident = d.table_bytes + d.stash_bytes + 2 * d.ext_bytes + d.cont_bytes + 4 * (n + 1)
+    raw = (1 << 32) * 12                      # keys + chain while the chain is ranked
+    kbo = 8 * (n + 1)                         # keys by ordinal while the table is filled
+    assert max(raw + kbo, kbo + resident) < 170e9
