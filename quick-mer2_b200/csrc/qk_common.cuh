@@ -73,8 +73,6 @@ struct qk_ctx {
     qk_bucket *buckets;
     qk_stash_entry *stash;
     uint32_t *ext_last, *ext_first, *ext_cont; // dictionary-order extension arrays (k = 30), else NULL
-    void *big_base[8];        // what cudaMalloc returned for the (optionally aligned) big arrays; see qk_big_alloc
-    int n_big;
     qk_table_desc desc;
 
     uint32_t *counters;       // n_kmers x u32, indexed by ordinal: the buffer jobs currently count into
@@ -95,7 +93,6 @@ struct qk_ctx {
 };
 
 int qk_fail(qk_ctx *ctx, int code, const char *fmt, ...);
-void qk_big_free_all(qk_ctx *ctx); // table, stash, extension arrays, counter buffer 0 (qk_dict.cu)
 int qk_cuda_fail(qk_ctx *ctx, cudaError_t e, const char *what);
 #define QK_CUDA(ctx, call)                                            \
     do {                                                              \

@@ -110,7 +110,12 @@ extern "C" void qk_ctx_destroy(qk_ctx *ctx)
     if (ctx->span_join) cudaEventDestroy(ctx->span_join);
     cudaFree(ctx->raw_keys);
     cudaFree(ctx->raw_next);
-    qk_big_free_all(ctx);
+    cudaFree(ctx->buckets);
+    cudaFree(ctx->stash);
+    cudaFree(ctx->ext_last);
+    cudaFree(ctx->ext_first);
+    cudaFree(ctx->ext_cont);
+    cudaFree(ctx->counters_buf[0]);
     cudaFree(ctx->counters_buf[1]);
     cudaFree(ctx->stats);
     cudaFree(ctx->frame_stream);

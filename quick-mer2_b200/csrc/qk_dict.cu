@@ -60,11 +60,12 @@ extern "C" int qk_dict_begin(qk_ctx *ctx, uint8_t k, uint64_t hash_size, uint64_
     QK_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaFree(ctx->raw_keys);
     cudaFree(ctx->raw_next);
-    qk_big_free_all(ctx);
+    cudaFree(ctx->buckets);
+    cudaFree(ctx->stash);
+    cudaFree(ctx->counters_buf[0]);
     cudaFree(ctx->counters_buf[1]);
     ctx->raw_keys = NULL; ctx->raw_next = NULL; ctx->buckets = NULL; ctx->stash = NULL; ctx->counters = NULL;
     ctx->counters_buf[0] = ctx->counters_buf[1] = NULL;
-    ctx->ext_last = ctx->ext_first = ctx->ext_cont = NULL;
     ctx->dict_state = 0;
     QK_CUDA(ctx, cudaMalloc((void **)&ctx->raw_keys, hash_size * sizeof(uint64_t)));
     QK_CUDA(ctx, cudaMalloc((void **)&ctx->raw_next, hash_size * sizeof(uint32_t)));
@@ -381,48 +382,29 @@ extern "C" int qk_table_geometry(uint64_t n_kmers, uint32_t k, qk_table_desc *de
     return QK_OK;
 }
 
-// Big device arrays, optionally placed on a QK_ALIGN_MB MiB boundary (experiment knob: the speed
-// of the count kernels depends on what was allocated before them, see profiles/README.md).
-static cudaError_t qk_big_alloc(qk_ctx *ctx, void **out, size_t bytes)
-{
-    static long align_mb = -1;
-    if (align_mb < 0) {
-        const char *e = getenv("QK_ALIGN_MB");
-        align_mb = e ? atol(e) : 0;
-    }
-    const size_t align = (size_t)align_mb << 20;
-    void *base = NULL;
-    cudaError_t err = cudaMalloc(&base, bytes + align);
-    if (err != cudaSuccess) return err;
-    if (ctx->n_big < 8) ctx->big_base[ctx->n_big++] = base;
-    *out = align ? (void *)(((uintptr_t)base + align - 1) / align * align) : base;
-    return cudaSuccess;
-}
-
-void qk_big_free_all(qk_ctx *ctx)
-{
-    for (int i = 0; i < ctx->n_big; ++i) cudaFree(ctx->big_base[i]);
-    ctx->n_big = 0;
-}
-
 static int qk_alloc_table(qk_ctx *ctx, const qk_table_desc *d)
 {
-    qk_big_free_all(ctx);
+    cudaFree(ctx->buckets);
+    cudaFree(ctx->stash);
+    cudaFree(ctx->counters_buf[0]);
     cudaFree(ctx->counters_buf[1]);
     ctx->counters_buf[0] = ctx->counters_buf[1] = NULL;
+    cudaFree(ctx->ext_last);
+    cudaFree(ctx->ext_first);
+    cudaFree(ctx->ext_cont);
     ctx->buckets = NULL; ctx->stash = NULL; ctx->counters = NULL;
     ctx->ext_last = ctx->ext_first = ctx->ext_cont = NULL;
-    QK_CUDA(ctx, qk_big_alloc(ctx, (void **)&ctx->buckets, d->table_bytes));
-    QK_CUDA(ctx, qk_big_alloc(ctx, (void **)&ctx->stash, d->stash_bytes));
+    QK_CUDA(ctx, cudaMalloc((void **)&ctx->buckets, d->table_bytes));
+    QK_CUDA(ctx, cudaMalloc((void **)&ctx->stash, d->stash_bytes));
     if (d->has_ext) {
-        QK_CUDA(ctx, qk_big_alloc(ctx, (void **)&ctx->ext_last, d->ext_bytes));
-        QK_CUDA(ctx, qk_big_alloc(ctx, (void **)&ctx->ext_first, d->ext_bytes));
-        QK_CUDA(ctx, qk_big_alloc(ctx, (void **)&ctx->ext_cont, d->cont_bytes));
+        QK_CUDA(ctx, cudaMalloc((void **)&ctx->ext_last, d->ext_bytes));
+        QK_CUDA(ctx, cudaMalloc((void **)&ctx->ext_first, d->ext_bytes));
+        QK_CUDA(ctx, cudaMalloc((void **)&ctx->ext_cont, d->cont_bytes));
         QK_CUDA(ctx, cudaMemset(ctx->ext_last, 0, d->ext_bytes));
         QK_CUDA(ctx, cudaMemset(ctx->ext_first, 0, d->ext_bytes));
         QK_CUDA(ctx, cudaMemset(ctx->ext_cont, 0, d->cont_bytes));
     }
-    QK_CUDA(ctx, qk_big_alloc(ctx, (void **)&ctx->counters_buf[0], (d->n_kmers + 1) * sizeof(uint32_t)));
+    QK_CUDA(ctx, cudaMalloc((void **)&ctx->counters_buf[0], (d->n_kmers + 1) * sizeof(uint32_t)));
     ctx->counters = ctx->counters_buf[0];
     QK_CUDA(ctx, cudaMemset(ctx->counters, 0, (d->n_kmers + 1) * sizeof(uint32_t)));
     QK_CUDA(ctx, cudaMemset(ctx->stats, 0, 4 * sizeof(unsigned long long))); // a new dictionary starts a new count
