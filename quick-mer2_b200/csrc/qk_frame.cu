@@ -16,7 +16,8 @@
 // The first line of the stream: '@' selects FASTQ and is consumed (start in s = 3); a FASTA
 // pipe loses its first line the same way (fseek fails, Q.c:396); seekable FASTA starts in 0.
 // Each line is therefore a function {0..3} -> {0..3} x {keep, drop}; composition of such
-// functions is associative, so the state before every line comes out of a parallel scan:
+// functions is associative, so the state before every line comes out of a parallel scan
+// (a thread composes the lines that start in its 64 bytes, then one CTA-wide scan per 16 KiB):
 //   pass 1  qk_frame_reduce : every CTA composes the lines that START in its span
 //   pass 2  qk_frame_carry  : one thread chains the CTA totals from the stream state
 //   pass 3  qk_frame_apply  : every CTA replays its span from its true incoming state and
@@ -29,7 +30,8 @@ int qk_ring_push(qk_ctx *ctx, qk_slot *sl, int kind, qk_timing_pair **out);
 int qk_launch_count(qk_ctx *ctx, qk_slot *sl, const uint8_t *dev_bytes, size_t n_bytes);
 
 #define QK_FRAME_THREADS 256
-#define QK_FRAME_TILE (QK_FRAME_THREADS * 16)
+#define QK_FRAME_PIECES 4                                     // 16-byte pieces per thread per tile
+#define QK_FRAME_TILE (QK_FRAME_THREADS * 16 * QK_FRAME_PIECES) // 16 KiB: one CTA-wide scan per tile
 
 // Transition function packed in 13 bits: map[s] in bits 2s+1:2s, keep[s] in bit 8+s (keep flag
 // of the LAST line that starts in the segment, entered in state s), bit 12 = segment has a line.
@@ -184,44 +186,57 @@ __global__ void __launch_bounds__(QK_FRAME_THREADS) qk_frame_kernel(const qk_fra
     uint32_t n_reads = 0, n_bases = 0, n_lines = 0;
 
     for (uint32_t tile = tile0; tile < tile_end; ++tile) {
-        const uint32_t pos = tile * QK_FRAME_TILE + tid * 16;
-        // previous byte: last byte of the previous thread's piece
-        uint4 v = qk_frame_load16(a.bytes, pos, a.n_bytes);
-        s_last[tid] = (uint8_t)(v.w >> 24);
+        const uint32_t pos0 = tile * QK_FRAME_TILE + tid * (16 * QK_FRAME_PIECES);
+        uint4 v[QK_FRAME_PIECES];
+#pragma unroll
+        for (int i = 0; i < QK_FRAME_PIECES; ++i) v[i] = qk_frame_load16(a.bytes, pos0 + 16 * i, a.n_bytes);
+        // the byte before my first piece is the last byte of the previous thread's last piece
+        s_last[tid] = (uint8_t)(v[QK_FRAME_PIECES - 1].w >> 24);
         __syncthreads();
-        const uint32_t prev_nl = tid ? (s_last[tid - 1] == '\n') : carry_nl;
+        uint32_t prev_nl = tid ? (s_last[tid - 1] == '\n') : carry_nl;
         const uint32_t tile_last_nl = s_last[QK_FRAME_THREADS - 1] == '\n';
-        qk_frame_piece p = qk_frame_piece_of(a, v, pos, prev_nl);
+        qk_frame_piece p[QK_FRAME_PIECES];
+        uint32_t elem = QK_FE_IDENTITY;
+#pragma unroll
+        for (int i = 0; i < QK_FRAME_PIECES; ++i) {
+            p[i] = qk_frame_piece_of(a, v[i], pos0 + 16 * i, prev_nl);
+            prev_nl = (p[i].nl >> 15) & 1u;
+            if (p[i].starts) elem = qk_fe_compose(elem, p[i].elem);
+        }
         uint32_t total;
-        const uint32_t before = qk_frame_block_scan(p.elem, s_warp, &total); // syncs: s_last is free again
+        const uint32_t before = qk_frame_block_scan(elem, s_warp, &total); // syncs: s_last is free again
         if (!APPLY) {
             run = qk_fe_compose(run, total);
         } else {
             uint32_t cur = qk_fe_apply(before, sk);   // state | keep << 2 entering this thread's bytes
-            // keep mask of the 16 bytes: segments between line starts
-            uint32_t keepmask = 0, m = p.starts, from = 0;
-            while (m) {
-                const uint32_t j = __ffs(m) - 1;
-                m &= m - 1;
-                if ((cur >> 2) & 1u) keepmask |= ((1u << j) - 1) & ~((1u << from) - 1);
-                const uint32_t e = qk_fe_line(qk_byte_of(p.v, j), a.fastq);
-                cur = qk_fe_apply(e, cur);
-                n_reads += (cur >> 2) & 1u;
-                ++n_lines;
-                from = j;
-            }
-            if ((cur >> 2) & 1u) keepmask |= 0xFFFFu & ~((1u << from) - 1);
-            if (pos < a.n_bytes) {
-                uint32_t valid = a.n_bytes - pos >= 16 ? 0xFFFFu : (1u << (a.n_bytes - pos)) - 1;
-                n_bases += __popc(keepmask & ~p.nl & valid);
-                uint32_t w[4] = {p.v.x, p.v.y, p.v.z, p.v.w};
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const uint32_t bits = (keepmask >> (4 * i)) & 0xFu;
-                    const uint32_t sel = (((bits * 0x00204081u) & 0x01010101u) * 0xFFu);
-                    w[i] = (w[i] & sel) | (0x0A0A0A0Au & ~sel);
+            for (int i = 0; i < QK_FRAME_PIECES; ++i) {
+                const uint32_t pos = pos0 + 16 * i;
+                // keep mask of the 16 bytes: segments between line starts
+                uint32_t keepmask = 0, m = p[i].starts, from = 0;
+                while (m) {
+                    const uint32_t j = __ffs(m) - 1;
+                    m &= m - 1;
+                    if ((cur >> 2) & 1u) keepmask |= ((1u << j) - 1) & ~((1u << from) - 1);
+                    const uint32_t e = qk_fe_line(qk_byte_of(p[i].v, j), a.fastq);
+                    cur = qk_fe_apply(e, cur);
+                    n_reads += (cur >> 2) & 1u;
+                    ++n_lines;
+                    from = j;
                 }
-                if (keepmask != 0xFFFFu) *reinterpret_cast<uint4 *>(a.bytes + pos) = make_uint4(w[0], w[1], w[2], w[3]);
+                if ((cur >> 2) & 1u) keepmask |= 0xFFFFu & ~((1u << from) - 1);
+                if (pos < a.n_bytes) {
+                    uint32_t valid = a.n_bytes - pos >= 16 ? 0xFFFFu : (1u << (a.n_bytes - pos)) - 1;
+                    n_bases += __popc(keepmask & ~p[i].nl & valid);
+                    uint32_t w[4] = {p[i].v.x, p[i].v.y, p[i].v.z, p[i].v.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t bits = (keepmask >> (4 * q)) & 0xFu;
+                        const uint32_t sel = (((bits * 0x00204081u) & 0x01010101u) * 0xFFu);
+                        w[q] = (w[q] & sel) | (0x0A0A0A0Au & ~sel);
+                    }
+                    if (keepmask != 0xFFFFu) *reinterpret_cast<uint4 *>(a.bytes + pos) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
             }
             sk = qk_fe_apply(total, sk);
         }
@@ -243,17 +258,25 @@ __global__ void __launch_bounds__(QK_FRAME_THREADS) qk_frame_kernel(const qk_fra
     }
 }
 
-// pass 2: chain the CTA totals from the stream state; leave each CTA's incoming state behind
-__global__ void qk_frame_carry(uint32_t *cta_elem, uint32_t n_ctas, unsigned long long *stream)
+// pass 2: chain the CTA totals from the stream state; leave each CTA's incoming state behind.
+// One CTA: everybody stages the <= QK_FRAME_MAX_CTAS words in shared memory, one thread chains
+// them there (a dependent global load per word cost 54 ns each), everybody writes back.
+__global__ void __launch_bounds__(256) qk_frame_carry(uint32_t *cta_elem, uint32_t n_ctas, unsigned long long *stream)
 {
-    if (threadIdx.x || blockIdx.x) return;
-    uint32_t sk = (uint32_t)stream[0] & 3u;
-    for (uint32_t b = 0; b < n_ctas; ++b) {
-        const uint32_t e = cta_elem[b];
-        cta_elem[b] = sk | (e & (1u << 13));
-        sk = qk_fe_apply(e & 0x1FFFu, sk);
+    __shared__ uint32_t s_e[QK_FRAME_MAX_CTAS];
+    for (uint32_t b = threadIdx.x; b < n_ctas; b += blockDim.x) s_e[b] = cta_elem[b];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t sk = (uint32_t)stream[0] & 3u;
+        for (uint32_t b = 0; b < n_ctas; ++b) {
+            const uint32_t e = s_e[b];
+            s_e[b] = sk | (e & (1u << 13));
+            sk = qk_fe_apply(e & 0x1FFFu, sk);
+        }
+        stream[0] = sk & 3u;
     }
-    stream[0] = sk & 3u;
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < n_ctas; b += blockDim.x) cta_elem[b] = s_e[b];
 }
 
 extern "C" int qk_raw_begin(qk_ctx *ctx, int fastq, int skip_first_line)
@@ -320,7 +343,7 @@ extern "C" int qk_submit_raw(qk_ctx *ctx, uint32_t slot, const uint8_t *bytes, s
     if (ctx->raw_prev_slot >= 0 && (uint32_t)ctx->raw_prev_slot != slot)
         QK_CUDA(ctx, cudaStreamWaitEvent(sl->stream, ctx->slots[ctx->raw_prev_slot].frame_done, 0));
     qk_frame_kernel<false><<<n_ctas, QK_FRAME_THREADS, 0, sl->stream>>>(a);
-    qk_frame_carry<<<1, 32, 0, sl->stream>>>(a.cta_elem, n_ctas, a.stream);
+    qk_frame_carry<<<1, 256, 0, sl->stream>>>(a.cta_elem, n_ctas, a.stream);
     QK_CUDA(ctx, cudaEventRecord(sl->frame_done, sl->stream));
     qk_frame_kernel<true><<<n_ctas, QK_FRAME_THREADS, 0, sl->stream>>>(a);
     QK_CUDA(ctx, cudaGetLastError());
