@@ -78,6 +78,16 @@ def test_cli_reads_from_a_pipe(qk, oracle, tmp_path):
     assert res.returncode == 0, res.stdout
     # first line is a '>' header, so losing it changes nothing
     assert (tmp_path / "p.bin").read_bytes() == (d / "expect.bin").read_bytes()
+    # headerless stream: the first line IS a read and is lost, exactly as the reference loses it
+    # (pinned against the reference binary in tests/test_oracle.py)
+    seq = [l for l in (d / "reads.fa").read_text().split("\n") if l and not l.startswith(">")]
+    data = ("\n".join(seq[:200]) + "\n").encode()
+    res = subprocess.run([str(qk.CLI_PATH), "count", str(d / "ref.fa"), "/dev/stdin", str(tmp_path / "q")],
+                         input=data, capture_output=True)
+    assert res.returncode == 0, res.stdout
+    (tmp_path / "tail.fa").write_bytes(data[data.index(b"\n") + 1:])
+    want, _ = oracle.count_bin(d / "ref.fa.qm", tmp_path / "tail.fa")
+    assert np.array_equal(np.fromfile(tmp_path / "q.bin", dtype=np.uint16), want)
 
 
 # ------------------------------------------------------------------ chunking / tiling ------

@@ -116,3 +116,26 @@ def test_oracle_against_live_reference(oracle, ref_binary, synth, tmp_path):
         assert (tmp_path / "port.txt").read_bytes() == (tmp_path / "live.txt").read_bytes()
         assert f"total {st['total_kmers']} kmers" in res.stdout
         assert st["hits"] > 0.5 * st["total_kmers"]
+
+
+def test_reference_on_a_pipe_loses_the_first_line(oracle, ref_binary, tmp_path):
+    """Q.c:396: on FASTA input the reference rewinds with fseek(0), which fails on a pipe, so the
+    first line is consumed (README.md:89-90 is the documented pipe use).  Pin that against the
+    reference itself: piping X must give what the file 'X minus its first line' gives."""
+    if ref_binary is None:
+        pytest.skip("oracle/_ref/quicKmer2 not built here")
+    d = GOLDEN / "k30_fasta_t0"
+    seq = [l for l in (d / "reads.fa").read_text().split("\n") if l and not l.startswith(">")]
+    data = ("\n".join(seq[:200]) + "\n").encode()          # headerless: the first line is a read
+    for name in ("ref.fa.qm", "ref.fa.qgc"):
+        (tmp_path / name).write_bytes((d / name).read_bytes())
+    res = subprocess.run([str(ref_binary), "count", "ref.fa", "/dev/stdin", "piped"], cwd=tmp_path, input=data,
+                         capture_output=True)
+    assert res.returncode == 0, res.stdout
+    (tmp_path / "all.fa").write_bytes(data)
+    (tmp_path / "tail.fa").write_bytes(data[data.index(b"\n") + 1:])
+    oracle.count(tmp_path / "ref.fa", tmp_path / "tail.fa", tmp_path / "want_tail")
+    oracle.count(tmp_path / "ref.fa", tmp_path / "all.fa", tmp_path / "want_all")
+    piped = (tmp_path / "piped.bin").read_bytes()
+    assert piped == (tmp_path / "want_tail.bin").read_bytes()
+    assert piped != (tmp_path / "want_all.bin").read_bytes()   # the lost line did carry dictionary k-mers
