@@ -95,3 +95,30 @@ def gpu_ctx(qk):
     ctx = qk.Context(device=0, n_slots=3, chunk_capacity=8 << 20)
     yield ctx
     ctx.close()
+
+
+def weird_stream(rng, seq, fastq_like, n_lines):
+    """Lines in arbitrary order -- not a valid FASTA/FASTQ -- so that the reference's line state
+    machine (Q.c:397-398, 451-455) is driven through every phase: '>' where a read is expected,
+    quality lines that start with '>' or '@', empty lines, N runs, CR."""
+    out = []
+    for _ in range(n_lines):
+        kind = rng.integers(0, 10)
+        a = int(rng.integers(0, len(seq) - 400))
+        body = seq[a:a + int(rng.integers(0, 300))]
+        if kind == 0:
+            out.append(">" + body[:20])
+        elif kind == 1:
+            out.append("@" + body[:30])
+        elif kind == 2:
+            out.append("+")
+        elif kind == 3:
+            out.append("")
+        elif kind == 4:
+            out.append(">" * int(rng.integers(1, 4)) + "III@@>>")
+        elif kind == 5:
+            out.append(body[:50] + "N" * int(rng.integers(1, 5)) + body[50:] + "\r")
+        else:
+            out.append(body)
+    first = "@first" if fastq_like else rng.choice([">first", seq[5:160], ""])
+    return "\n".join([first] + out) + "\n"

@@ -12,7 +12,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, golden_cases, golden_meta
+from conftest import GOLDEN, golden_cases, golden_meta, weird_stream
 
 
 @pytest.mark.parametrize("case", golden_cases())
@@ -139,3 +139,29 @@ def test_reference_on_a_pipe_loses_the_first_line(oracle, ref_binary, tmp_path):
     piped = (tmp_path / "piped.bin").read_bytes()
     assert piped == (tmp_path / "want_tail.bin").read_bytes()
     assert piped != (tmp_path / "want_all.bin").read_bytes()   # the lost line did carry dictionary k-mers
+
+
+@pytest.mark.parametrize("fastq_like", [True, False])
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_line_state_machine_against_live_reference(seed, fastq_like, oracle, ref_binary, tmp_path):
+    """The GPU framing tests compare with the oracle on streams that are NOT valid FASTA/FASTQ
+    ('>' where a read is expected, quality lines starting with '>' or '@', empty lines ...).
+    Here the oracle's reading of those streams is pinned to the reference binary itself."""
+    if ref_binary is None:
+        pytest.skip("oracle/_ref/quicKmer2 not built here")
+    d = GOLDEN / "k30_fasta_t0"
+    seq = "".join(l.strip() for l in open(d / "ref.fa") if not l.startswith(">")).replace("N", "")
+    rng = np.random.default_rng(100 + seed)
+    text = weird_stream(rng, seq, fastq_like, 3000)
+    (tmp_path / "w.txt").write_text(text, newline="")
+    for name in ("ref.fa.qm", "ref.fa.qgc"):
+        (tmp_path / name).write_bytes((d / name).read_bytes())
+    for threads in ([], ["-t", "2"]):
+        res = subprocess.run([str(ref_binary), "count", *threads, "ref.fa", "w.txt", "live"], cwd=tmp_path,
+                             capture_output=True, text=True)
+        assert res.returncode == 0, res.stdout + res.stderr
+        st = oracle.count(tmp_path / "ref.fa", tmp_path / "w.txt", tmp_path / "port")
+        assert (tmp_path / "port.bin").read_bytes() == (tmp_path / "live.bin").read_bytes()
+        assert (tmp_path / "port.txt").read_bytes() == (tmp_path / "live.txt").read_bytes()
+        assert f"total {st['total_kmers']} kmers" in res.stdout
+    assert st["fastq"] == int(fastq_like) and st["lines"] > 300
