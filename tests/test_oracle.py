@@ -165,3 +165,25 @@ def test_line_state_machine_against_live_reference(seed, fastq_like, oracle, ref
         assert (tmp_path / "port.txt").read_bytes() == (tmp_path / "live.txt").read_bytes()
         assert f"total {st['total_kmers']} kmers" in res.stdout
     assert st["fastq"] == int(fastq_like) and st["lines"] > 300
+
+
+@pytest.mark.parametrize("k", [20, 30])
+def test_synthetic_dictionary_equals_search(k, oracle, ref_binary, synth, tmp_path):
+    """`qk_synth dict` (used where the reference binary cannot travel) must describe the same
+    dictionary as the reference's `search -e 0`: same unique k-mers in the same chain order, hence
+    the same .bin for any reads (slot placement may differ -- it is not observable)."""
+    if ref_binary is None:
+        pytest.skip("oracle/_ref/quicKmer2 not built here")
+    a, b = tmp_path / "a", tmp_path / "b"
+    a.mkdir(); b.mkdir()
+    synth("ref", "--out", a / "ref.fa", "--bases", 300000, "--contigs", 3, "--seed", 5 + k, "--segdups", 6, "--segdup-len", 4000,
+          "--nblock", 700)
+    (b / "ref.fa").write_bytes((a / "ref.fa").read_bytes())
+    res = subprocess.run([str(ref_binary), "search", "-k", str(k), "-e", "0", "-s", "1M", "ref.fa"], cwd=a, capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    synth("dict", "--ref", b / "ref.fa", "--k", k, "--slots", "1M")
+    synth("reads", "--ref", a / "ref.fa", "--out", tmp_path / "r.fa", "--n", 30000, "--len", 150, "--seed", 3)
+    bin_a, sa = oracle.count_bin(a / "ref.fa.qm", tmp_path / "r.fa")
+    bin_b, sb = oracle.count_bin(b / "ref.fa.qm", tmp_path / "r.fa")
+    assert bin_a.size == bin_b.size > 200000
+    assert np.array_equal(bin_a, bin_b) and sa["hits"] == sb["hits"] > 0
