@@ -1,0 +1,198 @@
+"""The dictionary-order walk of qk_count_ext_kernel, restated in Python for ANY k and checked
+against a plain key -> ordinal lookup on adversarial inputs (CPU only).
+
+The CUDA kernel only exists for k = 30, where coincidences are astronomically rare.  The
+exactness argument is about keys, not about k, so the same construction is
+run here with k = 3..9 on low-complexity, palindrome-rich and repeat-rich sequences, where
+"accidental" continuations, reverse-complement palindromes and k-mers that continue in both
+orientations occur all the time.  If the walk ever assigned an ordinal that the dictionary
+lookup does not, the identities the kernel relies on would be wrong.
+
+Mirrors quick-mer2_b200/csrc/qk_dict.cu (qk_orient_insert_kernel) and qk_count.cu
+(qk_count_ext_kernel): block-wise orientation with look-ahead at run starts, cont / last /
+first / strand per ordinal, one anchor per run of 16 positions, steps checked in order.
+"""
+import numpy as np
+import pytest
+
+RUN = 16
+BLOCK = 8          # ordinals per orientation block (256 on the device): small, to hit the block seams
+
+
+def rc(x, k):
+    """reverse complement in the reference's encoding (A=0 C=1 T=2 G=3, complement = ^2)"""
+    out = 0
+    for _ in range(k):
+        out = (out << 2) | ((x & 3) ^ 2)
+        x >>= 2
+    return out
+
+
+def canonical_stream(codes, k):
+    """(key, is_fwd) for every position that ends a k-mer (Q.c:399-420 with a k-base rc register)."""
+    M = (1 << (2 * k)) - 1
+    fwd = rcv = 0
+    out = []
+    for i, c in enumerate(codes):
+        fwd = ((fwd << 2) | c) & M
+        rcv = (rcv >> 2) | ((c ^ 2) << (2 * (k - 1)))
+        if i >= k - 1:
+            out.append((min(fwd, rcv), fwd <= rcv, fwd))
+        else:
+            out.append(None)
+    return out
+
+
+def build_dictionary(ref_codes, k):
+    """Unique canonical k-mers of the reference in reference order (what `search -e 0` keeps)."""
+    stream = [s for s in canonical_stream(ref_codes, k) if s is not None]
+    counts = {}
+    for key, _, _ in stream:
+        counts[key] = counts.get(key, 0) + 1
+    ordered = [key for key, _, _ in stream if counts[key] == 1 and key != 0]
+    return ordered
+
+
+def orient(keys, k):
+    """qk_orient_insert_kernel: walking orientation F, cont / last / first / strand per ordinal."""
+    n = len(keys)
+    Mlow = (1 << (2 * (k - 1))) - 1
+    F = [0] * n
+    cont = [0] * n
+    for begin in range(0, n, BLOCK):
+        prev = None
+        for o in range(begin, min(n, begin + BLOCK)):
+            K, Kr = keys[o], rc(keys[o], k)
+            f, c = K, 0
+            if prev is not None:
+                want = prev & Mlow
+                if (K >> 2) == want:
+                    f, c = K, 1
+                elif (Kr >> 2) == want:
+                    f, c = Kr, 1
+            if not c and o + 1 < n:
+                nK, nKr = keys[o + 1], rc(keys[o + 1], k)
+                if (nK >> 2) == (K & Mlow) or (nKr >> 2) == (K & Mlow):
+                    f = K
+                elif (nK >> 2) == (Kr & Mlow) or (nKr >> 2) == (Kr & Mlow):
+                    f = Kr
+            F[o], cont[o] = f, c
+            prev = f
+    last = [f & 3 for f in F]
+    first = [f >> (2 * (k - 1)) for f in F]
+    strand = [int(F[o] == keys[o]) for o in range(n)]
+    return cont, last, first, strand
+
+
+def walk_counts(read_codes, keys, k, lookup, cont, last, first, strand):
+    """Ordinal per emitting position the way the kernel derives it; also how many came from the walk."""
+    stream = canonical_stream(read_codes, k)
+    n = len(keys)
+    got, walked = {}, 0
+    for base in range(0, len(read_codes), RUN):
+        run = [p for p in range(base, min(base + RUN, len(read_codes))) if stream[p] is not None]
+        if not run:
+            continue
+        ja = run[0]
+        key, is_fwd, _ = stream[ja]
+        oa = lookup.get(key)
+        verified = {}
+        if oa is not None:
+            plus = bool(strand[oa]) == is_fwd
+            o = oa
+            for p in range(ja + 1, min(base + RUN, len(read_codes))):
+                b = read_codes[p]
+                if plus:
+                    if o + 1 >= n or not cont[o + 1] or last[o + 1] != b:
+                        break
+                    o += 1
+                else:
+                    if o - 1 < 0 or not cont[o] or first[o - 1] != (b ^ 2):
+                        break
+                    o -= 1
+                verified[p] = o
+        for p in run:
+            if p == ja:
+                if oa is not None:
+                    got[p] = oa
+            elif p in verified:
+                got[p] = verified[p]
+                walked += 1
+            else:
+                o = lookup.get(stream[p][0])
+                if o is not None:
+                    got[p] = o
+    return got, walked
+
+
+def brute(read_codes, k, lookup):
+    return {p: lookup[s[0]] for p, s in enumerate(canonical_stream(read_codes, k)) if s is not None and s[0] in lookup}
+
+
+def make_reference(rng, n, flavour):
+    if flavour == "uniform":
+        return rng.integers(0, 4, n).tolist()
+    if flavour == "at_rich":                                # low complexity: lots of accidental overlaps
+        return rng.choice(4, n, p=[0.45, 0.05, 0.45, 0.05]).tolist()
+    if flavour == "tandem":                                 # short tandem repeats with point mutations
+        unit = rng.integers(0, 4, int(rng.integers(2, 7))).tolist()
+        ref = (unit * (n // len(unit) + 1))[:n]
+        for i in rng.integers(0, n, n // 15):
+            ref[i] = int(rng.integers(0, 4))
+        return ref
+    if flavour == "palindromic":                            # a stretch followed by its reverse complement, repeatedly
+        ref = []
+        while len(ref) < n:
+            s = rng.integers(0, 4, int(rng.integers(5, 40))).tolist()
+            ref += s + [c ^ 2 for c in reversed(s)]
+        return ref[:n]
+    raise ValueError(flavour)
+
+
+@pytest.mark.parametrize("flavour", ["uniform", "at_rich", "tandem", "palindromic"])
+@pytest.mark.parametrize("k", [3, 4, 5, 6, 9])
+def test_walk_equals_lookup(k, flavour):
+    rng = np.random.default_rng(1000 * k + len(flavour))
+    total_walked = total = 0
+    n_ref = max(k + 12, min(1500, 4 ** k // 3))               # short enough that unique k-mers exist at small k
+    for trial in range(12):
+        ref = make_reference(rng, n_ref, flavour)
+        keys = build_dictionary(ref, k)
+        if len(keys) < 4:
+            continue
+        lookup = {key: o for o, key in enumerate(keys)}
+        cont, last, first, strand = orient(keys, k)
+        for _ in range(40):
+            span = min(80, len(ref))
+            a = int(rng.integers(0, len(ref) - span + 1))
+            read = list(ref[a:a + int(rng.integers(k, span + 1))])
+            if rng.integers(0, 2):
+                read = [c ^ 2 for c in reversed(read)]       # reverse strand
+            for i in rng.integers(0, len(read), int(rng.integers(0, 3))):
+                read[i] = int(rng.integers(0, 4))            # sequencing errors
+            if rng.integers(0, 4) == 0:                      # chimeric: jump to another locus mid-read
+                b = int(rng.integers(0, max(1, len(ref) - 30)))
+                read = read[:len(read) // 2] + list(ref[b:b + 30])
+            got, walked = walk_counts(read, keys, k, lookup, cont, last, first, strand)
+            assert got == brute(read, k, lookup)
+            total_walked += walked
+            total += len(got)
+    if total == 0:
+        pytest.skip("no unique k-mers in these references (tiny k, repetitive sequence)")
+    assert total_walked > 0                                  # the walk really was exercised
+
+
+def test_orientation_is_consistent():
+    """cont[o] means exactly: F_o is F_{o-1} shifted by one base; strand says which orientation F_o is."""
+    rng = np.random.default_rng(7)
+    k = 7
+    ref = make_reference(rng, 3000, "uniform")
+    keys = build_dictionary(ref, k)
+    cont, last, first, strand = orient(keys, k)
+    Mlow = (1 << (2 * (k - 1))) - 1
+    F = [keys[o] if strand[o] else rc(keys[o], k) for o in range(len(keys))]
+    for o in range(1, len(keys)):
+        if cont[o]:
+            assert (F[o] >> 2) == (F[o - 1] & Mlow) and last[o] == (F[o] & 3) and first[o - 1] == F[o - 1] >> (2 * (k - 1))
+        assert o % BLOCK != 0 or cont[o] == 0
+    assert sum(cont) > 0.5 * len(keys)                       # a random reference is mostly walkable
