@@ -9,6 +9,7 @@
 
 #include <stddef.h>
 #include <stdint.h>
+#include <sys/types.h>
 
 #include "quickmer2_b200.h"
 
@@ -69,6 +70,20 @@ int qk_framer_next(qk_framer *f, uint8_t *dst, size_t cap, size_t *n_bytes, uint
 void qk_framer_get_stats(const qk_framer *f, qk_framer_stats *st);
 void qk_framer_close(qk_framer *f);
 
+/* ---- byte streams: plain or gzip, regular file or pipe -----------------------------------
+ * Everything that reads a reads stream sequentially goes through these: the gzip magic is
+ * recognised on files and pipes alike and the data inflated on the fly (concatenated members
+ * included).  The reference itself reads plain text only (its documented route for compressed
+ * input is a pipe, README.md:89-90). */
+typedef struct qk_stream qk_stream;
+qk_stream *qk_stream_open(const char *path);        /* NULL if it cannot be opened */
+qk_stream *qk_stream_open_fd(int fd, int seekable); /* takes ownership of fd       */
+/* Up to `cap` bytes; short only at the end of the stream; 0 = end, -1 = I/O or format error. */
+ssize_t qk_stream_read(qk_stream *s, uint8_t *dst, size_t cap);
+int qk_stream_is_gzip(const qk_stream *s);
+int qk_stream_seekable(const qk_stream *s);
+void qk_stream_close(qk_stream *s);
+
 /* ---- writers: Q.c:498-518 (.bin) and Q.c:522-542 (.txt) -------------------------------- */
 int qk_write_bin(const char *path, const uint16_t *counts, uint64_t n);
 /* Device -> .bin without a host copy of the whole array (qk_finish_pieces + fwrite). */
@@ -89,6 +104,7 @@ int qk_count_framer(qk_ctx *ctx, qk_framer *f, qk_framer_stats *st);
  * from it) or pageable (then they pass through the slots' pinned buffers). */
 int qk_count_raw_mem(qk_ctx *ctx, const uint8_t *data, size_t n, int seekable, qk_framer_stats *st);
 int qk_count_raw_fd(qk_ctx *ctx, int fd, int seekable, qk_framer_stats *st); /* does not close fd */
+int qk_count_raw_stream(qk_ctx *ctx, qk_stream *in, qk_framer_stats *st);    /* plain or gzip */
 int qk_count_raw_file(qk_ctx *ctx, const char *reads_path, qk_framer_stats *st);
 /* Regular files: `threads` readers (0 = QK_READER_THREADS or 4, at most the slot count)
  * pread() pieces into the pinned slot buffers in parallel; lines longer than 128 KiB are an

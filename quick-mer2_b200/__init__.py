@@ -148,6 +148,13 @@ SIGNATURES = {
     "qk_framer_next": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(C.c_size_t), _P, C.c_uint32, C.POINTER(C.c_uint32)]),
     "qk_framer_get_stats": (None, [_P, C.POINTER(FramerStats)]),
     "qk_framer_close": (None, [_P]),
+    "qk_stream_open": (_P, [C.c_char_p]),
+    "qk_stream_open_fd": (_P, [C.c_int, C.c_int]),
+    "qk_stream_read": (C.c_ssize_t, [_P, _P, C.c_size_t]),
+    "qk_stream_is_gzip": (C.c_int, [_P]),
+    "qk_stream_seekable": (C.c_int, [_P]),
+    "qk_stream_close": (None, [_P]),
+    "qk_count_raw_stream": (C.c_int, [_P, _P, C.POINTER(FramerStats)]),
     "qk_write_bin": (C.c_int, [C.c_char_p, _P, C.c_uint64]),
     "qk_write_bin_from_device": (C.c_int, [_P, C.c_char_p]),
     "qk_write_gc_txt": (C.c_int, [C.c_char_p, _P, _P, _P, C.POINTER(C.c_double)]),
@@ -448,6 +455,27 @@ def write_gc_txt(path, s: np.ndarray, q: np.ndarray, c: np.ndarray) -> float:
     if rc:
         raise QkError(rc, f"cannot write {path}")
     return mean.value
+
+
+def read_stream(path=None, fd=None, seekable: bool = True, piece: int = 1 << 16):
+    """All bytes of a plain or gzip stream through qk_stream_* (host only); returns (bytes, is_gzip)."""
+    L = lib()
+    s = L.qk_stream_open(os.fsencode(str(path))) if path is not None else L.qk_stream_open_fd(fd, int(seekable))
+    if not s:
+        raise QkError(6, f"cannot open {path if path is not None else fd}")
+    out, buf = [], np.empty(piece, dtype=np.uint8)
+    try:
+        gz = bool(L.qk_stream_is_gzip(s))
+        while True:
+            n = L.qk_stream_read(s, _np_ptr(buf), buf.size)
+            if n < 0:
+                raise QkError(6, "stream read failed (I/O error or corrupt gzip data)")
+            if n == 0:
+                break
+            out.append(buf[:n].tobytes())
+    finally:
+        L.qk_stream_close(s)
+    return b"".join(out), gz
 
 
 def frame(data: bytes, seekable: bool = True, chunk_capacity: int = 1 << 20, with_offsets: bool = False):

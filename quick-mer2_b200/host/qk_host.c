@@ -14,6 +14,7 @@
 #include <sys/stat.h>
 #include <time.h>
 #include <unistd.h>
+#include <zlib.h>
 
 #include "../../include/qk_host.h"
 
@@ -377,8 +378,132 @@ int qk_count_raw_mem(qk_ctx *ctx, const uint8_t *data, size_t n, int seekable, q
     return raw_finish(ctx, st, n, unterminated, fastq);
 }
 
+/* ---- byte streams: plain or gzip, regular file or pipe ---------------------------------------
+ * The reference reads plain text only; its documented way to feed compressed data is a pipe
+ * (README.md:89-90).  Here a reads stream is opened through qk_stream_*, which recognises the
+ * gzip magic (1f 8b) on files and pipes alike and inflates on the fly -- concatenated members
+ * (bgzip, `cat a.gz b.gz`) included.  SURVEY.md 8(f) rank 3. */
+struct qk_stream {
+    int fd, gz, seekable, in_eof, z_done, failed;
+    z_stream z;
+    uint8_t *in;            /* compressed bytes (gz) or the peeked first bytes (plain) */
+    size_t in_cap, in_pos, in_have;
+};
+
+static ssize_t stream_fill(qk_stream *s)
+{
+    if (s->in_eof) return 0;
+    s->in_pos = s->in_have = 0;
+    for (;;) {
+        ssize_t got = read(s->fd, s->in, s->in_cap);
+        if (got < 0 && errno == EINTR) continue;
+        if (got < 0) return -1;
+        if (got == 0) s->in_eof = 1;
+        s->in_have = (size_t)got;
+        return got;
+    }
+}
+
+qk_stream *qk_stream_open_fd(int fd, int seekable)
+{
+    qk_stream *s = calloc(1, sizeof *s);
+    if (!s) return NULL;
+    s->fd = fd;
+    s->seekable = seekable;
+    s->in_cap = (size_t)1 << 20;
+    s->in = malloc(s->in_cap);
+    if (!s->in || stream_fill(s) < 0) { free(s->in); free(s); return NULL; }
+    if (s->in_have >= 2 && s->in[0] == 0x1f && s->in[1] == 0x8b) {
+        s->gz = 1;
+        if (inflateInit2(&s->z, 15 + 32) != Z_OK) { free(s->in); free(s); return NULL; }
+    }
+    return s;
+}
+
+qk_stream *qk_stream_open(const char *path)
+{
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return NULL;
+    qk_stream *s = qk_stream_open_fd(fd, lseek(fd, 0, SEEK_CUR) != (off_t)-1);
+    if (!s) close(fd);
+    return s;
+}
+
+int qk_stream_is_gzip(const qk_stream *s) { return s ? s->gz : 0; }
+int qk_stream_seekable(const qk_stream *s) { return s ? s->seekable : 0; }
+
+/* Up to `cap` bytes of (decompressed) stream; short only at the end.  0 = end, -1 = error. */
+ssize_t qk_stream_read(qk_stream *s, uint8_t *dst, size_t cap)
+{
+    if (!s || !dst || s->failed) return -1;
+    size_t out = 0;
+    while (out < cap) {
+        if (!s->gz) {
+            if (s->in_pos < s->in_have) {                    /* the bytes read while peeking */
+                size_t m = s->in_have - s->in_pos < cap - out ? s->in_have - s->in_pos : cap - out;
+                memcpy(dst + out, s->in + s->in_pos, m);
+                s->in_pos += m;
+                out += m;
+                continue;
+            }
+            if (s->in_eof) break;
+            ssize_t got = read(s->fd, dst + out, cap - out);
+            if (got < 0 && errno == EINTR) continue;
+            if (got < 0) { s->failed = 1; return -1; }
+            if (got == 0) { s->in_eof = 1; break; }
+            out += (size_t)got;
+            continue;
+        }
+        if (s->in_pos == s->in_have) {
+            if (s->in_eof) {
+                if (!s->z_done) { s->failed = 1; return -1; } /* truncated member */
+                break;
+            }
+            if (stream_fill(s) < 0) { s->failed = 1; return -1; }
+            if (s->in_have == 0) continue;
+        }
+        if (s->z_done) {                                      /* another member follows */
+            if (inflateReset(&s->z) != Z_OK) { s->failed = 1; return -1; }
+            s->z_done = 0;
+        }
+        s->z.next_in = s->in + s->in_pos;
+        s->z.avail_in = (uInt)(s->in_have - s->in_pos);
+        s->z.next_out = dst + out;
+        s->z.avail_out = (uInt)(cap - out > 0x40000000u ? 0x40000000u : cap - out);
+        const uInt before_out = s->z.avail_out;
+        int zr = inflate(&s->z, Z_NO_FLUSH);
+        s->in_pos = s->in_have - s->z.avail_in;
+        out += before_out - s->z.avail_out;
+        if (zr == Z_STREAM_END) s->z_done = 1;
+        else if (zr != Z_OK && zr != Z_BUF_ERROR) { s->failed = 1; return -1; }
+    }
+    return (ssize_t)out;
+}
+
+void qk_stream_close(qk_stream *s)
+{
+    if (!s) return;
+    if (s->gz) inflateEnd(&s->z);
+    close(s->fd);
+    free(s->in);
+    free(s);
+}
+
 int qk_count_raw_fd(qk_ctx *ctx, int fd, int seekable, qk_framer_stats *st)
 {
+    int dupfd = dup(fd);                     /* the stream owns its descriptor; ours stays with the caller */
+    if (dupfd < 0) return QK_ERR_IO;
+    qk_stream *s = qk_stream_open_fd(dupfd, seekable);
+    if (!s) { close(dupfd); return QK_ERR_IO; }
+    int rc = qk_count_raw_stream(ctx, s, st);
+    qk_stream_close(s);
+    return rc;
+}
+
+int qk_count_raw_stream(qk_ctx *ctx, qk_stream *in, qk_framer_stats *st)
+{
+    if (!in) return QK_ERR_ARG;
+    const int seekable = qk_stream_seekable(in);
     uint32_t n_slots = 0;
     size_t cap = 0;
     int rc = qk_ctx_info(ctx, &n_slots, &cap);
@@ -396,11 +521,10 @@ int qk_count_raw_fd(qk_ctx *ctx, int fd, int seekable, qk_framer_stats *st)
         memcpy(host, tail, tail_len);
         size_t have = tail_len;
         tail_len = 0;
-        while (!eof && have < cap) {
-            ssize_t got = read(fd, host + have, cap - have);
-            if (got < 0 && errno == EINTR) continue;
+        if (!eof && have < cap) {            /* plain or inflated bytes, as many as fit */
+            ssize_t got = qk_stream_read(in, host + have, cap - have);
             if (got < 0) { rc = QK_ERR_IO; break; }
-            if (got == 0) eof = 1;
+            if ((size_t)got < cap - have) eof = 1;
             have += (size_t)got;
         }
         if (rc || have == 0) break;
@@ -732,6 +856,16 @@ static int qm_upload_array(qk_ctx *ctx, int fd, uint64_t file_off, uint64_t n_el
     return rc ? rc : g.err;
 }
 
+static int file_is_gzip(const char *path)
+{
+    uint8_t magic[2] = {0, 0};
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return 0;
+    ssize_t got = pread(fd, magic, 2, 0);
+    close(fd);
+    return got == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
+}
+
 static uint32_t reader_threads_default(void)
 {
     const char *e = getenv("QK_READER_THREADS");
@@ -748,8 +882,8 @@ int qk_count_raw_file_mt(qk_ctx *ctx, const char *reads_path, uint32_t threads, 
     struct stat sb;
     size_t cap = 0;
     qk_ctx_info(ctx, NULL, &cap);
-    if (fstat(fd, &sb) != 0 || !S_ISREG(sb.st_mode) || sb.st_size == 0 || cap < 4 * QK_HEAD) {
-        /* pipe, device, empty file, or slots too small for the headroom: sequential path */
+    if (fstat(fd, &sb) != 0 || !S_ISREG(sb.st_mode) || sb.st_size == 0 || cap < 4 * QK_HEAD || file_is_gzip(reads_path)) {
+        /* pipe, device, empty file, gzip, or slots too small for the headroom: sequential path */
         int seekable = lseek(fd, 0, SEEK_CUR) != (off_t)-1;
         int rc = qk_count_raw_fd(ctx, fd, seekable, st);
         close(fd);
@@ -802,8 +936,8 @@ int qk_count_file_multi(qk_multi *m, const char *reads_path, uint32_t threads_pe
     const uint32_t n = qk_multi_size(m);
     if (!m || n == 0 || !reads_path) return QK_ERR_ARG;
     struct stat sb;
-    if (n == 1 || stat(reads_path, &sb) != 0 || !S_ISREG(sb.st_mode) || sb.st_size == 0)
-        return qk_count_raw_file_mt(qk_multi_ctx(m, 0), reads_path, threads_per_gpu, st); /* pipes: one GPU */
+    if (n == 1 || stat(reads_path, &sb) != 0 || !S_ISREG(sb.st_mode) || sb.st_size == 0 || file_is_gzip(reads_path))
+        return qk_count_raw_file_mt(qk_multi_ctx(m, 0), reads_path, threads_per_gpu, st); /* pipes, gzip: one GPU */
     int fd = open(reads_path, O_RDONLY);
     if (fd < 0) return QK_ERR_IO;
     uint8_t first = 0;

@@ -90,6 +90,30 @@ def test_cli_reads_from_a_pipe(qk, oracle, tmp_path):
     assert np.array_equal(np.fromfile(tmp_path / "q.bin", dtype=np.uint16), want)
 
 
+def test_gzip_input(qk, tmp_path):
+    """reads.fq.gz (one member, several members, through a pipe): same .bin / .txt as the plain file."""
+    import gzip
+    d = GOLDEN / "k30_fastq_t3"
+    raw = (d / "reads.fq").read_bytes()
+    cut = raw.index(b"\n@", len(raw) // 2) + 1
+    (tmp_path / "one.fq.gz").write_bytes(gzip.compress(raw))
+    (tmp_path / "two.fq.gz").write_bytes(gzip.compress(raw[:cut]) + gzip.compress(raw[cut:]))
+    for name in ("one.fq.gz", "two.fq.gz"):
+        res = qk.run_cli(["count", "-t", "2", d / "ref.fa", tmp_path / name, tmp_path / "z"])
+        assert res.returncode == 0, res.stdout + res.stderr
+        assert (tmp_path / "z.bin").read_bytes() == (d / "expect.bin").read_bytes()
+        assert (tmp_path / "z.txt").read_bytes() == (d / "expect.txt").read_bytes()
+    res = subprocess.run([str(qk.CLI_PATH), "count", str(d / "ref.fa"), "/dev/stdin", str(tmp_path / "zp")],
+                         input=gzip.compress(raw), capture_output=True)
+    assert res.returncode == 0, res.stdout
+    assert (tmp_path / "zp.bin").read_bytes() == (d / "expect.bin").read_bytes()
+    st = qk.count(d / "ref.fa", tmp_path / "one.fq.gz", tmp_path / "py")      # the library call
+    assert (tmp_path / "py.bin").read_bytes() == (d / "expect.bin").read_bytes() and st["fastq"] == 1
+    (tmp_path / "bad.fq.gz").write_bytes(gzip.compress(raw)[:-100])
+    res = qk.run_cli(["count", d / "ref.fa", tmp_path / "bad.fq.gz", tmp_path / "bad"])
+    assert res.returncode == 1 and "Counting failed" in res.stdout                # a truncated file is an error, not a short count
+
+
 # ------------------------------------------------------------------ chunking / tiling ------
 @pytest.mark.parametrize("case", ["k30_fasta_t0", "k30_long_lines", "k12_fasta", "k31_fasta"])
 def test_chunk_boundaries_do_not_matter(case, qk, oracle, gpu_ctx):

@@ -244,3 +244,44 @@ def test_human_scale_fits_one_gpu(qk):
     raw = (1 << 32) * 12                      # keys + chain while the chain is ranked
     kbo = 8 * (n + 1)                         # keys by ordinal while the table is filled
     assert max(raw + kbo, kbo + resident) < 170e9
+
+
+# ---------------------------------------------------------------------------- streams ----
+def test_stream_plain_and_gzip(qk, tmp_path):
+    """qk_stream_*: plain files come back as they are, gzip files (also concatenated members, as
+    bgzip writes them) inflated; the same through a pipe; corrupt or truncated gzip data is an error."""
+    import gzip
+    raw = (GOLDEN / "k30_fastq_t3" / "reads.fq").read_bytes()
+    got, gz = qk.read_stream(GOLDEN / "k30_fastq_t3" / "reads.fq")
+    assert got == raw and not gz
+    (tmp_path / "one.gz").write_bytes(gzip.compress(raw))
+    got, gz = qk.read_stream(tmp_path / "one.gz", piece=1000)          # small pieces: many partial inflates
+    assert got == raw and gz
+    cut = raw.index(b"\n@", len(raw) // 3) + 1
+    (tmp_path / "two.gz").write_bytes(gzip.compress(raw[:cut]) + gzip.compress(b"") + gzip.compress(raw[cut:], 1))
+    got, gz = qk.read_stream(tmp_path / "two.gz", piece=1 << 20)
+    assert got == raw and gz
+    big = raw * 40                                                      # several refills of the 1 MiB input window
+    (tmp_path / "big.gz").write_bytes(gzip.compress(big, 1))
+    got, _ = qk.read_stream(tmp_path / "big.gz", piece=333333)
+    assert got == big
+    r, w = os.pipe()                                                    # through a pipe
+    if os.fork() == 0:
+        os.close(r)
+        os.write(w, gzip.compress(raw))
+        os._exit(0)
+    os.close(w)
+    got, gz = qk.read_stream(fd=r, seekable=False)
+    assert got == raw and gz
+    os.wait()
+    (tmp_path / "trunc.gz").write_bytes(gzip.compress(raw)[:-200])
+    with pytest.raises(qk.QkError):
+        qk.read_stream(tmp_path / "trunc.gz")
+    bad = bytearray(gzip.compress(raw)); bad[len(bad) // 2] ^= 0xFF
+    (tmp_path / "bad.gz").write_bytes(bytes(bad))
+    with pytest.raises(qk.QkError):
+        qk.read_stream(tmp_path / "bad.gz")
+    (tmp_path / "empty").write_bytes(b"")
+    assert qk.read_stream(tmp_path / "empty") == (b"", False)
+    with pytest.raises(qk.QkError):
+        qk.read_stream(tmp_path / "missing")
