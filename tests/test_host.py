@@ -285,3 +285,52 @@ def test_stream_plain_and_gzip(qk, tmp_path):
     assert qk.read_stream(tmp_path / "empty") == (b"", False)
     with pytest.raises(qk.QkError):
         qk.read_stream(tmp_path / "missing")
+
+
+def bgzf_compress(data: bytes, block=60000, level=6) -> bytes:
+    """BGZF as bgzip / BAM write it: gzip members with a 'BC' extra field holding the block size."""
+    import struct
+    import zlib
+    out = bytearray()
+    pieces = [data[i:i + block] for i in range(0, len(data), block)] + [b""]   # + the empty end marker
+    for piece in pieces:
+        c = zlib.compressobj(level, zlib.DEFLATED, -15)
+        comp = c.compress(piece) + c.flush()
+        bsize = 12 + 6 + len(comp) + 8 - 1
+        out += struct.pack("<4BI2BH2BHH", 0x1f, 0x8b, 8, 4, 0, 0, 0xff, 6, ord("B"), ord("C"), 2, bsize)
+        out += comp + struct.pack("<II", zlib.crc32(piece), len(piece))
+    return bytes(out)
+
+
+def test_stream_bgzf_is_inflated_in_parallel(qk, tmp_path):
+    import gzip
+    raw = (GOLDEN / "k30_fastq_t3" / "reads.fq").read_bytes() * 30          # ~2.9 MB: ~50 blocks
+    (tmp_path / "r.bgz").write_bytes(bgzf_compress(raw))
+    assert gzip.decompress((tmp_path / "r.bgz").read_bytes()) == raw       # it IS valid multi-member gzip
+    for piece in (777, 1 << 16, 1 << 22):
+        got, gz = qk.read_stream(tmp_path / "r.bgz", piece=piece)
+        assert got == raw and gz
+    os.environ["QK_NO_BGZF"] = "1"                                         # the serial inflater must agree
+    try:
+        assert qk.read_stream(tmp_path / "r.bgz")[0] == raw
+    finally:
+        del os.environ["QK_NO_BGZF"]
+    big = os.urandom(1 << 20) * 3 + raw * 20                                # incompressible blocks, > one 16 MiB window of input? no: several batches of output
+    (tmp_path / "big.bgz").write_bytes(bgzf_compress(big, block=65280, level=1))
+    assert qk.read_stream(tmp_path / "big.bgz", piece=1 << 20)[0] == big
+    data = bytearray(bgzf_compress(raw))
+    data[len(data) // 2] ^= 0x55                                            # corrupt one block: CRC or inflate must catch it
+    (tmp_path / "bad.bgz").write_bytes(bytes(data))
+    with pytest.raises(qk.QkError):
+        qk.read_stream(tmp_path / "bad.bgz")
+    (tmp_path / "cut.bgz").write_bytes(bgzf_compress(raw)[:-5000])          # truncated in the middle of a block
+    with pytest.raises(qk.QkError):
+        qk.read_stream(tmp_path / "cut.bgz")
+    r, w = os.pipe()
+    if os.fork() == 0:
+        os.close(r)
+        os.write(w, bgzf_compress(raw[:200000]))
+        os._exit(0)
+    os.close(w)
+    assert qk.read_stream(fd=r, seekable=False)[0] == raw[:200000]
+    os.wait()
