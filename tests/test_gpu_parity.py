@@ -98,7 +98,9 @@ def test_gzip_input(qk, tmp_path):
     cut = raw.index(b"\n@", len(raw) // 2) + 1
     (tmp_path / "one.fq.gz").write_bytes(gzip.compress(raw))
     (tmp_path / "two.fq.gz").write_bytes(gzip.compress(raw[:cut]) + gzip.compress(raw[cut:]))
-    for name in ("one.fq.gz", "two.fq.gz"):
+    from test_host import bgzf_compress
+    (tmp_path / "blocks.fq.gz").write_bytes(bgzf_compress(raw, block=20000))   # BGZF: inflated by several threads
+    for name in ("one.fq.gz", "two.fq.gz", "blocks.fq.gz"):
         res = qk.run_cli(["count", "-t", "2", d / "ref.fa", tmp_path / name, tmp_path / "z"])
         assert res.returncode == 0, res.stdout + res.stderr
         assert (tmp_path / "z.bin").read_bytes() == (d / "expect.bin").read_bytes()
