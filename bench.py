@@ -380,14 +380,8 @@ def gpu_arm(args):
     # (profiles/README.md) -- so the process group is initialised after it.
     chunk_cap = args.chunk_mib << 20
     ctx = qk.Context(device=local, n_slots=args.slots, chunk_capacity=chunk_cap)
-    if world > 1 or os.environ.get("QK_BENCH_FORCE_DIST"):
-        if world == 1:
-            os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29577")
-            os.environ.setdefault("RANK", "0"); os.environ.setdefault("WORLD_SIZE", "1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        if world == 1:
-            _t = torch.ones(1 << 20, device=f"cuda:{local}"); dist.all_reduce(_t); torch.cuda.synchronize()
     if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist.barrier()
     cdir = cache_dir(args.cache_dir)
     w = WORKLOADS[args.workload]
@@ -399,13 +393,9 @@ def gpu_arm(args):
         dist.barrier()
     d, ref, reads = prepare(args.workload, cdir, rank)
 
-    if os.environ.get("QK_BENCH_PREALLOC_AFTER_CTX_MB"):
-        _shift2 = torch.empty(int(os.environ["QK_BENCH_PREALLOC_AFTER_CTX_MB"]) << 20, dtype=torch.uint8, device=f"cuda:{local}")
     t0 = time.perf_counter()
     if rank == 0:
         n_kmers = ctx.load_dictionary(ref.with_suffix(".fa.qm"))
-    if os.environ.get("QK_BENCH_PREALLOC_AFTER_DICT_MB"):
-        _shift3 = torch.empty(int(os.environ["QK_BENCH_PREALLOC_AFTER_DICT_MB"]) << 20, dtype=torch.uint8, device=f"cuda:{local}")
     load_s = time.perf_counter() - t0
     bcast_s = 0.0
     if world > 1:
