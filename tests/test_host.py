@@ -334,3 +334,28 @@ def test_stream_bgzf_is_inflated_in_parallel(qk, tmp_path):
     os.close(w)
     assert qk.read_stream(fd=r, seekable=False)[0] == raw[:200000]
     os.wait()
+
+
+# ---------------------------------------------------------------------------- framer fuzz
+@pytest.mark.parametrize("fastq_like", [True, False])
+@pytest.mark.parametrize("seed", range(4))
+def test_host_framer_on_malformed_streams(seed, fastq_like, qk, oracle, tmp_path):
+    """The host framer against the oracle's fgets loop on streams that are not valid FASTA/FASTQ
+    (the oracle's reading of them is pinned to the reference binary in tests/test_oracle.py)."""
+    from conftest import weird_stream
+    rng = np.random.default_rng(500 + seed)
+    seq = "".join(rng.choice(list("ACGTacgtN"), size=5000))
+    text = weird_stream(rng, seq, fastq_like, 2000)
+    (tmp_path / "w.txt").write_text(text, newline="")
+    want, ost = oracle.frame_file(tmp_path / "w.txt")
+    for cap in (100000, 123457, 1 << 20):
+        chunks, st = qk.frame(text.encode(), seekable=True, chunk_capacity=cap)
+        assert b"".join(chunks) == want
+        assert (st["lines"], st["bases"], st["fastq"]) == (ost["lines"], ost["bases"], ost["fastq"])
+    # a pipe loses the first line in FASTA mode only (Q.c:395-396)
+    piped, pst = frame_all(qk, text.encode(), seekable=False)
+    if fastq_like:
+        assert piped == want
+    else:
+        (tmp_path / "t.txt").write_text(text[text.index("\n") + 1:], newline="")
+        assert piped == oracle.frame_file(tmp_path / "t.txt")[0]
