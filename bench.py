@@ -8,18 +8,26 @@ One "step" = one whole counting job over the workload's read set: zero the depth
 run codec + probe + increment over every framed chunk, (N > 1: NCCL-reduce the counters to
 rank 0).  Workloads follow BASELINE.json:configs:
 
+  config3  3.1 Gb human-scale reference (16 contigs, ~1/6 of it segmental duplications), k=30,
+           2^32-slot QM11 dictionary (48 GiB file, ~2.2 G unique k-mers, 32 GiB device table),
+           30x = 620 M x 150 bp reads per GPU -- the default: the configuration the metric is
+           quoted on (BASELINE.json:configs[2], 1/2/4/8 B200).  Generated on the GPU
+           (tools/qk_synth_gpu.cu); the reads of the HBM-resident leg never exist on the host.
+  config4  the same dictionary, 30x HiFi-like reads (median 15 kb, up to the 99,998-base line limit)
   config2  64 Mb reference with 200 x 20 kb segmental duplications, k=30 dictionary
-           (58 M k-mers, 1 GiB device table), 30x = 12.8 M x 150 bp FASTQ reads -- the
-           default, the configuration the metric is quoted on for one GPU
+           (58 M k-mers, 1 GiB device table), 30x = 12.8 M x 150 bp FASTQ reads
   config1  1 Mb reference, 1 M x 150 bp FASTA reads (the reference's CPU-runnable case)
-  tiny     smoke-sized (CI)
+  tiny / synth_small   smoke-sized (CI) versions of the file-based and the GPU-generated kind
 
 Printed keys (one JSON line, rank 0):
   value        k-mers/s, framed chunks already resident in HBM (device-event span, max over ranks)
   e2e          k-mers/s through the public call (raw FASTA/FASTQ bytes in pinned host memory ->
                H2D of whole-line pieces -> device framing + count kernels -> D2H of the uint16 depths)
   e2e_preframed  same but from pre-framed pinned chunks: the H2D-overlap pipeline alone
-  roofline     dominant kernel (qk_count_kernel): algorithmic bytes / mean launch time
+  roofline     dominant kernel: SURVEY 8(d) algorithmic bytes / mean launch time (`frac`), and the same on
+               the bytes the kernel actually asks for, from its own probe counters (`frac_issued`)
+  parity_ok    outside the timed region: every rank counts its shard once more; the reduced counters
+               must equal the sum of the per-rank ones under a position-weighted checksum (linearity)
   cpu_baseline the reference's own `count -t T` (oracle/_ref/quicKmer2) on a bounded sample
                of the same workload, on this box's host cores
 
@@ -94,6 +102,34 @@ WORKLOADS = {
 }
 
 
+HUMAN = dict(n_bases=3_100_000_000, contigs=16, seed=2026, dup_period=120_000, dup_len=22_000, div_ppm=5000, nblock=50_000)
+SMALL = dict(n_bases=40_000_000, contigs=4, seed=2026, dup_period=120_000, dup_len=22_000, div_ppm=5000, nblock=50_000)
+# GPU-generated workloads (tools/qk_synth_gpu.cu): genome + dictionary made on the device and written as the
+# QM11 files both arms read; reads generated straight into HBM (value) / pinned host memory (e2e) / a
+# sample file (CPU arm).  reads = per GPU.
+SYNTH_WORKLOADS = {
+    "config3": dict(genome=HUMAN, dict_dir="human_k30", k=30, slots=1 << 32, ctrl_block=100_000,
+                    reads=620_000_000, read_len=150, err_ppm=2000, fastq=True, hifi=False, seed=42, sample_reads=20_700_000,
+                    desc="3.1 Gb synthetic human-scale reference (16 contigs, 18% segmental duplications at 0.5% divergence), k=30, "
+                         "2^32-slot .qm; 30x = 620M x 150bp reads per GPU"),
+    "config4": dict(genome=HUMAN, dict_dir="human_k30", k=30, slots=1 << 32, ctrl_block=100_000,
+                    reads=5_470_000, read_len=15000, err_ppm=1000, fastq=False, hifi=True, seed=42, sample_reads=150_000,
+                    desc="config-3 dictionary; 30x HiFi-like reads (log-normal, median 15 kb, clipped to [1 kb, 99,998]), FASTA"),
+    "synth_small": dict(genome=SMALL, dict_dir="small_k30", k=30, slots=1 << 26, ctrl_block=100_000,
+                        reads=2_000_000, read_len=150, err_ppm=2000, fastq=True, hifi=False, seed=42, sample_reads=200_000,
+                        desc="40 Mb GPU-generated reference, k=30, 2M x 150bp reads (CI-sized config 3)"),
+    "synth_small_hifi": dict(genome=SMALL, dict_dir="small_k30", k=30, slots=1 << 26, ctrl_block=100_000,
+                             reads=20_000, read_len=15000, err_ppm=1000, fastq=False, hifi=True, seed=42, sample_reads=2_000,
+                             desc="40 Mb GPU-generated reference, k=30, 20k HiFi-like reads (CI-sized config 4)"),
+}
+
+
+def load_synth_gpu():
+    sys.path.insert(0, str(ROOT / "tools"))
+    import qk_synth_gpu
+    return qk_synth_gpu
+
+
 def load_package():
     spec = importlib.util.spec_from_file_location("quickmer2_b200", PKG_DIR / "__init__.py",
                                                   submodule_search_locations=[str(PKG_DIR)])
@@ -153,8 +189,72 @@ def ensure(path: Path, make):
         lock.unlink(missing_ok=True)
 
 
+def synth_genome(w, device=0):
+    qs = load_synth_gpu()
+    return qs.Genome.create(device=device, **w["genome"])
+
+
+def synth_lens(w, seed, first, n):
+    """Lengths of reads [first, first + n) of stream `seed` (HiFi workloads), else None."""
+    if not w["hifi"]:
+        return None
+    qs = load_synth_gpu()
+    # blocks of 2^20 reads so that any sub-range sees the same lengths
+    B = 1 << 20
+    out = []
+    for b in range(first // B, (first + n + B - 1) // B):
+        out.append(qs.hifi_lengths(B, seed * 1_000_003 + b, median=w["read_len"]))
+    lens = np.concatenate(out) if out else np.zeros(0, np.uint32)
+    return lens[first - (first // B) * B:][:n]
+
+
+def prepare_synth(name, cdir, sample=False, genome=None, device=0):
+    """GPU-generated workload: the QM11 dictionary files (shared by the workloads that name the same
+    dict_dir) and, if asked, the reads sample file of the CPU arm.  Needs a CUDA device only when
+    something is missing from the cache.  Returns (dir, ref prefix, sample path or None)."""
+    w = SYNTH_WORKLOADS[name]
+    qs = load_synth_gpu()
+    d = cdir / w["dict_dir"]
+    d.mkdir(parents=True, exist_ok=True)
+    ref = d / "ref.fa"
+    own = [None]
+
+    def g():
+        if genome is not None:
+            return genome
+        if own[0] is None:
+            own[0] = synth_genome(w, device)
+        return own[0]
+
+    def make_dict():
+        info = g().build_dict(k=w["k"], slots=w["slots"], ctrl_block=w["ctrl_block"])
+        log(f"dictionary on the GPU: {info}")
+        g().write_dict(d / "tmpdict", threads=min(16, os.cpu_count() or 1))
+        g().free_dict()
+        (d / "dict_info.json").write_text(json.dumps(info))
+        os.replace(d / "tmpdict.qgc", d / "ref.fa.qgc")
+        os.replace(d / "tmpdict.qm", d / "ref.fa.qm")
+    ensure(d / "ref.fa.qm", make_dict)
+    reads = None
+    if sample:
+        n = w["sample_reads"]
+        reads = d / f"sample_{name}_{n}_s{w['seed']}.{'fq' if w['fastq'] else 'fa'}"
+
+        def make_sample():
+            tmp = reads.with_suffix(".tmp")
+            g().reads_to_file(tmp, w["seed"], 0, n, w["read_len"], w["err_ppm"], qs.FASTQ if w["fastq"] else qs.FASTA,
+                              lens=synth_lens(w, w["seed"], 0, n))
+            os.replace(tmp, reads)
+        ensure(reads, make_sample)
+    if own[0] is not None:
+        own[0].close()
+    return d, ref, reads
+
+
 def prepare(name, cdir, rank_seed_offset=0, sample=False):
     """Reference, dictionary and reads of a workload; returns paths."""
+    if name in SYNTH_WORKLOADS:
+        return prepare_synth(name, cdir, sample=sample)
     w = WORKLOADS[name]
     d = cdir / name
     d.mkdir(parents=True, exist_ok=True)
@@ -286,10 +386,11 @@ def cpu_threads():
 
 
 def cpu_baseline(name, cdir, threads=None):
-    w = WORKLOADS[name]
+    table = SYNTH_WORKLOADS if name in SYNTH_WORKLOADS else WORKLOADS
+    w = table[name]
     if not REF_BIN.exists():      # only the single-threaded port is here: keep its sample to ~10-20 s of CPU work
         w = dict(w, sample_reads=max(1000, w["sample_reads"] // 64))
-        WORKLOADS[name] = w
+        table[name] = w
     d, ref, sample = prepare(name, cdir, sample=True)
     t, ncpu = cpu_threads()
     t = threads or t
@@ -322,20 +423,33 @@ def reference_arm(args):
     subprocess.run(["make", "-s", "-C", str(PKG_DIR), str(SYNTH)], check=True)
     if not REF_BIN.exists():                     # the compiled reference did not travel: time the port instead
         subprocess.run(["make", "-s", "-C", str(ROOT / "oracle"), "port"], check=True)
-    w = WORKLOADS[args.workload]
+    w = (SYNTH_WORKLOADS if args.workload in SYNTH_WORKLOADS else WORKLOADS)[args.workload]
     times, kmers, base = [], 0, None
+    t_start, steps_done, warm_done = time.time(), 0, 0
     for i in range(args.warmup + args.steps):
+        # Every step is a fresh run of the reference command, which first loads the dictionary (48 GiB at
+        # human scale): once the run has used its time budget, stop after >= 1 warm-up and >= 2 timed
+        # steps and report the steps really taken.
+        over = time.time() - t_start > args.reference_budget_s
+        if i < args.warmup and over and warm_done >= 1:
+            continue
+        if i >= args.warmup and over and steps_done >= 2:
+            break
         base = cpu_baseline(args.workload, cdir)
         if i >= args.warmup:
             times.append(base["seconds"])
             kmers += base["kmers"]
+            steps_done += 1
+        else:
+            warm_done += 1
         log(f"reference step {i}: {base['kmers'] / base['seconds'] / 1e6:.1f} M k-mers/s")
     value = kmers / sum(times)
     base["value"] = value
     base.pop("seconds"), base.pop("kmers")
     print(json.dumps({
         "impl": "reference", "metric": "k-mers/sec for quicKmer2 count", "value": value, "unit": "k-mers/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+        "n_gpus": args.gpus, "steps": steps_done, "warmup": warm_done, "ms_per_step": 1e3 * sum(times) / len(times),
+        "steps_requested": args.steps, "warmup_requested": args.warmup,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": {"workload": args.workload, "desc": w["desc"], "step": f"CPU count over a {w['sample_reads']}-read sample"},
         "cpu_baseline": base,
@@ -350,6 +464,192 @@ def measured_peaks():
     if p.exists():
         return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def profile_traffic(kernel, workload, chunk_mib):
+    """DRAM bytes per launch of the dominant kernel from a committed `ncu --set full` capture of this
+    very workload (profiles/traffic.json, keyed by kernel | workload | chunk size), else None."""
+    p = ROOT / "profiles" / "traffic.json"
+    if not p.exists():
+        return None, None
+    ent = json.loads(p.read_text()).get(f"{kernel}|{workload}|{chunk_mib}")
+    return (ent["dram_bytes_per_launch"], ent["source"]) if ent else (None, None)
+
+
+class FileData:
+    """Reads of a file-based workload: raw bytes (pinned), host-framed chunks (pinned) and their copy in HBM."""
+
+    def __init__(self, qk, torch, reads, chunk_cap, local):
+        raw_np = np.fromfile(reads, dtype=np.uint8)
+        self.raw = torch.from_numpy(raw_np).pin_memory()
+        self.raw_bytes = int(raw_np.size)
+        t0 = time.perf_counter()
+        chunks, fst = qk.frame(raw_np, seekable=True, chunk_capacity=chunk_cap)
+        self.frame_s = time.perf_counter() - t0
+        self.sizes = [len(c) for c in chunks]
+        self.offs, at = [], 0
+        for sz in self.sizes:
+            self.offs.append(at)
+            at = (at + sz + 255) // 256 * 256
+        self.framed = torch.empty(at + 4096, dtype=torch.uint8).pin_memory()
+        fnp = self.framed.numpy()
+        for c, o in zip(chunks, self.offs):
+            fnp[o:o + len(c)] = np.frombuffer(c, dtype=np.uint8)
+        del chunks
+        self.dev = self.framed.to(f"cuda:{local}")
+        torch.cuda.synchronize()
+        self.dev_base, self.host_base = self.dev.data_ptr(), self.framed.data_ptr()
+        self.n_framed = sum(self.sizes)
+        self.lines, self.bases = fst["lines"], fst["bases"]
+        # the host legs run over the same reads
+        self.h_offs, self.h_sizes, self.h_framed_bytes = self.offs, self.sizes, self.n_framed
+        self.h_lines, self.h_bases = self.lines, self.bases
+        self.reads_file = reads
+        self.note = None
+
+
+class SynthData:
+    """Reads of a GPU-generated workload.  value: `reads` records per GPU generated straight into HBM as
+    framed sequence lines (they never exist on the host).  Host legs (e2e, e2e_preframed): a bounded
+    prefix of the same stream, as raw FASTQ/FASTA and as framed lines, in pinned host memory."""
+
+    def __init__(self, qs, torch, genome, w, seed, chunk_cap, local, world, reads_scale, e2e_cov_cap):
+        fmt_raw = qs.FASTQ if w["fastq"] else qs.FASTA
+        n = max(1000, int(w["reads"] * reads_scale))
+        L = w["read_len"]
+        free_b, _ = C_mem_info(qs, local)
+        # ---- value: framed reads in HBM, cut into chunks of whole records at 16-byte-aligned offsets
+        lens = synth_lens(w, seed, 0, n)
+        per = (lens.astype(np.uint64) + 1) if lens is not None else None
+        budget = free_b - (6 << 30)
+        need = int(per.sum()) if per is not None else n * (L + 1)
+        if need > budget:                                 # (a table larger than planned): fewer reads, said in `note`
+            keep = budget / need
+            n = int(n * keep) // 16 * 16
+            lens = None if lens is None else lens[:n]
+            per = None if per is None else per[:n]
+            self.note = f"reads per GPU cut to {n} to fit HBM next to the table"
+        else:
+            self.note = None
+        if lens is None:
+            rpc = max(16, (chunk_cap // (L + 1)) // 16 * 16)        # reads per chunk; 16 records = a multiple of 16 bytes
+            starts = list(range(0, n, rpc))
+            self.sizes = [min(rpc, n - a) * (L + 1) for a in starts]
+            self.offs = [a * (L + 1) for a in starts]
+            total = n * (L + 1)
+            self.devbuf = qs.DeviceBuffer(local, total + 4096)
+            genome.reads_into(self.devbuf.ptr, seed, 0, n, L, w["err_ppm"], qs.FRAMED)
+            self.bases = n * L
+        else:
+            offsets, self.offs, self.sizes = chunk_layout(per, chunk_cap)
+            total = int(offsets[-1] + per[-1]) if n else 0
+            self.devbuf = qs.DeviceBuffer(local, total + 4096)
+            genome.reads_into(self.devbuf.ptr, seed, 0, n, L, w["err_ppm"], qs.FRAMED, lens, offsets)
+            self.bases = int(lens.astype(np.uint64).sum())
+        self.dev_base = self.devbuf.ptr
+        self.n_framed = sum(self.sizes)
+        self.lines = n
+        self.frame_s = 0.0
+
+        # ---- host legs: a prefix of the stream in pinned memory, sized to what the host can pin
+        avail = host_mem_available()
+        rec_raw = qs.record_bytes(L, fmt_raw) if lens is None else None
+        mean_raw = rec_raw if lens is None else float(np.mean(per)) * (1 if not w["fastq"] else 2) + 15
+        mean_framed = (L + 1) if lens is None else float(np.mean(per))
+        cap_bytes = max(1 << 28, int((avail - (24 << 30)) / max(1, world) * 0.6))
+        hn = int(min(n, e2e_cov_cap * n / 30.0, cap_bytes / (mean_raw + mean_framed)))
+        hn = max(16, hn // 16 * 16)
+        hlens = None if lens is None else lens[:hn]
+        raw_total, raw_offsets = qs.layout(hn, L, fmt_raw, hlens)
+        self.raw = torch.empty(raw_total + 64, dtype=torch.uint8, pin_memory=True)
+        self.raw_bytes = raw_total
+        fill_pinned(qs, genome, self.raw.data_ptr(), seed, hn, L, w["err_ppm"], fmt_raw, hlens, raw_offsets, local)
+        if hlens is None:
+            rpc = max(16, (chunk_cap // (L + 1)) // 16 * 16)
+            starts = list(range(0, hn, rpc))
+            self.h_sizes = [min(rpc, hn - a) * (L + 1) for a in starts]
+            self.h_offs = [a * (L + 1) for a in starts]
+            f_total, f_offsets = hn * (L + 1), None
+        else:
+            f_offsets, self.h_offs, self.h_sizes = chunk_layout(per[:hn], chunk_cap)
+            f_total = int(f_offsets[-1] + per[hn - 1])
+        self.framed = torch.empty(f_total + 4096, dtype=torch.uint8, pin_memory=True)
+        fill_pinned(qs, genome, self.framed.data_ptr(), seed, hn, L, w["err_ppm"], qs.FRAMED, hlens, f_offsets, local)
+        self.host_base = self.framed.data_ptr()
+        self.h_framed_bytes = sum(self.h_sizes)
+        self.h_lines = hn
+        self.h_bases = hn * L if hlens is None else int(hlens.astype(np.uint64).sum())
+        self.reads_file = None
+
+    def free_host(self):
+        self.raw = self.framed = None
+
+
+def chunk_layout(per, chunk_cap):
+    """Records of `per[i]` bytes packed into chunks of at most chunk_cap bytes, every chunk starting at a
+    16-byte-aligned offset: returns (record offsets, chunk offsets, chunk sizes)."""
+    n = per.size
+    offsets = np.zeros(n, dtype=np.uint64)
+    c_offs, c_sizes = [], []
+    csum = np.concatenate([[0], np.cumsum(per, dtype=np.uint64)])
+    i, at = 0, 0
+    while i < n:
+        j = int(np.searchsorted(csum, csum[i] + np.uint64(chunk_cap - 16), side="right")) - 1
+        j = max(j, i + 1)
+        offsets[i:j] = (csum[i:j] - csum[i]) + np.uint64(at)
+        size = int(csum[j] - csum[i])
+        c_offs.append(at)
+        c_sizes.append(size)
+        at = (at + size + 255) // 256 * 256
+        i = j
+    return offsets, c_offs, c_sizes
+
+
+def fill_pinned(qs, genome, host_ptr, seed, n, L, err_ppm, fmt, lens, offsets, local, piece_bytes=1 << 30):
+    """Generate records [0, n) on the device a piece at a time and copy them to pinned host memory at
+    host_ptr (+ their offsets)."""
+    tmp = qs.DeviceBuffer(local, piece_bytes + (1 << 20))
+    try:
+        if lens is None:
+            rec = qs.record_bytes(L, fmt)
+            per_piece = max(1, piece_bytes // rec)
+            for a in range(0, n, per_piece):
+                m = min(per_piece, n - a)
+                genome.reads_into(tmp.ptr, seed, a, m, L, err_ppm, fmt)
+                if qs.lib().qs_copy_to_host(host_ptr + a * rec, tmp.ptr, m * rec):
+                    raise RuntimeError("D2H failed")
+        else:
+            rec = (lens.astype(np.uint64) + 1) if fmt == qs.FRAMED else (13 + lens.astype(np.uint64) + 1) if fmt == qs.FASTA \
+                else (13 + 2 * (lens.astype(np.uint64) + 1) + 2)
+            ends = offsets + rec
+            a = 0
+            while a < n:                          # groups of records spanning at most one staging piece
+                base = int(offsets[a])
+                b = max(a + 1, int(np.searchsorted(ends, np.uint64(base + piece_bytes), side="right")))
+                span = int(ends[b - 1]) - base    # (alignment gaps between chunks carry garbage: never read)
+                genome.reads_into(tmp.ptr, seed, a, b - a, L, err_ppm, fmt, lens[a:b], offsets[a:b] - np.uint64(base))
+                if qs.lib().qs_copy_to_host(host_ptr + base, tmp.ptr, span):
+                    raise RuntimeError("D2H failed")
+                a = b
+    finally:
+        tmp.free()
+
+
+def host_mem_available():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) << 10
+    except OSError:
+        pass
+    return 32 << 30
+
+
+def C_mem_info(qs, device):
+    import ctypes
+    f, t = ctypes.c_uint64(), ctypes.c_uint64()
+    qs.lib().qs_device_mem_info(device, ctypes.byref(f), ctypes.byref(t))
+    return f.value, t.value
 
 
 def gpu_arm(args):
@@ -375,23 +675,35 @@ def gpu_arm(args):
         time.sleep(1.0)                              # rank 0's make may still be writing
     if os.environ.get("QK_BENCH_PREALLOC_MB"):       # diagnostic: another CUDA allocation before the context
         _shift = torch.empty(int(os.environ["QK_BENCH_PREALLOC_MB"]) << 20, dtype=torch.uint8, device=f"cuda:{local}")
-    # The context goes first: with any other CUDA allocation made before it (a 64 MB torch tensor, or
-    # NCCL's buffers at init) the count kernels run 6-7 % slower -- measured, cause not established
-    # (profiles/README.md) -- so the process group is initialised after it.
+    # The context goes first (see profiles/README.md, allocation order), the process group after it.
     chunk_cap = args.chunk_mib << 20
     ctx = qk.Context(device=local, n_slots=args.slots, chunk_capacity=chunk_cap)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist.barrier()
     cdir = cache_dir(args.cache_dir)
-    w = WORKLOADS[args.workload]
+    synth = args.workload in SYNTH_WORKLOADS
+    w = (SYNTH_WORKLOADS if synth else WORKLOADS)[args.workload]
 
     # ---- data: every rank has its own reads shard (seed + rank); rank 0 builds the dictionary
-    if rank == 0:
-        d, ref, reads = prepare(args.workload, cdir, 0)
-    if world > 1:
-        dist.barrier()
-    d, ref, reads = prepare(args.workload, cdir, rank)
+    t_setup = time.perf_counter()
+    genome = None
+    if synth:
+        qs = load_synth_gpu()
+        genome = synth_genome(w, local)
+        if rank == 0:
+            d, ref, _ = prepare_synth(args.workload, cdir, sample=not args.no_cpu and not args.kernel_only, genome=genome, device=local)
+        if world > 1:
+            dist.barrier()
+        d, ref = cdir / w["dict_dir"], cdir / w["dict_dir"] / "ref.fa"
+        reads = None
+    else:
+        if rank == 0:
+            d, ref, reads = prepare(args.workload, cdir, 0)
+        if world > 1:
+            dist.barrier()
+        d, ref, reads = prepare(args.workload, cdir, rank)
+    gen_s = time.perf_counter() - t_setup
 
     t0 = time.perf_counter()
     if rank == 0:
@@ -412,33 +724,23 @@ def gpu_arm(args):
         counters_ab.append(qd.counters_tensor(ctx, local))
         ctx.select_counters(0)
 
-    # ---- host side: raw reads in memory, framed chunks (pinned), device-resident copy ----
-    raw_np = np.fromfile(reads, dtype=np.uint8)
-    raw_pinned = torch.from_numpy(raw_np).pin_memory()       # the e2e leg DMAs straight from here
+    # ---- reads: in HBM for `value`; raw + framed in pinned host memory for the e2e legs ----
     t0 = time.perf_counter()
-    chunks, fst = qk.frame(raw_np, seekable=True, chunk_capacity=chunk_cap)
-    frame_s = time.perf_counter() - t0
-    sizes = [len(c) for c in chunks]
-    offs, at = [], 0
-    for s in sizes:
-        offs.append(at)
-        at = (at + s + 255) // 256 * 256
-    framed = torch.empty(at + 4096, dtype=torch.uint8).pin_memory()
-    fnp = framed.numpy()
-    for c, o in zip(chunks, offs):
-        fnp[o:o + len(c)] = np.frombuffer(c, dtype=np.uint8)
-    del chunks
-    dev = framed.to(f"cuda:{local}")
-    torch.cuda.synchronize()
-    dev_base, host_base = dev.data_ptr(), framed.data_ptr()
-    n_framed = sum(sizes)
+    if synth:
+        data = SynthData(qs, torch, genome, w, w["seed"] + rank, chunk_cap, local, world, args.reads_scale, args.e2e_coverage)
+        genome.close()
+    else:
+        data = FileData(qk, torch, reads, chunk_cap, local)
+    reads_s = time.perf_counter() - t0
+    log(f"rank {rank}: data ready (dictionary files {gen_s:.1f} s, load+build {load_s:.1f} s, broadcast {bcast_s:.1f} s, reads {reads_s:.1f} s); "
+        f"{data.lines} reads / {data.n_framed >> 20} MiB framed in HBM in {len(data.sizes)} chunks")
 
     stream0 = torch.cuda.ExternalStream(ctx.slot_stream(0), device=f"cuda:{local}")
 
     pending = [None, None]                        # the reduce still in flight on each counter buffer
     job_no = [0]
 
-    def job_device():
+    def job_device(reduce=True):
         # one stream (slot 0): launches run back to back, so the per-launch event times are not
         # inflated by two kernels sharing the SMs and the kernel's share of the step is meaningful.
         # Nothing here waits on the host: reset, kernels and (N > 1) the reduce are stream-ordered.
@@ -450,15 +752,14 @@ def gpu_arm(args):
                     pending[b].wait()
                 pending[b] = None
         ctx.reset_async()
-        for o, s in zip(offs, sizes):
-            ctx.submit_device(dev_base + o, s, slot=0)
-
-    def finish_device_step():
-        b = job_no[0] & 1 if world > 1 else 0
+        base = data.dev_base
+        for o, sz in zip(data.offs, data.sizes):
+            ctx.submit_device(base + o, sz, slot=0)
         job_no[0] += 1
-        if world > 1 and not os.environ.get("QK_BENCH_NO_REDUCE"):   # (diagnostic knob: what the reduce costs)
+        if world > 1 and reduce and not os.environ.get("QK_BENCH_NO_REDUCE"):   # (diagnostic knob: what the reduce costs)
             with torch.cuda.stream(stream0):      # NCCL starts after slot 0's kernels; slot 0 does NOT wait for it
                 pending[b] = dist.reduce(counters_ab[b], 0, op=dist.ReduceOp.SUM, async_op=True)
+        return b
 
     def drain_device():
         for b in (0, 1):
@@ -469,12 +770,12 @@ def gpu_arm(args):
 
     def job_preframed():
         ctx.reset()
-        for i, (o, s) in enumerate(zip(offs, sizes)):
-            ctx.submit_host(host_base + o, s, slot=i % ctx.n_slots)
+        for i, (o, sz) in enumerate(zip(data.h_offs, data.h_sizes)):
+            ctx.submit_host(data.host_base + o, sz, slot=i % ctx.n_slots)
 
     def job_raw():
         ctx.reset()
-        ctx.count_mem(raw_pinned.data_ptr(), raw_pinned.numel())
+        ctx.count_mem(data.raw.data_ptr(), data.raw_bytes)
 
     def finish_step():
         """N > 1: combine the per-GPU counters on rank 0 (the one exchange step of the path)."""
@@ -490,9 +791,23 @@ def gpu_arm(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    def all_sum(vals):
+        if world == 1:
+            return [int(v) for v in vals]
+        t = torch.tensor(vals, dtype=torch.int64, device=f"cuda:{local}")
+        dist.all_reduce(t)
+        return [int(x) for x in t.tolist()]
+
+    def all_max(v):
+        if world == 1:
+            return float(v)
+        t = torch.tensor([v], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     # ---- value: inputs resident in HBM ---------------------------------------------------
     for _ in range(args.warmup):
-        job_device(); finish_device_step()
+        job_device()
     drain_device()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
@@ -500,7 +815,7 @@ def gpu_arm(args):
     t_wall0 = time.time()
     ctx.span_begin()
     for _ in range(args.steps):
-        job_device(); finish_device_step()
+        job_device()
     drain_device()                                # the last reduce is inside the span too
     span_ms = ctx.span_end()
     barrier()
@@ -510,27 +825,51 @@ def gpu_arm(args):
     tm = {"kernel_ms": tm["kernel_ms"] / args.steps, "h2d_ms": tm["h2d_ms"] / args.steps, "launches": tm["launches"] // args.steps}
     stats = ctx.stats()                           # device totals of the last step (each step zeroes them)
     step_kmers, step_hits = stats["total_kmers"], stats["hits"]
-    if world > 1:
-        t = torch.tensor([span_ms], dtype=torch.float64, device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        span_ms = float(t.item())
-        t = torch.tensor([step_kmers, step_hits, n_framed], dtype=torch.int64, device=f"cuda:{local}")
-        dist.all_reduce(t)
-        job_kmers, job_hits, job_bytes = (int(x) for x in t.tolist())
-    else:
-        job_kmers, job_hits, job_bytes = step_kmers, step_hits, n_framed
+    span_ms = all_max(span_ms)
+    job_kmers, job_hits, job_bytes, job_bases = all_sum([step_kmers, step_hits, data.n_framed, data.bases])
     ms_per_step = span_ms / args.steps
     value = job_kmers / (ms_per_step * 1e-3)
 
-    # sanity (outside the timed region): every hit landed on exactly one counter (the buffer of the last job)
+    # ---- parity, outside the timed region: the reduced counters are the sum of the per-rank ones ---------
+    # One more job without the reduce; every rank takes a position-weighted checksum of its own counters
+    # (linear in the counters, arithmetic mod 2^63), the checksums are added over the ranks; then the reduce
+    # runs and rank 0 takes the same checksum of the reduced counters.  Also: every hit is on exactly one counter.
+    def checksum(t):
+        tot, wsum = 0, 0
+        n = t.numel()
+        piece = 1 << 27
+        for a in range(0, n, piece):
+            x = t[a:a + piece].to(torch.int64) & 0xFFFFFFFF
+            idx = torch.arange(a, a + x.numel(), device=x.device, dtype=torch.int64)
+            wgt = ((idx * 2654435761) & 0xFFFFF) | 1
+            tot += int(x.sum().item())
+            wsum = (wsum + int((x * wgt).sum().item())) & ((1 << 62) - 1)
+        return tot, wsum
+
+    b = job_device(reduce=False)
+    ctx.sync()
+    torch.cuda.synchronize()
+    own_tot, own_w = checksum(counters_ab[b])
+    own_hits = ctx.stats()["hits"]
+    sum_tot, sum_hits = all_sum([own_tot, own_hits])
+    (sum_w,) = all_sum([own_w])
+    sum_w &= (1 << 62) - 1
+    if world > 1:
+        dist.reduce(counters_ab[b], 0, op=dist.ReduceOp.SUM)
+        torch.cuda.synchronize()
+    parity = None
     if rank == 0:
-        total_counts = int(ctx.counters().astype(np.int64).sum())
-        assert total_counts == job_hits or os.environ.get("QK_BENCH_NO_REDUCE"), (total_counts, job_hits)
+        red_tot, red_w = checksum(counters_ab[b])
+        parity = {"ok": bool(red_tot == sum_tot == sum_hits and red_w == sum_w), "counter_sum": red_tot, "hits": sum_hits,
+                  "weighted_checksum_reduced": red_w, "weighted_checksum_sum_of_ranks": sum_w,
+                  "how": "extra job outside the timed region: sum over ranks of a position-weighted checksum of each rank's own "
+                         "counters == the same checksum of the NCCL-reduced counters on rank 0; counter sum == hits"}
+        assert parity["ok"] or os.environ.get("QK_BENCH_NO_REDUCE"), parity
     ctx.select_counters(0)
 
     # ---- e2e_preframed and e2e: host buffers, copies inside the timed region --------------
-    result_pinned = torch.empty(n_kmers, dtype=torch.int16).pin_memory()
-    result_np = result_pinned.numpy().view(np.uint16)
+    result_pinned = torch.empty(n_kmers, dtype=torch.int16, pin_memory=True) if rank == 0 else None
+    result_np = result_pinned.numpy().view(np.uint16) if rank == 0 else None
 
     def timed_host(job, steps, warm):
         for _ in range(warm):
@@ -542,30 +881,36 @@ def gpu_arm(args):
             if rank == 0:
                 ctx.finish(result_np)             # D2H of the step's result: uint16 depths in .bin order (pinned)
         barrier()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{local}")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        return dt / steps
+        dt = all_max(time.perf_counter() - t0)
+        (k,) = all_sum([ctx.stats()["total_kmers"]])
+        return dt / steps, k
 
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    h_kmers = None
     if args.kernel_only:
         pre_s = raw_s = float("nan")
         h2d_ms_step = None
     else:
-        pre_s = timed_host(job_preframed, args.steps, 1)
+        pre_s, h_kmers = timed_host(job_preframed, e2e_steps, 1)
         h2d_ms_step = ctx.timing()["h2d_ms"]
-        raw_s = timed_host(job_raw, e2e_steps, 1)
+        raw_s, h_kmers_raw = timed_host(job_raw, e2e_steps, 1)
+        assert h_kmers_raw == h_kmers, (h_kmers_raw, h_kmers)
+    (h_raw_bytes, h_framed_bytes, h_bases) = all_sum([data.raw_bytes, data.h_framed_bytes, data.h_bases])
 
     # ---- e2e from a FILE (page cache): reader threads pread() into the pinned slots ---------
     file_s = None
-    if world == 1 and not args.kernel_only:
+    file_reads = data.reads_file
+    if synth and rank == 0 and not args.no_cpu and not args.kernel_only:
+        file_reads = prepare_synth(args.workload, cdir, sample=True)[2]      # the CPU arm's sample (already cached)
+    if world == 1 and not args.kernel_only and file_reads is not None:
         def job_file():
             ctx.reset()
-            ctx.count_file(reads, threads=args.reader_threads)
-        file_s = timed_host(job_file, 2, 1)
+            ctx.count_file(file_reads, threads=args.reader_threads)
+        file_s, file_kmers = timed_host(job_file, 2, 1)
+        file_bytes = os.path.getsize(file_reads)
 
+    if synth:
+        data.free_host()
     if rank != 0:
         ctx.close()
         if world > 1:
@@ -575,9 +920,13 @@ def gpu_arm(args):
 
     # ---- roofline of the dominant kernel -------------------------------------------------
     launches = int(tm["launches"])
-    alg_bytes_step = 32 * step_kmers + 4 * step_hits + n_framed   # bucket sector + counter word + input byte
+    alg_bytes_step = 32 * step_kmers + 4 * step_hits + data.n_framed   # bucket sector + counter word + input byte
+    # what the kernel really asks of memory, from its own counters: 32 B per bucket probe it issued, 16 B of
+    # extension-array words per walk it started, 4 B per hit, 1 B per input byte
+    issued_bytes_step = 32 * stats["bucket_probes"] + 16 * stats["walks"] + 4 * step_hits + data.n_framed
     avg_launch_ms = tm["kernel_ms"] / max(1, launches)
     achieved = alg_bytes_step / max(1, launches) / (avg_launch_ms * 1e-3) / 1e9
+    achieved_issued = issued_bytes_step / max(1, launches) / (avg_launch_ms * 1e-3) / 1e9
     peak, peak_src = measured_peaks()
     if args.kernel_only:
         gather = h2d = float("nan")
@@ -585,23 +934,29 @@ def gpu_arm(args):
         gather = ctx.bench_gather(int(desc.table_bytes), gran=32, loads_in_flight=8, n_gathers=1 << 30)
         h2d = ctx.bench_h2d(min(chunk_cap, 64 << 20), repeats=16)
     ext = bool(desc.has_ext) and not os.environ.get("QK_CLASSIC_KERNEL")
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of
-    # `bench.py --kernel-only` on this workload (profiles/r1_count_ext_kernel_ncu_full_summary.csv); null elsewhere
-    traffic = 1249798000 + 194004224 if (args.workload == "config2" and ext and args.chunk_mib == 64) else None
+    kernel_name = "qk_count_ext_kernel" if ext else "qk_count_kernel"
+    traffic, traffic_src = profile_traffic(kernel_name, args.workload, args.chunk_mib)
+    probe_rate = stats["bucket_probes"] / max(1, launches) / (avg_launch_ms * 1e-3)
     roofline = {
-        "bound": "hbm", "kernel": "qk_count_ext_kernel<4,1>" if ext else "qk_count_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "peak_source": peak_src, "traffic": traffic,
-        "traffic_source": "ncu --set full, profiles/r1_count_ext_kernel_ncu_full_summary.csv" if traffic else None,
+        "bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
         "algorithmic_bytes_per_launch": alg_bytes_step / max(1, launches),
-        "bytes_model": "SURVEY 8(d): 32 B bucket sector per emitted k-mer + 4 B counter per hit + 1 B per input byte"
-                       + (" (the extension kernel derives most hits from dictionary order and probes far fewer sectors, so measured DRAM traffic is BELOW this figure)" if ext else ""),
-        "probes_avoided_fraction": (stats.get("ext_verified", 0) / max(1, step_kmers)),
+        "bytes_model": "SURVEY 8(d): 32 B bucket sector per emitted k-mer + 4 B counter per hit + 1 B per input byte",
+        "achieved_issued": achieved_issued, "frac_issued": achieved_issued / peak,
+        "issued_bytes_per_launch": issued_bytes_step / max(1, launches),
+        "issued_model": "bytes the kernel asks for, from its own counters: 32 B x bucket probes issued + 16 B x dictionary-order walks "
+                        "started + 4 B x hits + 1 B x input bytes",
+        "bucket_probes_per_kmer": stats["bucket_probes"] / max(1, step_kmers),
+        "probes_avoided_fraction": 1.0 - stats["bucket_probes"] / max(1, step_kmers),
+        "hits_by_walk_fraction": stats.get("ext_verified", 0) / max(1, step_hits),
         "avg_launch_ms": avg_launch_ms, "launches_per_step": launches,
         "kernel_share_of_step": tm["kernel_ms"] / ms_per_step if world == 1 else None,
         "gather_peak_gbs": gather, "gather_peak_how": f"random 32 B sector loads over a {int(desc.table_bytes) >> 20} MiB table, 8 in flight/thread (qk_bench_gather)",
-        "frac_of_gather_peak": (32 * step_kmers / max(1, launches)) / (avg_launch_ms * 1e-3) / 1e9 / gather,
+        "probe_rate_gps": probe_rate / 1e9,
+        "frac_of_gather_peak": 32 * probe_rate / 1e9 / gather if gather == gather else None,
+        "frac_of_gather_peak_how": "bucket probes issued per second x 32 B / the measured random-sector gather GB/s",
         "h2d_peak_gbs": h2d,
-        "frac_of_h2d_peak_preframed": (n_framed / pre_s / 1e9) / h2d,
+        "frac_of_h2d_peak_preframed": (h_framed_bytes / world / pre_s / 1e9) / h2d if h2d == h2d else None,
     }
 
     base = None
@@ -612,35 +967,41 @@ def gpu_arm(args):
         except Exception as e:  # the baseline must not sink the GPU number
             base = {"value": None, "unit": "k-mers/s", "cores": 0, "kind": "unavailable", "sample": str(e)}
 
-    bases_step = fst["bases"]
+    nan = float("nan")
+    hk = h_kmers if h_kmers is not None else 0
     out = {
         "metric": "k-mers/sec for quicKmer2 count", "value": value, "unit": "k-mers/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic",
+        "value_is": "counting of framed reads already resident in HBM (H2D and record framing excluded); e2e includes both",
         "config": {"workload": args.workload, "desc": w["desc"], "k": int(desc.k), "dict_kmers": n_kmers,
-                   "table_MiB": int(desc.table_bytes) >> 20, "reads_per_gpu": fst["lines"], "kmers_per_step": job_kmers,
+                   "table_MiB": int(desc.table_bytes) >> 20, "reads_per_gpu": data.lines, "kmers_per_step": job_kmers,
                    "hit_fraction": job_hits / max(1, job_kmers), "chunk_MiB": args.chunk_mib,
                    "parallelism": f"reads sharded over {world} GPU(s), dictionary replicated"
                                   + (", NCCL reduce of the counters per step, overlapped with the next step's counting (two counter buffers)" if world > 1 else ""),
                    "l2": "inputs (framed reads + table) exceed the 126 MB L2 every step; no flush needed"
-                         if n_framed + int(desc.table_bytes) > (256 << 20) else "working set fits L2: HBM term does not bind"},
-        "bases_per_s": bases_step * world / (ms_per_step * 1e-3),
-        "e2e": {"value": job_kmers / raw_s, "unit": "k-mers/s", "h2d_bytes_per_step": int(raw_np.size), "d2h_bytes_per_step": 2 * n_kmers + 64,
-                "h2d_gbs": raw_np.size / raw_s / 1e9, "frac_of_h2d_peak": (raw_np.size / raw_s / 1e9) / h2d if h2d == h2d else None,
-                "bases_per_s": bases_step * world / raw_s,
+                         if data.n_framed + int(desc.table_bytes) > (256 << 20) else "working set fits L2: HBM term does not bind",
+                   "note": data.note},
+        "bases_per_s": job_bases / (ms_per_step * 1e-3),
+        "e2e": {"value": hk / raw_s, "unit": "k-mers/s", "h2d_bytes_per_step": h_raw_bytes, "d2h_bytes_per_step": 2 * n_kmers + 64,
+                "h2d_gbs": h_raw_bytes / raw_s / 1e9, "frac_of_h2d_peak": (h_raw_bytes / world / raw_s / 1e9) / h2d if h2d == h2d else None,
+                "bases_per_s": h_bases / raw_s,
                 "path": "raw FASTA/FASTQ bytes in pinned host memory -> qk_count_raw_mem (cut at line ends, H2D, device framing, count kernels) -> qk_finish (uint16 depths D2H)",
-                "steps": e2e_steps, "raw_bytes_per_step": int(raw_np.size)},
-        "e2e_preframed": {"value": job_kmers / pre_s, "unit": "k-mers/s", "h2d_gbs": n_framed / pre_s / 1e9,
+                "steps": e2e_steps, "raw_bytes_per_step": h_raw_bytes, "reads_per_step": data.h_lines * world, "kmers_per_step": hk,
+                "sample": None if not synth else f"the first {data.h_lines} reads of each GPU's stream ({data.h_lines / max(1, data.lines) * 30:.1f}x of its 30x): "
+                                                 "what the host can hold pinned; the rate does not depend on the length of the stream"},
+        "e2e_preframed": {"value": hk / pre_s, "unit": "k-mers/s", "h2d_gbs": h_framed_bytes / pre_s / 1e9,
                           "h2d_ms_per_step": h2d_ms_step,
                           "path": "pre-framed pinned host chunks -> qk_submit (H2D + kernel per chunk) -> qk_finish"},
         "e2e_file": None if file_s is None else {
-            "value": job_kmers / file_s, "unit": "k-mers/s", "file_gbs": raw_np.size / file_s / 1e9, "reader_threads": args.reader_threads,
+            "value": file_kmers / file_s, "unit": "k-mers/s", "file_gbs": file_bytes / file_s / 1e9, "reader_threads": args.reader_threads,
             "path": "reads FILE (page cache) -> qk_count_raw_file_mt (pread into pinned slots, H2D, device framing, count) -> qk_finish"},
         "gpu_launches": launches * args.steps,
+        "parity_ok": parity["ok"], "parity": parity,
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": base,
-        "setup": {"dict_load_build_s": load_s, "dict_bcast_s": bcast_s, "host_frame_s": frame_s,
+        "setup": {"dict_files_s": gen_s, "dict_load_build_s": load_s, "dict_bcast_s": bcast_s, "reads_s": reads_s, "host_frame_s": data.frame_s,
                   "stash_used": int(desc.stash_used), "n_buckets": int(desc.n_buckets)},
     }
     print(json.dumps(out).replace('NaN', 'null'), flush=True)
@@ -656,7 +1017,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS) + sorted(SYNTH_WORKLOADS))
+    ap.add_argument("--reads-scale", type=float, default=1.0, help="GPU-generated workloads: fraction of the workload's reads per GPU (quick runs)")
+    ap.add_argument("--e2e-coverage", type=float, default=8.0, help="GPU-generated workloads: the host legs run over at most this coverage (of 30x) in pinned memory")
+    ap.add_argument("--reference-budget-s", type=float, default=240.0, help="--impl reference: stop starting new steps after this many seconds")
     ap.add_argument("--cache-dir", default=None)
     ap.add_argument("--chunk-mib", type=int, default=64)
     ap.add_argument("--e2e-steps", type=int, default=3)

@@ -162,6 +162,11 @@ int qk_stats(qk_ctx *ctx, uint64_t *total_kmers, uint64_t *hits, uint64_t *lines
 /* How many of the hits were derived from a neighbouring k-mer through the dictionary-order
  * extension arrays instead of a table probe (0 when the dictionary has none, k != 30). */
 int qk_stats_ext(qk_ctx *ctx, uint64_t *verified_by_extension);
+/* What the count kernels actually asked of memory (for the roofline): 32-byte bucket sectors
+ * loaded from the table (one per emitted k-mer without the extension arrays; anchors + positions
+ * the walk could not settle with them), and dictionary-order walks started (each reads four words
+ * of the extension arrays). */
+int qk_stats_probes(qk_ctx *ctx, uint64_t *bucket_probes, uint64_t *walks);
 
 /* Device pointer of the per-ordinal uint32 counters (n_kmers entries), for an NCCL
  * reduce across GPUs; the low 16 bits are the reference's uint16 depth (Q.c:23,291). */

@@ -118,6 +118,7 @@ SIGNATURES = {
     "qk_sync": (C.c_int, [_P]),
     "qk_stats": (C.c_int, [_P, _U64P, _U64P, _U64P]),
     "qk_stats_ext": (C.c_int, [_P, _U64P]),
+    "qk_stats_probes": (C.c_int, [_P, _U64P, _U64P]),
     "qk_counters_device_ptr": (C.c_int, [_P, C.POINTER(_P), _U64P]),
     "qk_reset_counters": (C.c_int, [_P]),
     "qk_reset_counters_async": (C.c_int, [_P]),
@@ -362,7 +363,10 @@ class Context:
         self._check(self._lib.qk_stats(self._h, C.byref(t), C.byref(h), C.byref(l)))
         e = C.c_uint64()
         self._check(self._lib.qk_stats_ext(self._h, C.byref(e)))
-        return {"total_kmers": t.value, "hits": h.value, "lines": l.value, "ext_verified": e.value}
+        p, w = C.c_uint64(), C.c_uint64()
+        self._check(self._lib.qk_stats_probes(self._h, C.byref(p), C.byref(w)))
+        return {"total_kmers": t.value, "hits": h.value, "lines": l.value, "ext_verified": e.value,
+                "bucket_probes": p.value, "walks": w.value}
 
     def timing(self) -> dict:
         k, h, n = C.c_double(), C.c_double(), C.c_uint64()

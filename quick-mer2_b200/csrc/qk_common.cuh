@@ -25,6 +25,7 @@
 #define QK_KEY_BITS 60
 #define QK_BUCKET_ENTRIES 4
 #define QK_FRAME_MAX_CTAS 2048   // CTAs of the device framing passes (per chunk)
+#define QK_STATS_WORDS 8
 
 struct __align__(32) qk_bucket { unsigned long long e[QK_BUCKET_ENTRIES]; };
 struct __align__(16) qk_stash_entry { unsigned long long key; uint32_t ord1; uint32_t pad; };
@@ -77,7 +78,8 @@ struct qk_ctx {
 
     uint32_t *counters;       // n_kmers x u32, indexed by ordinal: the buffer jobs currently count into
     uint32_t *counters_buf[2]; // [0] always allocated with the table; [1] on first qk_counters_select(1)
-    unsigned long long *stats; // device: [0] emitted k-mers, [1] hits
+    unsigned long long *stats; // device: [0] emitted k-mers, [1] hits, [2] hits derived by the dictionary-order walk, [3] micro-benchmark sink,
+                               // [4] bucket probes issued, [5] stash probes, [6] walks started (anchors that hit)
     uint64_t lines;
 
     double kernel_ms, h2d_ms;

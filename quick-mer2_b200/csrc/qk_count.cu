@@ -305,6 +305,7 @@ __global__ void __launch_bounds__(QK_THREADS, 3) qk_count_kernel(const qk_count_
     if (lane == 0) {
         atomicAdd(a.stats + 0, (unsigned long long)n_emit);
         atomicAdd(a.stats + 1, (unsigned long long)n_hit);
+        atomicAdd(a.stats + 4, (unsigned long long)n_emit); // one bucket probe per emitted k-mer
     }
 }
 
@@ -443,7 +444,7 @@ __global__ void __launch_bounds__(QK_THREADS, MINB) qk_count_ext_kernel(const qk
 
     const qk_table_view tv = a.tv;
     const uint32_t ord_mask = tv.ord_bits >= 32 ? 0xFFFFFFFFu : (1u << tv.ord_bits) - 1;
-    uint32_t n_emit = 0, n_hit = 0, n_ext = 0;
+    uint32_t n_emit = 0, n_hit = 0, n_ext = 0, n_probe = 0, n_walk = 0;
     const uint32_t w = lane >> 1, half = lane & 1; // the word and the half of it this lane owns
 
     auto key_at = [&](uint32_t idx, bool *is_fwd) -> uint64_t { // canonical 30-mer ending at position idx of the sub-tile
@@ -508,11 +509,13 @@ __global__ void __launch_bounds__(QK_THREADS, MINB) qk_count_ext_kernel(const qk
         uint32_t a_strand = 0, a_ord1 = 0, verified = 0;
         bool plus = true;
         if (emit) a_ord1 = qk_probe_resolve(tv, ap, abk, ord_mask, &a_strand);
+        n_probe += emit != 0;
         const uint64_t oa = a_ord1 ? a_ord1 - 1 : 0;
         if (a_ord1) {
             const uint32_t nsteps = 15 - ja;
             plus = (a_strand != 0) == a_fwd;
             if (nsteps && (plus || oa >= 15)) {
+                ++n_walk;
                 // read bases of the steps, step i (position ja + i) in bits 2i-1:2i-2
                 uint32_t R = qk_rev16pairs(my_codes) >> (2 * (ja + 1));
                 uint32_t D, Cb;
@@ -554,6 +557,7 @@ __global__ void __launch_bounds__(QK_THREADS, MINB) qk_count_ext_kernel(const qk
         uint32_t todo = emit & ~verified;
         if (emit) todo &= ~(1u << ja);
         const uint32_t cnt = __popc(todo);
+        n_probe += cnt;
         uint32_t incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -612,11 +616,15 @@ __global__ void __launch_bounds__(QK_THREADS, MINB) qk_count_ext_kernel(const qk
         n_emit += __shfl_xor_sync(FULL, n_emit, o);
         n_hit += __shfl_xor_sync(FULL, n_hit, o);
         n_ext += __shfl_xor_sync(FULL, n_ext, o);
+        n_probe += __shfl_xor_sync(FULL, n_probe, o);
+        n_walk += __shfl_xor_sync(FULL, n_walk, o);
     }
     if (lane == 0) {
         atomicAdd(a.stats + 0, (unsigned long long)n_emit);
         atomicAdd(a.stats + 1, (unsigned long long)n_hit);
         atomicAdd(a.stats + 2, (unsigned long long)n_ext);
+        atomicAdd(a.stats + 4, (unsigned long long)n_probe);
+        atomicAdd(a.stats + 6, (unsigned long long)n_walk);
     }
 }
 
@@ -728,7 +736,7 @@ extern "C" int qk_reset_counters(qk_ctx *ctx)
     int rc = qk_sync(ctx);
     if (rc) return rc;
     QK_CUDA(ctx, cudaMemset(ctx->counters, 0, (ctx->desc.n_kmers + 1) * sizeof(uint32_t)));
-    QK_CUDA(ctx, cudaMemset(ctx->stats, 0, 4 * sizeof(unsigned long long)));
+    QK_CUDA(ctx, cudaMemset(ctx->stats, 0, QK_STATS_WORDS * sizeof(unsigned long long)));
     QK_CUDA(ctx, cudaMemset(ctx->frame_stream + 1, 0, 3 * sizeof(unsigned long long))); // totals, not the line state
     QK_CUDA(ctx, cudaDeviceSynchronize()); // the slot streams do not order against stream 0
     ctx->lines = 0;
@@ -768,7 +776,7 @@ extern "C" int qk_reset_counters_async(qk_ctx *ctx)
         QK_CUDA(ctx, cudaStreamWaitEvent(s0, ctx->span_join, 0));
     }
     QK_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, (ctx->desc.n_kmers + 1) * sizeof(uint32_t), s0));
-    QK_CUDA(ctx, cudaMemsetAsync(ctx->stats, 0, 4 * sizeof(unsigned long long), s0));
+    QK_CUDA(ctx, cudaMemsetAsync(ctx->stats, 0, QK_STATS_WORDS * sizeof(unsigned long long), s0));
     QK_CUDA(ctx, cudaMemsetAsync(ctx->frame_stream + 1, 0, 3 * sizeof(unsigned long long), s0));
     QK_CUDA(ctx, cudaEventRecord(ctx->span_join, s0));
     for (uint32_t s = 1; s < ctx->n_slots; ++s) QK_CUDA(ctx, cudaStreamWaitEvent(ctx->slots[s].stream, ctx->span_join, 0));

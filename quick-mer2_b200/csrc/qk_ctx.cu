@@ -79,10 +79,10 @@ extern "C" int qk_ctx_create(qk_ctx **out, int device, uint32_t n_slots, size_t 
     QK_CUDA(ctx, cudaEventCreate(&ctx->span_a));
     QK_CUDA(ctx, cudaEventCreate(&ctx->span_b));
     QK_CUDA(ctx, cudaEventCreateWithFlags(&ctx->span_join, cudaEventDisableTiming));
-    QK_CUDA(ctx, cudaMalloc((void **)&ctx->stats, 4 * sizeof(unsigned long long)));
-    QK_CUDA(ctx, cudaMemset(ctx->stats, 0, 4 * sizeof(unsigned long long)));
-    QK_CUDA(ctx, cudaMalloc((void **)&ctx->frame_stream, 4 * sizeof(unsigned long long)));
-    QK_CUDA(ctx, cudaMemset(ctx->frame_stream, 0, 4 * sizeof(unsigned long long)));
+    QK_CUDA(ctx, cudaMalloc((void **)&ctx->stats, QK_STATS_WORDS * sizeof(unsigned long long)));
+    QK_CUDA(ctx, cudaMemset(ctx->stats, 0, QK_STATS_WORDS * sizeof(unsigned long long)));
+    QK_CUDA(ctx, cudaMalloc((void **)&ctx->frame_stream, QK_STATS_WORDS * sizeof(unsigned long long)));
+    QK_CUDA(ctx, cudaMemset(ctx->frame_stream, 0, QK_STATS_WORDS * sizeof(unsigned long long)));
     QK_CUDA(ctx, cudaMalloc((void **)&ctx->frame_elems, (size_t)n_slots * QK_FRAME_MAX_CTAS * sizeof(uint32_t)));
     ctx->raw_prev_slot = -1;
     return QK_OK;
@@ -221,6 +221,18 @@ extern "C" int qk_stats_ext(qk_ctx *ctx, uint64_t *verified_by_extension)
     unsigned long long h[4];
     QK_CUDA(ctx, cudaMemcpy(h, ctx->stats, sizeof h, cudaMemcpyDeviceToHost));
     *verified_by_extension = h[2];
+    return QK_OK;
+}
+
+extern "C" int qk_stats_probes(qk_ctx *ctx, uint64_t *bucket_probes, uint64_t *walks)
+{
+    if (!ctx) return QK_ERR_ARG;
+    int rc = qk_sync(ctx);
+    if (rc) return rc;
+    unsigned long long h[QK_STATS_WORDS];
+    QK_CUDA(ctx, cudaMemcpy(h, ctx->stats, sizeof h, cudaMemcpyDeviceToHost));
+    if (bucket_probes) *bucket_probes = h[4];
+    if (walks) *walks = h[6];
     return QK_OK;
 }
 

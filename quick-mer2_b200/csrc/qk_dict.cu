@@ -407,7 +407,7 @@ static int qk_alloc_table(qk_ctx *ctx, const qk_table_desc *d)
     QK_CUDA(ctx, cudaMalloc((void **)&ctx->counters_buf[0], (d->n_kmers + 1) * sizeof(uint32_t)));
     ctx->counters = ctx->counters_buf[0];
     QK_CUDA(ctx, cudaMemset(ctx->counters, 0, (d->n_kmers + 1) * sizeof(uint32_t)));
-    QK_CUDA(ctx, cudaMemset(ctx->stats, 0, 4 * sizeof(unsigned long long))); // a new dictionary starts a new count
+    QK_CUDA(ctx, cudaMemset(ctx->stats, 0, QK_STATS_WORDS * sizeof(unsigned long long))); // a new dictionary starts a new count
     QK_CUDA(ctx, cudaMemset(ctx->frame_stream, 0, 4 * sizeof(unsigned long long)));
     QK_CUDA(ctx, cudaDeviceSynchronize()); // the slot streams do not order against stream 0
     ctx->lines = 0;

@@ -165,6 +165,13 @@ int qk_count_main(int argc, char **argv)
     }
     time(&end_time);
     double t2 = now_sec();
+    {   /* Q.c:446: one line per 2^30 k-mers processed.  The device counts them all in seconds, so the
+         * lines are written once the total is known: the same lines, in the same place in the output.
+         * (QK_PROGRESS_SHIFT lowers the 30 for tests.) */
+        const char *e = getenv("QK_PROGRESS_SHIFT");
+        const int shift = e && atoi(e) > 0 && atoi(e) < 63 ? atoi(e) : 30;
+        for (uint64_t g = 1; g <= (total >> shift); ++g) printf("Read %liG kmers\n", (long)g);
+    }
     printf("Counting elapse %u sec, total %lu kmers\n", (unsigned)(end_time - start_time), (unsigned long)total); /* Q.c:481 */
     printf("Pileup finish\nRead chain file %lu entries\n", (unsigned long)hdr.hash_size);                         /* Q.c:483 */
 

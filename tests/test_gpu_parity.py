@@ -68,6 +68,24 @@ def test_cli_is_a_drop_in(case, qk, tmp_path):
     assert total.endswith(f"total {meta['total_kmers']} kmers")
 
 
+def test_cli_progress_lines(qk, tmp_path):
+    """Q.c:446: `Read %liG kmers` once per 2^30 k-mers processed, before `Counting elapse`.  The
+    threshold is lowered (QK_PROGRESS_SHIFT) so that a small input crosses it."""
+    meta = golden_meta("k30_fastq_t3")
+    d = GOLDEN / "k30_fastq_t3"
+    res = qk.run_cli(["count", d / "ref.fa", d / meta["reads"], tmp_path / "p"], env=dict(os.environ, QK_PROGRESS_SHIFT="12"))
+    assert res.returncode == 0, res.stdout + res.stderr
+    lines = res.stdout.splitlines()
+    at = [i for i, l in enumerate(lines) if l.startswith("Counting elapse")][0]
+    n = meta["total_kmers"] >> 12
+    assert n >= 3
+    assert lines[at - n:at] == [f"Read {g}G kmers" for g in range(1, n + 1)]
+    assert not any(l.startswith("Read ") and l.endswith("G kmers") for l in lines[:at - n] + lines[at:])
+    # at the reference's own threshold a small input prints none
+    res = qk.run_cli(["count", d / "ref.fa", d / meta["reads"], tmp_path / "p"])
+    assert not any(l.endswith("G kmers") for l in res.stdout.splitlines())
+
+
 def test_cli_reads_from_a_pipe(qk, oracle, tmp_path):
     """README.md:89-90: samtools | awk | quicKmer2 count ref /dev/fd/0 out.  On a pipe the
     reference's fseek(0) fails and the first line is consumed (Q.c:396)."""
