@@ -102,15 +102,15 @@ WORKLOADS = {
 }
 
 
-HUMAN = dict(n_bases=3_100_000_000, contigs=16, seed=2026, dup_period=120_000, dup_len=22_000, div_ppm=5000, nblock=50_000)
-SMALL = dict(n_bases=40_000_000, contigs=4, seed=2026, dup_period=120_000, dup_len=22_000, div_ppm=5000, nblock=50_000)
+HUMAN = dict(n_bases=3_100_000_000, contigs=16, seed=2026, dup_period=120_000, dup_len=26_000, div_ppm=5000, nblock=50_000)
+SMALL = dict(n_bases=40_000_000, contigs=4, seed=2026, dup_period=120_000, dup_len=26_000, div_ppm=5000, nblock=50_000)
 # GPU-generated workloads (tools/qk_synth_gpu.cu): genome + dictionary made on the device and written as the
 # QM11 files both arms read; reads generated straight into HBM (value) / pinned host memory (e2e) / a
 # sample file (CPU arm).  reads = per GPU.
 SYNTH_WORKLOADS = {
     "config3": dict(genome=HUMAN, dict_dir="human_k30", k=30, slots=1 << 32, ctrl_block=100_000,
                     reads=620_000_000, read_len=150, err_ppm=2000, fastq=True, hifi=False, seed=42, sample_reads=20_700_000,
-                    desc="3.1 Gb synthetic human-scale reference (16 contigs, 18% segmental duplications at 0.5% divergence), k=30, "
+                    desc="3.1 Gb synthetic human-scale reference (16 contigs, 22% segmental duplications at 0.5% divergence), k=30, "
                          "2^32-slot .qm; 30x = 620M x 150bp reads per GPU"),
     "config4": dict(genome=HUMAN, dict_dir="human_k30", k=30, slots=1 << 32, ctrl_block=100_000,
                     reads=5_470_000, read_len=15000, err_ppm=1000, fastq=False, hifi=True, seed=42, sample_reads=150_000,

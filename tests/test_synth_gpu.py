@@ -110,7 +110,8 @@ def test_gpu_genome_and_reads(qk, oracle, tmp_path):
             ctx.count_file(tmp_path / "r.fq")
             st = ctx.stats()
             assert np.array_equal(ctx.finish(), want)
-            assert st["total_kmers"] == ost["total_kmers"] == n * 121 and st["hits"] == ost["hits"] > 0.5 * n * 121
+            # (reads that overlap the N block emit fewer than 121 k-mers)
+            assert 0.98 * n * 121 < st["total_kmers"] == ost["total_kmers"] <= n * 121 and st["hits"] == ost["hits"] > 0.5 * n * 121
 
         # HiFi-like records: caller-given lengths, some beyond the 65,536 run-counter wrap
         lens = np.array([1000, 70000, 99998, 15000, 133333], dtype=np.uint32)
