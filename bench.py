@@ -773,9 +773,19 @@ def gpu_arm(args):
         for i, (o, sz) in enumerate(zip(data.h_offs, data.h_sizes)):
             ctx.submit_host(data.host_base + o, sz, slot=i % ctx.n_slots)
 
-    def job_raw():
+    cpus = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    framer_threads = args.framer_threads or max(1, cpus // max(1, world))
+    host_framing = args.framer == "host" or (args.framer == "auto" and framer_threads >= 6)
+
+    def job_raw_device():
         ctx.reset()
         ctx.count_mem(data.raw.data_ptr(), data.raw_bytes)
+
+    def job_raw_host():
+        ctx.reset()
+        ctx.count_mem_mt(data.raw.data_ptr(), data.raw_bytes, threads=framer_threads)
+
+    job_raw = job_raw_host if host_framing else job_raw_device
 
     def finish_step():
         """N > 1: combine the per-GPU counters on rank 0 (the one exchange step of the path)."""
@@ -895,6 +905,10 @@ def gpu_arm(args):
         h2d_ms_step = ctx.timing()["h2d_ms"]
         raw_s, h_kmers_raw = timed_host(job_raw, e2e_steps, 1)
         assert h_kmers_raw == h_kmers, (h_kmers_raw, h_kmers)
+        other_s = None
+        if world == 1:                              # the other framing policy, for comparison
+            other_s, k2 = timed_host(job_raw_device if host_framing else job_raw_host, e2e_steps, 1)
+            assert k2 == h_kmers, (k2, h_kmers)
     (h_raw_bytes, h_framed_bytes, h_bases) = all_sum([data.raw_bytes, data.h_framed_bytes, data.h_bases])
 
     # ---- e2e from a FILE (page cache): reader threads pread() into the pinned slots ---------
@@ -909,8 +923,14 @@ def gpu_arm(args):
         file_s, file_kmers = timed_host(job_file, 2, 1)
         file_bytes = os.path.getsize(file_reads)
 
+    framer_gbs = None
+    if rank == 0 and not args.kernel_only:
+        framer_gbs = qk.bench_framer(data.raw.data_ptr(), min(data.raw_bytes, 4 << 30), threads=framer_threads, repeats=2)
     if synth:
         data.free_host()
+        data.devbuf.free()                          # the micro-benchmarks below need the HBM
+    else:
+        data.dev = None
     if rank != 0:
         ctx.close()
         if world > 1:
@@ -931,6 +951,7 @@ def gpu_arm(args):
     if args.kernel_only:
         gather = h2d = float("nan")
     else:
+        torch.cuda.empty_cache()
         gather = ctx.bench_gather(int(desc.table_bytes), gran=32, loads_in_flight=8, n_gathers=1 << 30)
         h2d = ctx.bench_h2d(min(chunk_cap, 64 << 20), repeats=16)
     ext = bool(desc.has_ext) and not os.environ.get("QK_CLASSIC_KERNEL")
@@ -983,10 +1004,20 @@ def gpu_arm(args):
                          if data.n_framed + int(desc.table_bytes) > (256 << 20) else "working set fits L2: HBM term does not bind",
                    "note": data.note},
         "bases_per_s": job_bases / (ms_per_step * 1e-3),
-        "e2e": {"value": hk / raw_s, "unit": "k-mers/s", "h2d_bytes_per_step": h_raw_bytes, "d2h_bytes_per_step": 2 * n_kmers + 64,
-                "h2d_gbs": h_raw_bytes / raw_s / 1e9, "frac_of_h2d_peak": (h_raw_bytes / world / raw_s / 1e9) / h2d if h2d == h2d else None,
+        "e2e": {"value": hk / raw_s, "unit": "k-mers/s", "h2d_bytes_per_step": h_framed_bytes if host_framing else h_raw_bytes,
+                "d2h_bytes_per_step": 2 * n_kmers + 64,
+                "h2d_gbs": (h_framed_bytes if host_framing else h_raw_bytes) / raw_s / 1e9,
+                "frac_of_h2d_peak": ((h_framed_bytes if host_framing else h_raw_bytes) / world / raw_s / 1e9) / h2d if h2d == h2d else None,
                 "bases_per_s": h_bases / raw_s,
-                "path": "raw FASTA/FASTQ bytes in pinned host memory -> qk_count_raw_mem (cut at line ends, H2D, device framing, count kernels) -> qk_finish (uint16 depths D2H)",
+                "framing": f"host, {framer_threads} threads per GPU" if host_framing else "device",
+                "host_raw_gbs": h_raw_bytes / raw_s / 1e9,
+                "host_framer_alone_gbs": None if framer_gbs is None else {"raw_in": framer_gbs[0], "framed_out": framer_gbs[1], "threads": framer_threads},
+                "other_framing": None if args.kernel_only or other_s is None else {
+                    "framing": "device" if host_framing else f"host, {framer_threads} threads", "value": hk / other_s,
+                    "h2d_bytes_per_step": h_raw_bytes if host_framing else h_framed_bytes},
+                "path": ("raw FASTA/FASTQ bytes in host memory -> qk_count_mem_mt (host threads frame blocks in parallel, sequence lines only into the pinned slots, H2D, count kernels) -> qk_finish (uint16 depths D2H)"
+                         if host_framing else
+                         "raw FASTA/FASTQ bytes in pinned host memory -> qk_count_raw_mem (cut at line ends, H2D, device framing, count kernels) -> qk_finish (uint16 depths D2H)"),
                 "steps": e2e_steps, "raw_bytes_per_step": h_raw_bytes, "reads_per_step": data.h_lines * world, "kmers_per_step": hk,
                 "sample": None if not synth else f"the first {data.h_lines} reads of each GPU's stream ({data.h_lines / max(1, data.lines) * 30:.1f}x of its 30x): "
                                                  "what the host can hold pinned; the rate does not depend on the length of the stream"},
@@ -1020,6 +1051,10 @@ def main():
     ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS) + sorted(SYNTH_WORKLOADS))
     ap.add_argument("--reads-scale", type=float, default=1.0, help="GPU-generated workloads: fraction of the workload's reads per GPU (quick runs)")
     ap.add_argument("--e2e-coverage", type=float, default=8.0, help="GPU-generated workloads: the host legs run over at most this coverage (of 30x) in pinned memory")
+    ap.add_argument("--framer", default="auto", choices=["auto", "host", "device"],
+                    help="e2e leg: record framing by host threads (ships sequence lines only) or on the device (ships the raw stream); "
+                         "auto = host when there are >= 6 host CPUs per GPU")
+    ap.add_argument("--framer-threads", type=int, default=0, help="host framer threads per GPU (0 = host CPUs / GPUs)")
     ap.add_argument("--reference-budget-s", type=float, default=240.0, help="--impl reference: stop starting new steps after this many seconds")
     ap.add_argument("--cache-dir", default=None)
     ap.add_argument("--chunk-mib", type=int, default=64)

@@ -111,6 +111,36 @@ int qk_count_raw_file(qk_ctx *ctx, const char *reads_path, qk_framer_stats *st);
  * error on this path.  Pipes fall back to qk_count_raw_fd. */
 int qk_count_raw_file_mt(qk_ctx *ctx, const char *reads_path, uint32_t threads, qk_framer_stats *st);
 
+/* ---- all host cores frame, any GPU counts (host/qk_framer_mt.c) ---------------------------------
+ * The framing rules above applied by `threads` workers (0 = QK_FRAMER_THREADS or every online
+ * CPU) to blocks of the input in parallel; only the sequence lines are copied into the pinned
+ * slot buffers, so FASTQ crosses the host link at ~1.25 instead of ~2.6 bytes per k-mer.  The
+ * framed chunks go to whichever of the n_ctx contexts (same slot count and capacity; one per
+ * GPU; same dictionary) has a slot free first.  Same result, byte for byte, as qk_count_framer /
+ * qk_count_raw_mem.  qk_count_file_mt maps a regular file (the page cache is the input buffer);
+ * pipes and gzip files are counted by ctxs[0] through the sequential stream path. */
+int qk_count_mem_mt(qk_ctx *const *ctxs, uint32_t n_ctx, const uint8_t *data, size_t n, int seekable, uint32_t threads,
+                    qk_framer_stats *st);
+/* The framer alone, with the consumer of the framed chunks as a parameter: n_ctx consumers with
+ * n_slots buffers of `cap` bytes each.  The framer fills buffer(c, s) -- after ready(c, s)
+ * returned 1 or wait(c, s) returned 0 for a buffer it has submitted before -- and hands it over
+ * with submit(c, s, seq, n_bytes, n_lines), seq = ordinal of the chunk in the framed stream; submit
+ * is called from worker threads, one call at a time per consumer c. */
+typedef struct qk_chunk_sink {
+    void *user;
+    uint32_t n_ctx, n_slots;
+    size_t cap;
+    uint8_t *(*buffer)(void *user, uint32_t c, uint32_t s);
+    int (*ready)(void *user, uint32_t c, uint32_t s);
+    int (*wait)(void *user, uint32_t c, uint32_t s);
+    int (*submit)(void *user, uint32_t c, uint32_t s, uint64_t seq, size_t n_bytes, uint32_t n_lines);
+} qk_chunk_sink;
+int qk_frame_mem_mt(const qk_chunk_sink *sink, const uint8_t *data, size_t n, int seekable, uint32_t threads, qk_framer_stats *st);
+/* Measurement: the framer alone over `data`, chunks discarded; GB/s of raw input consumed and of
+ * framed output produced (the host-side term of the end-to-end roofline). */
+int qk_bench_framer(const uint8_t *data, size_t n, uint32_t threads, int repeats, double *raw_gbs, double *framed_gbs);
+int qk_count_file_mt(qk_ctx *const *ctxs, uint32_t n_ctx, const char *reads_path, uint32_t threads, qk_framer_stats *st);
+
 /* ---- one reads file, several GPUs ---------------------------------------------------------
  * qk_shard_bounds: the line-aligned byte range [begin, end) of shard `rank` of `world`
  * (regular files only).  qk_count_raw_range counts that range on one context, starting the

@@ -153,6 +153,8 @@ int qk_host_is_pinned(const void *p);
 void *qk_slot_stream(qk_ctx *ctx, uint32_t slot);
 /* Block until the host buffer last submitted on `slot` may be overwritten. */
 int qk_wait_slot(qk_ctx *ctx, uint32_t slot);
+/* The same without blocking: 1 = may be overwritten, 0 = its copy is still in flight, < 0 = -QK_ERR_*. */
+int qk_slot_ready(qk_ctx *ctx, uint32_t slot);
 /* Block until every enqueued chunk has been counted. */
 int qk_sync(qk_ctx *ctx);
 

@@ -115,6 +115,7 @@ SIGNATURES = {
     "qk_raw_stats": (C.c_int, [_P, _U64P, _U64P, _U64P]),
     "qk_host_is_pinned": (C.c_int, [_P]),
     "qk_wait_slot": (C.c_int, [_P, C.c_uint32]),
+    "qk_slot_ready": (C.c_int, [_P, C.c_uint32]),
     "qk_sync": (C.c_int, [_P]),
     "qk_stats": (C.c_int, [_P, _U64P, _U64P, _U64P]),
     "qk_stats_ext": (C.c_int, [_P, _U64P]),
@@ -164,6 +165,10 @@ SIGNATURES = {
     "qk_count_raw_mem": (C.c_int, [_P, _P, C.c_size_t, C.c_int, C.POINTER(FramerStats)]),
     "qk_count_raw_fd": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(FramerStats)]),
     "qk_count_raw_file": (C.c_int, [_P, C.c_char_p, C.POINTER(FramerStats)]),
+    "qk_frame_mem_mt": (C.c_int, [_P, _P, C.c_size_t, C.c_int, C.c_uint32, C.POINTER(FramerStats)]),
+    "qk_bench_framer": (C.c_int, [_P, C.c_size_t, C.c_uint32, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "qk_count_mem_mt": (C.c_int, [C.POINTER(_P), C.c_uint32, _P, C.c_size_t, C.c_int, C.c_uint32, C.POINTER(FramerStats)]),
+    "qk_count_file_mt": (C.c_int, [C.POINTER(_P), C.c_uint32, C.c_char_p, C.c_uint32, C.POINTER(FramerStats)]),
     "qk_shard_bounds": (C.c_int, [C.c_char_p, C.c_uint32, C.c_uint32, _U64P, _U64P]),
     "qk_fastq_state_guess": (C.c_int, [_P, C.c_size_t, C.POINTER(C.c_uint32)]),
     "qk_count_raw_range": (C.c_int, [_P, C.c_char_p, C.c_uint64, C.c_uint64, C.c_int, C.c_uint32, C.POINTER(FramerStats),
@@ -425,6 +430,25 @@ class Context:
             self._lib.qk_framer_close(fr)
         return st.as_dict()
 
+    def count_mem_mt(self, host_ptr: int, n_bytes: int, seekable: bool = True, threads: int = 0, peers=()) -> dict:
+        """Count raw FASTA/FASTQ bytes at a host address with the framing done by `threads` host workers
+        (only sequence lines cross the host link); `peers` = further contexts (other GPUs, same
+        dictionary and slot geometry) that take chunks from the same queue."""
+        st = FramerStats()
+        hs = (C.c_void_p * (1 + len(peers)))(self._h, *[p._h for p in peers])
+        self._check(self._lib.qk_count_mem_mt(hs, 1 + len(peers), host_ptr, n_bytes, int(seekable), threads, C.byref(st)))
+        return st.as_dict()
+
+    def count_file_mt(self, reads_path, threads: int = 0, peers=()) -> dict:
+        """The same for a reads file (mapped; pipes and gzip fall back to the sequential stream path)."""
+        st = FramerStats()
+        hs = (C.c_void_p * (1 + len(peers)))(self._h, *[p._h for p in peers])
+        rc = self._lib.qk_count_file_mt(hs, 1 + len(peers), os.fsencode(str(reads_path)), threads, C.byref(st))
+        if rc == 6:
+            raise QkError(rc, f"cannot read {reads_path}")
+        self._check(rc)
+        return st.as_dict()
+
     def count_range(self, reads_path, begin: int, end: int, fastq: bool, line_state: int):
         """Count bytes [begin, end) of a reads file starting in `line_state`; returns (stats, final state)."""
         st, fin = FramerStats(), C.c_uint32()
@@ -507,6 +531,56 @@ def frame(data: bytes, seekable: bool = True, chunk_capacity: int = 1 << 20, wit
     finally:
         L.qk_framer_close(fr)
     return (chunks, offsets, st.as_dict()) if with_offsets else (chunks, st.as_dict())
+
+
+class ChunkSink(C.Structure):
+    """struct qk_chunk_sink (include/qk_host.h)."""
+    BUFFER = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32)
+    READY = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_uint32)
+    SUBMIT = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_size_t, C.c_uint32)
+    _fields_ = [("user", C.c_void_p), ("n_ctx", C.c_uint32), ("n_slots", C.c_uint32), ("cap", C.c_size_t),
+                ("buffer", BUFFER), ("ready", READY), ("wait", READY), ("submit", SUBMIT)]
+
+
+def frame_mt(data: bytes, seekable: bool = True, threads: int = 4, n_ctx: int = 1, n_slots: int = 3, cap: int = 1 << 20,
+             busy_every: int = 0):
+    """Host-only: the multi-threaded framer (qk_frame_mem_mt) into Python-owned buffers.  Returns
+    (chunks in stream order, per-chunk (consumer, lines), stats).  busy_every > 0 makes ready()
+    answer "busy" now and then, as a GPU whose copy is still in flight would."""
+    import threading
+    L = lib()
+    buf = np.frombuffer(data, dtype=np.uint8) if len(data) else np.zeros(0, dtype=np.uint8)
+    bufs = [[np.zeros(cap, dtype=np.uint8) for _ in range(n_slots)] for _ in range(n_ctx)]
+    got, lock, calls = {}, threading.Lock(), [0]
+
+    def ready(_u, c, s):
+        with lock:
+            calls[0] += 1
+            return 0 if busy_every and calls[0] % busy_every == 0 else 1
+
+    def submit(_u, c, s, seq, n_bytes, n_lines):
+        with lock:
+            got[seq] = (bufs[c][s][:n_bytes].tobytes(), c, n_lines)
+        return 0
+
+    sink = ChunkSink(None, n_ctx, n_slots, cap, ChunkSink.BUFFER(lambda _u, c, s: bufs[c][s].ctypes.data), ChunkSink.READY(ready),
+                     ChunkSink.READY(lambda _u, c, s: 0), ChunkSink.SUBMIT(submit))
+    st = FramerStats()
+    rc = L.qk_frame_mem_mt(C.byref(sink), _np_ptr(buf), buf.size, int(seekable), threads, C.byref(st))
+    if rc:
+        raise QkError(rc, "qk_frame_mem_mt")
+    order = sorted(got)
+    assert order == list(range(len(order))), order
+    return [got[i][0] for i in order], [(got[i][1], got[i][2]) for i in order], st.as_dict()
+
+
+def bench_framer(host_ptr: int, n_bytes: int, threads: int = 0, repeats: int = 3):
+    """GB/s (raw in, framed out) of the multi-threaded host framer alone."""
+    a, b = C.c_double(), C.c_double()
+    rc = lib().qk_bench_framer(host_ptr, n_bytes, threads, repeats, C.byref(a), C.byref(b))
+    if rc:
+        raise QkError(rc, "qk_bench_framer")
+    return a.value, b.value
 
 
 def count(ref_prefix, reads_path, out_prefix, threads: int = 0, device: int = 0, host_framer: bool = False,

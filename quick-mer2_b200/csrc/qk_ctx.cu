@@ -185,8 +185,20 @@ extern "C" void *qk_slot_stream(qk_ctx *ctx, uint32_t slot)
 extern "C" int qk_wait_slot(qk_ctx *ctx, uint32_t slot)
 {
     if (!ctx || slot >= ctx->n_slots) return QK_ERR_ARG;
+    // reader / framer threads call this: they have no current device of their own
+    QK_CUDA(ctx, cudaSetDevice(ctx->device));
     QK_CUDA(ctx, cudaEventSynchronize(ctx->slots[slot].h2d_done));
     return QK_OK;
+}
+
+extern "C" int qk_slot_ready(qk_ctx *ctx, uint32_t slot)
+{
+    if (!ctx || slot >= ctx->n_slots) return -QK_ERR_ARG;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) { cudaGetLastError(); return -QK_ERR_CUDA; }
+    const cudaError_t e = cudaEventQuery(ctx->slots[slot].h2d_done);
+    if (e == cudaSuccess) return 1;
+    if (e == cudaErrorNotReady) { cudaGetLastError(); return 0; }
+    return -qk_cuda_fail(ctx, e, "cudaEventQuery");
 }
 
 extern "C" int qk_sync(qk_ctx *ctx)

@@ -21,7 +21,7 @@ static void help_count(void)
 {
     puts("\nquicKmer2 count [Options] ref.fa sample.fast[a/q] Out_prefix\n\nOptions:");
     puts("-h\t\tShow this help information");
-    puts("-t [num]\tNumber of threads reading the input into pinned memory (counting runs on the GPU)");
+    puts("-t [num]\tNumber of host threads framing / reading the input into pinned memory (counting runs on the GPU)");
     puts("-g [list]\tCUDA device index, or a comma-separated list to shard the reads over several GPUs (default 0)");
 }
 
@@ -147,7 +147,18 @@ int qk_count_main(int argc, char **argv)
         rc = qk_count_raw_fd(ctx, pipe_fd, 0, &st);      /* a pipe feeds one GPU */
         close(pipe_fd);
     } else {
-        rc = qk_count_file_multi(m, reads, threads, &st); /* -t N: reader threads per GPU (0 = default) */
+        /* Who frames?  With enough host cores per GPU the host does (all cores, sequence lines only over
+         * the link, chunks to whichever GPU is free: host/qk_framer_mt.c); otherwise the raw stream is
+         * shipped and the device frames it (csrc/qk_frame.cu).  QK_FRAMER=host|device overrides.
+         * -t N: framer threads in all / reader threads per GPU (0 = default). */
+        const char *pol = getenv("QK_FRAMER");
+        const long cpus = sysconf(_SC_NPROCESSORS_ONLN);
+        const int by_host = pol ? !strcmp(pol, "host") : cpus / (long)n_dev >= 6;
+        if (by_host) {
+            qk_ctx *ctxs[QK_HOST_MAX_SLOTS];
+            for (uint32_t i = 0; i < n_dev; ++i) ctxs[i] = qk_multi_ctx(m, i);
+            rc = qk_count_file_mt(ctxs, n_dev, reads, threads, &st);
+        } else rc = qk_count_file_multi(m, reads, threads, &st);
     }
     uint64_t total = 0, hits = 0;
     for (uint32_t i = 0; !rc && i < n_dev; ++i) {

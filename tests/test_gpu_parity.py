@@ -134,6 +134,54 @@ def test_gzip_input(qk, tmp_path):
     assert res.returncode == 1 and "Counting failed" in res.stdout                # a truncated file is an error, not a short count
 
 
+@pytest.mark.parametrize("case", golden_cases())
+def test_golden_with_the_multithreaded_host_framer(case, qk, tmp_path):
+    """qk_count_file_mt / qk_count_mem_mt: host threads frame blocks of the input in parallel and ship only
+    the sequence lines -- same .bin as the reference wrote, from a file (mapped), from memory, in pipe
+    mode, with small chunks and few slots."""
+    meta = golden_meta(case)
+    d = GOLDEN / case
+    want = np.fromfile(d / "expect.bin", dtype=np.uint16)
+    raw = (d / meta["reads"]).read_bytes()
+    buf = np.frombuffer(raw, dtype=np.uint8)
+    for n_slots, cap, threads in ((2, 200000, 5), (4, 4 << 20, 16)):
+        with qk.Context(device=0, n_slots=n_slots, chunk_capacity=cap) as ctx:
+            ctx.load_dictionary(d / "ref.fa.qm")
+            st = ctx.count_file_mt(d / meta["reads"], threads=threads)
+            assert np.array_equal(ctx.finish(), want)
+            assert ctx.stats()["total_kmers"] == meta["total_kmers"]
+            ctx.reset()
+            st2 = ctx.count_mem_mt(buf.ctypes.data, buf.size, seekable=True, threads=threads)
+            assert np.array_equal(ctx.finish(), want) and st2 == st
+    # both framing policies of the command
+    for pol in ("host", "device"):
+        res = qk.run_cli(["count", "-t", "3", d / "ref.fa", d / meta["reads"], tmp_path / pol], env=dict(os.environ, QK_FRAMER=pol))
+        assert res.returncode == 0, res.stdout + res.stderr
+        assert (tmp_path / f"{pol}.bin").read_bytes() == (d / "expect.bin").read_bytes()
+
+
+def test_mt_host_framer_feeds_several_gpus(qk, mid_dict, oracle, synth, tmp_path):
+    """One queue of framed chunks, several GPUs taking from it; the sum of their counters is the count."""
+    n = qk.lib().qk_device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs (gpurun --gpus 2)")
+    reads = tmp_path / "r.fq"
+    synth("reads", "--ref", mid_dict / "ref.fa", "--out", reads, "--n", 300000, "--len", 150, "--seed", 77, "--fastq", "--rand-qual")
+    want, ost = oracle.count_bin(mid_dict / "ref.fa.qm", reads)
+    ctxs = [qk.Context(device=i, n_slots=3, chunk_capacity=2 << 20) for i in range(min(n, 4))]
+    try:
+        for c in ctxs:
+            c.load_dictionary(mid_dict / "ref.fa.qm")
+        st = ctxs[0].count_file_mt(reads, threads=8, peers=ctxs[1:])
+        per = [c.counters().astype(np.uint64) for c in ctxs]
+        assert all(p.sum() > 0 for p in per)                      # every GPU took chunks
+        assert np.array_equal((sum(per) & 0xFFFF).astype(np.uint16), want)
+        assert sum(c.stats()["total_kmers"] for c in ctxs) == ost["total_kmers"] and st["lines"] == ost["lines"]
+    finally:
+        for c in ctxs:
+            c.close()
+
+
 # ------------------------------------------------------------------ chunking / tiling ------
 @pytest.mark.parametrize("case", ["k30_fasta_t0", "k30_long_lines", "k12_fasta", "k31_fasta"])
 def test_chunk_boundaries_do_not_matter(case, qk, oracle, gpu_ctx):
@@ -461,8 +509,9 @@ def _n_gpus(qk):
     return qk.lib().qk_device_count()
 
 
+@pytest.mark.parametrize("framer", ["host", "device"])
 @pytest.mark.parametrize("kind", ["fastq", "fasta", "fastq_out_of_phase", "golden"])
-def test_cli_on_several_gpus(kind, mid_dict, qk, oracle, synth, tmp_path):
+def test_cli_on_several_gpus(kind, framer, mid_dict, qk, oracle, synth, tmp_path):
     """`quicKmer2_b200 count -g 0,1[,2,3]`: one process, NCCL broadcast of the dictionary, one
     shard per GPU, NCCL reduce of the counters -- same .bin / .txt as one GPU and the reference."""
     n = _n_gpus(qk)
@@ -484,7 +533,8 @@ def test_cli_on_several_gpus(kind, mid_dict, qk, oracle, synth, tmp_path):
             reads.write_bytes(data[:cut] + b"@odd\n>not a read\n+\nIIII\n" + data[cut:])
         oracle.count(ref, reads, tmp_path / "want")
         want_bin, want_txt = (tmp_path / "want.bin").read_bytes(), (tmp_path / "want.txt").read_bytes()
-    res = qk.run_cli(["count", "-t", "4", "-g", gpus, ref, reads, tmp_path / "multi"])
+    # framer = host: all host cores frame, chunks go to whichever GPU is free; device: one raw shard per GPU
+    res = qk.run_cli(["count", "-t", "4", "-g", gpus, ref, reads, tmp_path / "multi"], env=dict(os.environ, QK_FRAMER=framer))
     assert res.returncode == 0, res.stdout + res.stderr
     assert (tmp_path / "multi.bin").read_bytes() == want_bin
     assert (tmp_path / "multi.txt").read_bytes() == want_txt

@@ -359,3 +359,58 @@ def test_host_framer_on_malformed_streams(seed, fastq_like, qk, oracle, tmp_path
     else:
         (tmp_path / "t.txt").write_text(text[text.index("\n") + 1:], newline="")
         assert piped == oracle.frame_file(tmp_path / "t.txt")[0]
+
+
+# ---------------------------------------------------------------------------- multi-threaded framer
+@pytest.mark.parametrize("fastq_like", [True, False])
+@pytest.mark.parametrize("seed", range(3))
+def test_mt_framer_on_malformed_streams(seed, fastq_like, qk, oracle, tmp_path):
+    """qk_frame_mem_mt (all host cores, blocks framed in parallel, state handed from block to block)
+    produces the oracle's framed stream byte for byte -- whatever the thread count, the block size
+    (it follows the chunk capacity), the number of consumers and their back-pressure."""
+    from conftest import weird_stream
+    rng = np.random.default_rng(900 + seed)
+    seq = "".join(rng.choice(list("ACGTacgtN"), size=5000))
+    text = weird_stream(rng, seq, fastq_like, 6000)
+    (tmp_path / "w.txt").write_text(text, newline="")
+    want, ost = oracle.frame_file(tmp_path / "w.txt")
+    for threads, n_ctx, n_slots, cap, busy in ((1, 1, 2, 200000, 0), (4, 1, 3, 200000, 3), (7, 3, 2, 300000, 2), (3, 2, 4, 1 << 20, 0)):
+        chunks, who, st = qk.frame_mt(text.encode(), seekable=True, threads=threads, n_ctx=n_ctx, n_slots=n_slots, cap=cap, busy_every=busy)
+        assert b"".join(chunks) == want, (threads, n_ctx, cap)
+        assert (st["lines"], st["bases"], st["fastq"], st["raw_bytes"]) == (ost["lines"], ost["bases"], ost["fastq"], len(text.encode()))
+        assert all(len(c) <= cap and c.endswith(b"\n") for c in chunks)
+        assert sum(l for _, l in who) == ost["lines"]
+        if n_ctx > 1 and len(chunks) >= 2 * n_ctx:
+            assert len({c for c, _ in who}) == n_ctx       # every consumer got chunks
+    # a pipe loses the first line in FASTA mode only (Q.c:395-396)
+    piped = b"".join(qk.frame_mt(text.encode(), seekable=False, threads=3, cap=200000)[0])
+    assert piped == b"".join(qk.frame(text.encode(), seekable=False, chunk_capacity=200000)[0])   # (pinned to the oracle above)
+    if fastq_like:
+        assert piped == want
+
+
+def test_mt_framer_edges(qk):
+    """Empty input, no newline at all, unterminated last line (T9), lines that span several blocks, lines of
+    the maximum length, and the scalar scan (QK_NO_AVX512) against the single-threaded framer."""
+    rng = np.random.default_rng(77)
+    base = lambda n: bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=n))
+    cases = [b"", b"ACGT", b"\n", b"\n\n\n", b">h\nACGT\nAC", b"@r\n" + base(150) + b"\n+\n" + b"I" * 150,
+             b">x\n" + base(99998) + b"\n>y\n" + base(70000) + b"\n" + base(30) + b"\n",
+             b"".join(b">r%d\n" % i + base(int(rng.integers(0, 4000))) + b"\n" for i in range(800)),
+             b"".join(b"@r%d\n" % i + base(150) + b"\n+\n" + bytes(rng.integers(33, 75, size=150, dtype=np.uint8)) + b"\n" for i in range(3000))]
+    for data in cases:
+        ref_chunks, rst = qk.frame(data, seekable=True, chunk_capacity=400000)
+        for env in ({}, {"QK_NO_AVX512": "1"}):
+            os.environ.update(env)
+            try:
+                for threads in (1, 5):
+                    chunks, _, st = qk.frame_mt(data, seekable=True, threads=threads, cap=400000)
+                    assert b"".join(chunks) == b"".join(ref_chunks)
+                    assert {k: st[k] for k in ("lines", "bases", "unterminated", "long_lines", "fastq")} == \
+                           {k: rst[k] for k in ("lines", "bases", "unterminated", "long_lines", "fastq")}
+            finally:
+                for k in env:
+                    del os.environ[k]
+    # a line longer than a chunk is an error, not a hang
+    with pytest.raises(qk.QkError):
+        qk.frame_mt(b">x\n" + base(300000) + b"\n", threads=2, cap=200000)

@@ -695,7 +695,45 @@ __device__ __forceinline__ uint8_t qs_record_byte(const uint8_t *__restrict__ se
     return b < pad_len ? 'I' : '\n';
 }
 
-// fixed-length reads: a warp per read, lanes stride over the record's bytes
+// The bytes of one record, written by `nthr` cooperating threads (thread t of them): the bases four at a
+// time (one hash decides the substitutions of four bases), the rest byte by byte.
+__device__ __forceinline__ void qs_write_record(const uint8_t *__restrict__ seq, const qs_reads_params &rp, uint64_t i, uint64_t at,
+                                                uint32_t L, uint32_t pad_len, uint8_t *__restrict__ dst, uint32_t t, uint32_t nthr)
+{
+    const int format = rp.format;
+    const uint32_t hdr = format ? 13u : 0u;
+    for (uint32_t b = t; b < hdr; b += nthr) dst[b] = qs_record_byte(seq, rp, i, at, L, pad_len, b);
+    uint8_t *sq = dst + hdr;
+    const bool rc = (i & 1) != 0;
+    for (uint32_t g = t; 4 * g < pad_len; g += nthr) {
+        const uint64_t h = rp.err_threshold ? qs_hash(rp.seed, i, 16 + g) : ~0ull;
+#pragma unroll
+        for (uint32_t u4 = 0; u4 < 4; ++u4) {
+            const uint32_t j = 4 * g + u4;
+            if (j >= pad_len) break;
+            uint8_t c = 'N';
+            if (j < L) {
+                if (rc) {
+                    c = seq[at + L - 1 - j];
+                    c = c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : c;
+                } else c = seq[at + j];
+                const uint32_t u = (uint32_t)(h >> (16 * u4)) & 0xFFFFu;
+                if (rp.err_threshold && c != 'N' && (u >> 2) < rp.err_threshold) {
+                    const uint32_t code = (c >> 1) & 3;
+                    c = "ACTG"[(code + 1 + (uint32_t)(qs_hash(rp.seed ^ 0x5EEDull, i, j) % 3)) & 3];
+                }
+            }
+            sq[j] = c;
+        }
+    }
+    if (t == 0) sq[pad_len] = '\n';
+    if (format == 2) {
+        uint8_t *q = sq + pad_len + 1;
+        for (uint32_t b = t; b < pad_len + 3; b += nthr) q[b] = b == 0 ? '+' : b == 1 ? '\n' : b == pad_len + 2 ? '\n' : 'I';
+    }
+}
+
+// fixed-length reads: a warp per read
 __global__ void qs_reads_fixed_kernel(const uint8_t *__restrict__ seq, qs_contigs ct, qs_reads_params rp, uint8_t *__restrict__ out)
 {
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -703,11 +741,12 @@ __global__ void qs_reads_fixed_kernel(const uint8_t *__restrict__ seq, qs_contig
     const uint64_t rec = qs_record_bytes(rp.len, rp.format);
     for (uint64_t r = warp; r < rp.n_reads; r += n_warps) {
         const uint64_t i = rp.first_read + r;
-        uint64_t at;
-        uint32_t L;
-        qs_read_place(ct, rp.genome_n, rp.seed, i, rp.len, &at, &L);
-        uint8_t *dst = out + r * rec;
-        for (uint64_t b = lane; b < rec; b += 32) dst[b] = qs_record_byte(seq, rp, i, at, L, rp.len, b);
+        uint64_t at = 0;
+        uint32_t L = 0;
+        if (lane == 0) qs_read_place(ct, rp.genome_n, rp.seed, i, rp.len, &at, &L);
+        at = __shfl_sync(0xffffffffu, at, 0);
+        L = __shfl_sync(0xffffffffu, L, 0);
+        qs_write_record(seq, rp, i, at, L, rp.len, out + r * rec, lane, 32);
     }
 }
 
@@ -720,9 +759,7 @@ __global__ void qs_reads_var_kernel(const uint8_t *__restrict__ seq, qs_contigs 
         uint64_t at;
         uint32_t L;
         qs_read_place(ct, rp.genome_n, rp.seed, i, lens[r], &at, &L);
-        const uint64_t rec = qs_record_bytes(lens[r], rp.format);
-        uint8_t *dst = out + offsets[r];
-        for (uint64_t b = threadIdx.x; b < rec; b += blockDim.x) dst[b] = qs_record_byte(seq, rp, i, at, L, lens[r], b);
+        qs_write_record(seq, rp, i, at, L, lens[r], out + offsets[r], threadIdx.x, blockDim.x);
     }
 }
 
