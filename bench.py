@@ -482,6 +482,7 @@ class FileData:
     def __init__(self, qk, torch, reads, chunk_cap, local):
         raw_np = np.fromfile(reads, dtype=np.uint8)
         self.raw = torch.from_numpy(raw_np).pin_memory()
+        self.raw_ptr = self.raw.data_ptr()
         self.raw_bytes = int(raw_np.size)
         t0 = time.perf_counter()
         chunks, fst = qk.frame(raw_np, seekable=True, chunk_capacity=chunk_cap)
@@ -556,14 +557,19 @@ class SynthData:
         rec_raw = qs.record_bytes(L, fmt_raw) if lens is None else None
         mean_raw = rec_raw if lens is None else float(np.mean(per)) * (1 if not w["fastq"] else 2) + 15
         mean_framed = (L + 1) if lens is None else float(np.mean(per))
-        cap_bytes = max(1 << 28, int((avail - (24 << 30)) / max(1, world) * 0.6))
+        # leave room for the reference's CPU run that follows on rank 0 (its table + counters: 10 bytes per slot)
+        reserve = (24 << 30) + 10 * w["slots"]
+        cap_bytes = max(1 << 28, int((avail - reserve) / max(1, world) * 0.6))
         hn = int(min(n, e2e_cov_cap * n / 30.0, cap_bytes / (mean_raw + mean_framed)))
         hn = max(16, hn // 16 * 16)
         hlens = None if lens is None else lens[:hn]
         raw_total, raw_offsets = qs.layout(hn, L, fmt_raw, hlens)
-        self.raw = torch.empty(raw_total + 64, dtype=torch.uint8, pin_memory=True)
+        self._qs = qs
+        self.raw_ptr = qs.lib().qs_pinned_alloc(raw_total + 64)          # (not torch: its pinned allocator never gives memory back)
+        if not self.raw_ptr:
+            raise MemoryError(f"cannot pin {raw_total} bytes of host memory")
         self.raw_bytes = raw_total
-        fill_pinned(qs, genome, self.raw.data_ptr(), seed, hn, L, w["err_ppm"], fmt_raw, hlens, raw_offsets, local)
+        fill_pinned(qs, genome, self.raw_ptr, seed, hn, L, w["err_ppm"], fmt_raw, hlens, raw_offsets, local)
         if hlens is None:
             rpc = max(16, (chunk_cap // (L + 1)) // 16 * 16)
             starts = list(range(0, hn, rpc))
@@ -573,16 +579,20 @@ class SynthData:
         else:
             f_offsets, self.h_offs, self.h_sizes = chunk_layout(per[:hn], chunk_cap)
             f_total = int(f_offsets[-1] + per[hn - 1])
-        self.framed = torch.empty(f_total + 4096, dtype=torch.uint8, pin_memory=True)
-        fill_pinned(qs, genome, self.framed.data_ptr(), seed, hn, L, w["err_ppm"], qs.FRAMED, hlens, f_offsets, local)
-        self.host_base = self.framed.data_ptr()
+        self.host_base = qs.lib().qs_pinned_alloc(f_total + 4096)
+        if not self.host_base:
+            raise MemoryError(f"cannot pin {f_total} bytes of host memory")
+        fill_pinned(qs, genome, self.host_base, seed, hn, L, w["err_ppm"], qs.FRAMED, hlens, f_offsets, local)
         self.h_framed_bytes = sum(self.h_sizes)
         self.h_lines = hn
         self.h_bases = hn * L if hlens is None else int(hlens.astype(np.uint64).sum())
         self.reads_file = None
 
     def free_host(self):
-        self.raw = self.framed = None
+        for p in (self.raw_ptr, self.host_base):
+            if p:
+                self._qs.lib().qs_pinned_free(p)
+        self.raw_ptr = self.host_base = None
 
 
 def chunk_layout(per, chunk_cap):
@@ -779,11 +789,11 @@ def gpu_arm(args):
 
     def job_raw_device():
         ctx.reset()
-        ctx.count_mem(data.raw.data_ptr(), data.raw_bytes)
+        ctx.count_mem(data.raw_ptr, data.raw_bytes)
 
     def job_raw_host():
         ctx.reset()
-        ctx.count_mem_mt(data.raw.data_ptr(), data.raw_bytes, threads=framer_threads)
+        ctx.count_mem_mt(data.raw_ptr, data.raw_bytes, threads=framer_threads)
 
     job_raw = job_raw_host if host_framing else job_raw_device
 
@@ -878,8 +888,14 @@ def gpu_arm(args):
     ctx.select_counters(0)
 
     # ---- e2e_preframed and e2e: host buffers, copies inside the timed region --------------
-    result_pinned = torch.empty(n_kmers, dtype=torch.int16, pin_memory=True) if rank == 0 else None
-    result_np = result_pinned.numpy().view(np.uint16) if rank == 0 else None
+    result_np = None
+    if rank == 0:                                   # (own pinned allocation: given back before the CPU leg)
+        import ctypes
+        qsl = load_synth_gpu().lib()
+        result_ptr = qsl.qs_pinned_alloc(2 * n_kmers + 64)
+        if not result_ptr:
+            raise MemoryError("cannot pin the result buffer")
+        result_np = np.ctypeslib.as_array(ctypes.cast(result_ptr, ctypes.POINTER(ctypes.c_uint16)), shape=(n_kmers,))
 
     def timed_host(job, steps, warm):
         for _ in range(warm):
@@ -925,7 +941,10 @@ def gpu_arm(args):
 
     framer_gbs = None
     if rank == 0 and not args.kernel_only:
-        framer_gbs = qk.bench_framer(data.raw.data_ptr(), min(data.raw_bytes, 4 << 30), threads=framer_threads, repeats=2)
+        framer_gbs = qk.bench_framer(data.raw_ptr, min(data.raw_bytes, 4 << 30), threads=framer_threads, repeats=2)
+    if rank == 0:
+        result_np = None
+        qsl.qs_pinned_free(result_ptr)
     if synth:
         data.free_host()
         data.devbuf.free()                          # the micro-benchmarks below need the HBM
@@ -1050,7 +1069,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS) + sorted(SYNTH_WORKLOADS))
     ap.add_argument("--reads-scale", type=float, default=1.0, help="GPU-generated workloads: fraction of the workload's reads per GPU (quick runs)")
-    ap.add_argument("--e2e-coverage", type=float, default=8.0, help="GPU-generated workloads: the host legs run over at most this coverage (of 30x) in pinned memory")
+    ap.add_argument("--e2e-coverage", type=float, default=4.0, help="GPU-generated workloads: the host legs run over at most this coverage (of 30x) in pinned memory")
     ap.add_argument("--framer", default="auto", choices=["auto", "host", "device"],
                     help="e2e leg: record framing by host threads (ships sequence lines only) or on the device (ships the raw stream); "
                          "auto = host when there are >= 6 host CPUs per GPU")

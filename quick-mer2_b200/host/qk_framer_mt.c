@@ -41,7 +41,7 @@
 #define QK_MT_MAX_CTX 16
 #define QK_MT_MAX_THREADS 128
 
-enum { SLOT_FREE = 0, SLOT_FILLING = 1, SLOT_SUBMITTED = 2 };
+enum { SLOT_FREE = 0, SLOT_FILLING = 1, SLOT_SUBMITTING = 2, SLOT_SUBMITTED = 3 };
 
 typedef struct {
     _Atomic int state;          /* SLOT_* */
@@ -249,10 +249,12 @@ static void try_submit(mt_job *j, int c, int s)
     mt_chunk *ch = &j->chunk[c][s];
     if (!atomic_load(&ch->closed) || atomic_load(&ch->pending) != 0) return;
     int expect = SLOT_FILLING;
-    if (!atomic_compare_exchange_strong(&ch->state, &expect, SLOT_SUBMITTED)) return; /* somebody else did */
+    if (!atomic_compare_exchange_strong(&ch->state, &expect, SLOT_SUBMITTING)) return; /* somebody else does */
     pthread_mutex_lock(&j->submit_mu[c]);
     int rc = ch->fill ? j->sink->submit(j->sink->user, (uint32_t)c, (uint32_t)s, ch->seq, ch->fill, ch->lines) : QK_OK;
     pthread_mutex_unlock(&j->submit_mu[c]);
+    /* only now may the resolver ask ready()/wait() about this buffer: they speak of the submission just made */
+    atomic_store(&ch->state, ch->fill ? SLOT_SUBMITTED : SLOT_FREE);
     if (rc) { int z = 0; atomic_compare_exchange_strong(&j->err, &z, rc); }
 }
 
@@ -278,7 +280,7 @@ static int open_chunk(mt_job *j)
             const int c = (int)((j->rr + t) % j->n_ctx);
             const int s = (int)j->next_slot[c];
             const int st = atomic_load(&j->chunk[c][s].state);
-            if (st == SLOT_FILLING) continue;                   /* its last block is still being copied */
+            if (st == SLOT_FILLING || st == SLOT_SUBMITTING) continue; /* its last block is still being copied / handed over */
             if (st == SLOT_SUBMITTED) {
                 int ready = j->sink->ready(j->sink->user, (uint32_t)c, (uint32_t)s);
                 if (ready < 0) return -ready;

@@ -627,3 +627,70 @@ def test_roofline_microbenchmarks_run(qk, gpu_ctx):
     g = gpu_ctx.bench_gather(1 << 30, gran=32, loads_in_flight=4, n_gathers=1 << 26)
     h = gpu_ctx.bench_h2d(8 << 20, repeats=8)
     assert 50 < g < 8000 and 1 < h < 200
+
+
+# ------------------------------------------------------------------ dictionaries from the reference's own tools (T14)
+def _ref_tool(ref_binary, args, cwd):
+    res = subprocess.run([str(ref_binary), *map(str, args)], cwd=cwd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout[-2000:]
+    return res.stdout
+
+
+def _count_both(qk, ref_binary, d, prefix, reads, threads=2):
+    """Our command and the reference's on the same files; returns (ours .bin, theirs .bin, ours .txt or None, theirs)."""
+    res = qk.run_cli(["count", "-t", threads, prefix, reads, "ours"], cwd=d)
+    assert res.returncode == 0, res.stdout + res.stderr
+    _ref_tool(ref_binary, ["count", "-t", threads, prefix, reads, "theirs"], d)
+    txt = lambda p: (d / p).read_bytes() if (d / p).exists() else None
+    return (d / "ours.bin").read_bytes(), (d / "theirs.bin").read_bytes(), txt("ours.txt"), txt("theirs.txt")
+
+
+@pytest.mark.parametrize("k", [30, 31, 32, 20])
+def test_dictionary_written_by_reference_index(k, qk, ref_binary, synth, tmp_path):
+    """`quicKmer2 index` (Q.c:127-254): k-mers from column 4 of a BED file, duplicates and reverse-complement
+    duplicates included (both copies get a slot and a place on the chain, Q.c:209-216).  k = 32 is the
+    reference's degenerate case (mask 1 << 64, Q.c:419): every read k-mer becomes key 0 and the .bin is zeros."""
+    if ref_binary is None:
+        pytest.skip("compiled reference not available")
+    synth("ref", "--out", tmp_path / "g.fa", "--bases", 30000, "--contigs", 1, "--seed", 3)
+    seq = "".join(l for l in (tmp_path / "g.fa").read_text().split("\n") if not l.startswith(">"))
+    comp = str.maketrans("ACGT", "TGCA")
+    rng = np.random.default_rng(k)
+    starts = rng.permutation(len(seq) - k)[:4000]
+    kmers = [seq[a:a + k] for a in starts]
+    kmers += kmers[:60] + [m.translate(comp)[::-1] for m in kmers[100:140]]      # duplicates on both strands
+    with open(tmp_path / "kmers.bed", "w") as f:
+        for i, m in enumerate(kmers):
+            f.write(f"chr1\t{i}\t{i + k}\t{m}\n")
+    _ref_tool(ref_binary, ["index", "-k", k, "-s", "16K", "kmers.bed", "idx.fa.qm"], tmp_path)
+    synth("reads", "--ref", tmp_path / "g.fa", "--out", tmp_path / "r.fq", "--n", 3000, "--len", 150, "--seed", 8, "--fastq")
+    ours, theirs, _, _ = _count_both(qk, ref_binary, tmp_path, "idx.fa", "r.fq")
+    assert ours == theirs and len(ours) == 2 * len(kmers)
+    got = np.frombuffer(ours, dtype=np.uint16)
+    assert (got.sum() > 0) == (k != 32)
+
+
+@pytest.mark.parametrize("tool", ["search_e1", "search_e2", "sparse"])
+def test_dictionary_written_by_reference_search_and_sparse(tool, qk, ref_binary, synth, tmp_path):
+    """`search -e 1 / -e 2` (edit-distance filter, Q.c:1190-1231) and `sparse` (thinned .rqm, Q.c:1306-1483):
+    the dictionaries the reference's own tools write, counted by both commands."""
+    if ref_binary is None:
+        pytest.skip("compiled reference not available")
+    synth("ref", "--out", tmp_path / "ref.fa", "--bases", 60000, "--contigs", 2, "--seed", 12, "--segdups", 3, "--segdup-len", 3000,
+          "--divergence-ppm", 20000, "--nblock", 500)
+    synth("ctrl", "--ref", tmp_path / "ref.fa", "--out", tmp_path / "ctrl.bed", "--block", 5000)
+    e = {"search_e1": 1, "search_e2": 2, "sparse": 0}[tool]
+    _ref_tool(ref_binary, ["search", "-k", 30, "-e", e, "-t", 4, "-s", "256K", "-c", "ctrl.bed", "ref.fa"], tmp_path)
+    prefix = "ref.fa"
+    if tool == "sparse":
+        _ref_tool(ref_binary, ["sparse", "-c", "ctrl.bed", 7, "ref.fa"], tmp_path)
+        (tmp_path / "thin.fa.qm").write_bytes((tmp_path / "ref.fa.rqm").read_bytes())   # count opens <prefix>.qm only (Q.c:335-337)
+        for ext in (".qgc",):
+            if (tmp_path / ("ref.fa" + ext)).exists():
+                (tmp_path / ("thin.fa" + ext)).write_bytes((tmp_path / ("ref.fa" + ext)).read_bytes())
+        prefix = "thin.fa"
+    synth("reads", "--ref", tmp_path / "ref.fa", "--out", tmp_path / "r.fq", "--n", 20000, "--len", 150, "--seed", 4, "--fastq")
+    ours, theirs, otxt, ttxt = _count_both(qk, ref_binary, tmp_path, prefix, "r.fq", threads=3)
+    assert ours == theirs and len(ours) > 1000
+    assert otxt == ttxt
+    assert np.frombuffer(ours, dtype=np.uint16).sum() > 0
