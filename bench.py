@@ -935,7 +935,10 @@ def gpu_arm(args):
     if world == 1 and not args.kernel_only and file_reads is not None:
         def job_file():
             ctx.reset()
-            ctx.count_file(file_reads, threads=args.reader_threads)
+            if host_framing:
+                ctx.count_file_mt(file_reads, threads=framer_threads)
+            else:
+                ctx.count_file(file_reads, threads=args.reader_threads)
         file_s, file_kmers = timed_host(job_file, 2, 1)
         file_bytes = os.path.getsize(file_reads)
 
@@ -1044,8 +1047,11 @@ def gpu_arm(args):
                           "h2d_ms_per_step": h2d_ms_step,
                           "path": "pre-framed pinned host chunks -> qk_submit (H2D + kernel per chunk) -> qk_finish"},
         "e2e_file": None if file_s is None else {
-            "value": file_kmers / file_s, "unit": "k-mers/s", "file_gbs": file_bytes / file_s / 1e9, "reader_threads": args.reader_threads,
-            "path": "reads FILE (page cache) -> qk_count_raw_file_mt (pread into pinned slots, H2D, device framing, count) -> qk_finish"},
+            "value": file_kmers / file_s, "unit": "k-mers/s", "file_gbs": file_bytes / file_s / 1e9,
+            "threads": framer_threads if host_framing else args.reader_threads,
+            "path": ("reads FILE (page cache, mapped) -> qk_count_file_mt (host threads frame blocks of the mapping, sequence lines into the pinned slots, H2D, count) -> qk_finish"
+                     if host_framing else
+                     "reads FILE (page cache) -> qk_count_raw_file_mt (pread into pinned slots, H2D, device framing, count) -> qk_finish")},
         "gpu_launches": launches * args.steps,
         "parity_ok": parity["ok"], "parity": parity,
         "clocks": clocks,
