@@ -139,6 +139,8 @@ int qk_frame_mem_mt(const qk_chunk_sink *sink, const uint8_t *data, size_t n, in
 /* Measurement: the framer alone over `data`, chunks discarded; GB/s of raw input consumed and of
  * framed output produced (the host-side term of the end-to-end roofline). */
 int qk_bench_framer(const uint8_t *data, size_t n, uint32_t threads, int repeats, double *raw_gbs, double *framed_gbs);
+/* For scale: what the host's memory gives `threads` threads -- GB/s of a pure read and of memcpy (bytes copied). */
+int qk_bench_host_memory(size_t bytes_per_thread, uint32_t threads, double *read_gbs, double *copy_gbs);
 int qk_count_file_mt(qk_ctx *const *ctxs, uint32_t n_ctx, const char *reads_path, uint32_t threads, qk_framer_stats *st);
 
 /* ---- one reads file, several GPUs ---------------------------------------------------------

@@ -167,6 +167,7 @@ SIGNATURES = {
     "qk_count_raw_file": (C.c_int, [_P, C.c_char_p, C.POINTER(FramerStats)]),
     "qk_frame_mem_mt": (C.c_int, [_P, _P, C.c_size_t, C.c_int, C.c_uint32, C.POINTER(FramerStats)]),
     "qk_bench_framer": (C.c_int, [_P, C.c_size_t, C.c_uint32, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "qk_bench_host_memory": (C.c_int, [C.c_size_t, C.c_uint32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "qk_count_mem_mt": (C.c_int, [C.POINTER(_P), C.c_uint32, _P, C.c_size_t, C.c_int, C.c_uint32, C.POINTER(FramerStats)]),
     "qk_count_file_mt": (C.c_int, [C.POINTER(_P), C.c_uint32, C.c_char_p, C.c_uint32, C.POINTER(FramerStats)]),
     "qk_shard_bounds": (C.c_int, [C.c_char_p, C.c_uint32, C.c_uint32, _U64P, _U64P]),
@@ -580,6 +581,14 @@ def bench_framer(host_ptr: int, n_bytes: int, threads: int = 0, repeats: int = 3
     rc = lib().qk_bench_framer(host_ptr, n_bytes, threads, repeats, C.byref(a), C.byref(b))
     if rc:
         raise QkError(rc, "qk_bench_framer")
+    return a.value, b.value
+
+
+def bench_host_memory(bytes_per_thread: int = 256 << 20, threads: int = 8):
+    a, b = C.c_double(), C.c_double()
+    rc = lib().qk_bench_host_memory(bytes_per_thread, threads, C.byref(a), C.byref(b))
+    if rc:
+        raise QkError(rc, "qk_bench_host_memory")
     return a.value, b.value
 
 

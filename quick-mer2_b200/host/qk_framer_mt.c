@@ -74,6 +74,8 @@ typedef struct {
     _Atomic int err;
     int avx512;
     uint16_t tab[2][256];                /* the line state machine from all four entry states at once */
+    size_t stage_cap;                    /* bytes of a worker's staging buffer */
+    int nt;                              /* staged non-temporal stores (QK_FRAMER_NT=0 turns them off) */
 } mt_job;
 
 /* ---- line scan + state machine ------------------------------------------------------------ */
@@ -176,14 +178,33 @@ __attribute__((target("avx512f,avx512bw,bmi,bmi2,popcnt"))) static int scan_avx5
         }
         p += 64;
     }
-    /* (B) */
+    /* (B) -- on locals: the keep bytes may alias anything, so nothing of S is touched inside the loop */
     const size_t lines = (size_t)(out - (S->starts + 1));
-    uint64_t *st = S->starts;
+    const uint64_t *__restrict__ st = S->starts;
+    uint8_t *__restrict__ keep = S->keep;
+    const uint16_t(*__restrict__ tab)[256] = S->tab;
+    uint32_t P = S->P, l0 = 0, l1 = 0, l2 = 0, l3 = 0;
+    size_t b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+    size_t ls = st[0];
     for (size_t k = 0; k < lines; ++k) {
-        const size_t ls = st[k], le = st[k + 1];
-        S->n_lines = k;                      /* sim_line appends at n_lines: rewrites st[k + 1] with itself */
-        sim_line(S, d[ls], ls, le);
+        const size_t le = st[k + 1], len = le - ls;
+        const uint32_t e = tab[d[ls] == '>'][P];
+        const uint32_t kk = e >> 8;
+        P = e & 0xFFu;
+        keep[k] = (uint8_t)kk;
+        b0 += len & ((size_t)0 - (kk & 1u));
+        b1 += len & ((size_t)0 - ((kk >> 1) & 1u));
+        b2 += len & ((size_t)0 - ((kk >> 2) & 1u));
+        b3 += len & ((size_t)0 - ((kk >> 3) & 1u));
+        l0 += kk & 1u;
+        l1 += (kk >> 1) & 1u;
+        l2 += (kk >> 2) & 1u;
+        l3 += (kk >> 3) & 1u;
+        ls = le;
     }
+    S->P = P;
+    S->out_bytes[0] += b0; S->out_bytes[1] += b1; S->out_bytes[2] += b2; S->out_bytes[3] += b3;
+    S->out_lines[0] += l0; S->out_lines[1] += l1; S->out_lines[2] += l2; S->out_lines[3] += l3;
     S->n_lines = lines;
     return ended;
 }
@@ -202,28 +223,42 @@ static int scan_plain(const uint8_t *d, size_t from, size_t n, size_t stop_at, m
     return 0;
 }
 
-/* the kept lines of trajectory s_in, back to back at o; returns the number of lines longer than the reference's buffer */
-__attribute__((target("avx512f,avx512bw"))) static uint64_t copy_avx512(uint8_t *o, const uint8_t *d, size_t n, const mt_sim *S, uint32_t s_in)
+/* the kept lines of trajectory s_in, back to back at o; returns the number of lines longer than the reference's buffer.
+ * The lines are gathered in `stage` (thread-local, cache-resident, co-aligned with o modulo 64) and go to the pinned
+ * chunk buffer with non-temporal 64-byte stores: the destination is written once and read by the DMA engine only, so
+ * the read-for-ownership a normal store costs (as much DRAM traffic again as the write itself) is saved. */
+__attribute__((target("avx512f,avx512bw"))) static uint64_t copy_avx512(uint8_t *o, const uint8_t *d, size_t n, const mt_sim *S, uint32_t s_in,
+                                                                        uint8_t *stage)
 {
     uint64_t longl = 0;
+    uint8_t *w = stage + ((uintptr_t)o & 63);
+    uint8_t *const w0 = w;
     for (size_t k = 0; k < S->n_lines; ++k) {
         if (!((S->keep[k] >> s_in) & 1u)) continue;
         const size_t ls = S->starts[k], le = S->starts[k + 1], len = le - ls;
         const uint8_t *src = d + ls;
         if (le > n) {                                            /* unterminated last line: we terminate it (T9) */
-            memcpy(o, src, n - ls);
-            o[n - ls] = '\n';
+            memcpy(w, src, n - ls);
+            w[n - ls] = '\n';
         } else if (len >= 64 && len <= 4096) {                   /* whole vectors, the last one flush with the end */
             size_t i = 0;
-            for (; i + 64 <= len; i += 64) _mm512_storeu_si512((void *)(o + i), _mm512_loadu_si512((const void *)(src + i)));
-            if (i < len) _mm512_storeu_si512((void *)(o + len - 64), _mm512_loadu_si512((const void *)(src + len - 64)));
+            for (; i + 64 <= len; i += 64) _mm512_storeu_si512((void *)(w + i), _mm512_loadu_si512((const void *)(src + i)));
+            if (i < len) _mm512_storeu_si512((void *)(w + len - 64), _mm512_loadu_si512((const void *)(src + len - 64)));
         } else if (len < 64) {
             const __mmask64 mk = ((uint64_t)1 << len) - 1;
-            _mm512_mask_storeu_epi8((void *)o, mk, _mm512_maskz_loadu_epi8(mk, (const void *)src));
-        } else memcpy(o, src, len);
-        o += len;
+            _mm512_mask_storeu_epi8((void *)w, mk, _mm512_maskz_loadu_epi8(mk, (const void *)src));
+        } else memcpy(w, src, len);
+        w += len;
         longl += len > QK_MAX_LINE_BYTES;
     }
+    /* stage -> destination */
+    size_t total = (size_t)(w - w0), at = 0;
+    const uint8_t *r = w0;
+    const size_t head = (64 - ((uintptr_t)o & 63)) & 63;
+    if (head && total >= head) { memcpy(o, r, head); at = head; }
+    for (; at + 64 <= total; at += 64) _mm512_stream_si512((void *)(o + at), _mm512_load_si512((const void *)(r + at)));
+    if (at < total) memcpy(o + at, r + at, total - at);
+    _mm_sfence();                                                /* before the chunk is handed to the copy engine */
     return longl;
 }
 
@@ -314,7 +349,7 @@ static int open_chunk(mt_job *j)
 }
 
 /* ---- worker ----------------------------------------------------------------------------------- */
-typedef struct { mt_job *j; uint64_t *starts; uint8_t *keep; size_t starts_cap; } mt_worker;
+typedef struct { mt_job *j; uint64_t *starts; uint8_t *keep, *stage; size_t starts_cap; } mt_worker;
 
 static void *worker(void *arg)
 {
@@ -391,7 +426,7 @@ static void *worker(void *arg)
         atomic_store_explicit(&j->resolved, i + 1, memory_order_release);
         /* 4. copy the sequence lines */
         if (dst) {
-            const uint64_t longl = j->avx512 ? copy_avx512(dst, d, n, &S, s_in) : copy_plain(dst, d, n, &S, s_in);
+            const uint64_t longl = j->avx512 && j->nt && out <= j->stage_cap ? copy_avx512(dst, d, n, &S, s_in, w->stage) : copy_plain(dst, d, n, &S, s_in);
             if (longl) { pthread_mutex_lock(&j->submit_mu[0]); j->long_lines += longl; pthread_mutex_unlock(&j->submit_mu[0]); }
             atomic_fetch_sub(&j->chunk[c][s].pending, 1);
             try_submit(j, c, s);
@@ -428,12 +463,14 @@ int qk_frame_mem_mt(const qk_chunk_sink *sink, const uint8_t *data, size_t n, in
     j->state = n && (j->fastq || !seekable) ? 3u : 0u;               /* first line consumed: FASTQ always, FASTA on a pipe (Q.c:396) */
     /* blocks: large enough to amortise the hand-over, small enough that a block's output (<= block + one
      * line) fits a chunk several times over */
-    j->block = (size_t)1 << 20;
+    j->block = (size_t)512 << 10;        /* block + its kept lines (staged) + the line table stay in a 2 MB L2 */
     while (j->block > ((size_t)16 << 10) && j->block + 100000 > j->cap / 2) j->block >>= 1;
     j->n_blocks = (n + j->block - 1) / j->block;
     j->cur_ctx = j->cur_slot = -1;
     j->avx512 = __builtin_cpu_supports("avx512bw") && !getenv("QK_NO_AVX512");
+    { const char *e = getenv("QK_FRAMER_NT"); j->nt = e ? atoi(e) != 0 : 1; }
     build_table(j->tab, j->fastq);
+    j->stage_cap = j->block + ((size_t)128 << 10);
     if (!threads) threads = default_threads(j->n_ctx);
     if (threads > QK_MT_MAX_THREADS) threads = QK_MT_MAX_THREADS;
     if (threads > j->n_blocks) threads = j->n_blocks ? (uint32_t)j->n_blocks : 1;
@@ -447,7 +484,8 @@ int qk_frame_mem_mt(const qk_chunk_sink *sink, const uint8_t *data, size_t n, in
         wk[t].starts_cap = starts_cap;
         wk[t].starts = malloc(starts_cap * sizeof(uint64_t));
         wk[t].keep = malloc(starts_cap);
-        if (!wk[t].starts || !wk[t].keep) { free(wk[t].starts); free(wk[t].keep); rc = QK_ERR_NOMEM; break; }
+        wk[t].stage = j->avx512 ? aligned_alloc(64, (j->stage_cap + 128 + 63) / 64 * 64) : NULL;
+        if (!wk[t].starts || !wk[t].keep || (j->avx512 && !wk[t].stage)) { free(wk[t].starts); free(wk[t].keep); free(wk[t].stage); rc = QK_ERR_NOMEM; break; }
         ++allocated;
     }
     if (rc) { int z = 0; atomic_compare_exchange_strong(&j->err, &z, rc); }
@@ -457,7 +495,7 @@ int qk_frame_mem_mt(const qk_chunk_sink *sink, const uint8_t *data, size_t n, in
     }
     if (!rc && j->n_blocks) worker(&wk[threads - 1]);
     for (uint32_t t = 0; t < started; ++t) pthread_join(th[t], NULL);
-    for (uint32_t t = 0; t < allocated; ++t) { free(wk[t].starts); free(wk[t].keep); }
+    for (uint32_t t = 0; t < allocated; ++t) { free(wk[t].starts); free(wk[t].keep); free(wk[t].stage); }
     if (!rc) rc = atomic_load(&j->err);
     for (uint32_t c = 0; c < j->n_ctx; ++c) pthread_mutex_destroy(&j->submit_mu[c]);
     if (st) {
@@ -543,6 +581,53 @@ int qk_bench_framer(const uint8_t *data, size_t n, uint32_t threads, int repeats
     if (raw_gbs) *raw_gbs = (double)n * repeats / dt / 1e9;
     if (framed_gbs) *framed_gbs = (double)atomic_load(&ns.bytes) / dt / 1e9;
     for (uint32_t s = 0; s < n_slots; ++s) free(ns.buf[s]);
+    return rc;
+}
+
+/* Host memory bandwidth with `threads` threads, for scale: GB/s of a pure read (sum) and of memcpy (bytes copied). */
+typedef struct { uint8_t *a, *b; size_t n; int mode; uint64_t sink; } hm_job;
+static void *hm_worker(void *arg)
+{
+    hm_job *h = arg;
+    if (h->mode == 0) {
+        const uint64_t *p = (const uint64_t *)h->a;
+        uint64_t acc = 0;
+        for (size_t i = 0; i < h->n / 8; ++i) acc += p[i];
+        h->sink = acc;
+    } else memcpy(h->b, h->a, h->n);
+    return NULL;
+}
+int qk_bench_host_memory(size_t bytes_per_thread, uint32_t threads, double *read_gbs, double *copy_gbs)
+{
+    if (threads < 1 || threads > QK_MT_MAX_THREADS || bytes_per_thread < 4096) return QK_ERR_ARG;
+    hm_job job[QK_MT_MAX_THREADS];
+    pthread_t th[QK_MT_MAX_THREADS];
+    memset(job, 0, sizeof job);
+    int rc = QK_OK;
+    for (uint32_t t = 0; t < threads; ++t) {
+        job[t].n = bytes_per_thread / 8 * 8;
+        job[t].a = malloc(job[t].n);
+        job[t].b = malloc(job[t].n);
+        if (!job[t].a || !job[t].b) { rc = QK_ERR_NOMEM; break; }
+        memset(job[t].a, 1, job[t].n);
+        memset(job[t].b, 2, job[t].n);
+    }
+    for (int mode = 0; !rc && mode < 2; ++mode) {
+        double best = 0;
+        for (int rep = 0; rep < 3; ++rep) {
+            struct timespec t0, t1;
+            clock_gettime(CLOCK_MONOTONIC, &t0);
+            for (uint32_t t = 0; t < threads; ++t) { job[t].mode = mode; pthread_create(&th[t], NULL, hm_worker, &job[t]); }
+            for (uint32_t t = 0; t < threads; ++t) pthread_join(th[t], NULL);
+            clock_gettime(CLOCK_MONOTONIC, &t1);
+            const double dt = (t1.tv_sec - t0.tv_sec) + (t1.tv_nsec - t0.tv_nsec) * 1e-9;
+            const double g = (double)job[0].n * threads / dt / 1e9;
+            if (g > best) best = g;
+        }
+        if (mode == 0 && read_gbs) *read_gbs = best;
+        if (mode == 1 && copy_gbs) *copy_gbs = best;
+    }
+    for (uint32_t t = 0; t < threads; ++t) { free(job[t].a); free(job[t].b); }
     return rc;
 }
 
