@@ -785,7 +785,7 @@ def gpu_arm(args):
 
     cpus = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     framer_threads = args.framer_threads or max(1, cpus // max(1, world))
-    host_framing = args.framer == "host" or (args.framer == "auto" and framer_threads >= 6)
+    host_framing = args.framer == "host" or (args.framer == "auto" and framer_threads >= 12)   # measured: profiles/README.md
 
     def job_raw_device():
         ctx.reset()
@@ -1078,7 +1078,7 @@ def main():
     ap.add_argument("--e2e-coverage", type=float, default=4.0, help="GPU-generated workloads: the host legs run over at most this coverage (of 30x) in pinned memory")
     ap.add_argument("--framer", default="auto", choices=["auto", "host", "device"],
                     help="e2e leg: record framing by host threads (ships sequence lines only) or on the device (ships the raw stream); "
-                         "auto = host when there are >= 6 host CPUs per GPU")
+                         "auto = host when there are >= 12 host CPUs per GPU")
     ap.add_argument("--framer-threads", type=int, default=0, help="host framer threads per GPU (0 = host CPUs / GPUs)")
     ap.add_argument("--reference-budget-s", type=float, default=240.0, help="--impl reference: stop starting new steps after this many seconds")
     ap.add_argument("--cache-dir", default=None)

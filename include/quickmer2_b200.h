@@ -93,8 +93,8 @@ typedef struct qk_table_desc {
     uint32_t rem_bits;       /* 60 - bucket_bits                                 */
     uint64_t skipped_keys;   /* dictionary keys no read can produce (>= 2^60) or
                                 shadowed duplicates; their ordinals stay 0       */
-    uint64_t ext_bytes;      /* bytes of each 2-bit-per-ordinal extension array  */
-    uint64_t cont_bytes;     /* bytes of the 1-bit-per-ordinal continuation array */
+    uint64_t ext_bytes;      /* bytes of the dictionary-order extension array: 12 bytes per 16 ordinals */
+    uint64_t cont_bytes;     /* 0 (the continuation bits live in the same array)  */
     uint32_t has_ext;        /* 1: dictionary-order extension arrays present (k = 30) */
     uint32_t reserved;
 } qk_table_desc;
@@ -107,8 +107,9 @@ int qk_table_geometry(uint64_t n_kmers, uint32_t k, qk_table_desc *desc);
 int qk_dict_adopt(qk_ctx *ctx, const qk_table_desc *desc);
 /* Device pointers of the table image (for NCCL broadcast / peer copies). */
 int qk_dict_device_ptrs(const qk_ctx *ctx, void **table, void **stash);
-/* ... and of the extension arrays (NULL when has_ext == 0): last base and first base of every
- * dictionary k-mer in its walking orientation (ext_bytes each), continuation bits (cont_bytes). */
+/* ... and of the extension array (NULL when has_ext == 0) through *last: per 16 ordinals three words --
+ * last bases and first bases of the dictionary k-mers in their walking orientation (2 bits each) and
+ * continuation bits (ext_bytes in all).  *first and *cont come back NULL. */
 int qk_dict_ext_ptrs(const qk_ctx *ctx, void **last, void **first, void **cont);
 
 /* ------------------------------------------------------------------ counting --------

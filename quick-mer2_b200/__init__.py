@@ -301,7 +301,7 @@ class Context:
         if d.has_ext:
             a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
             self._check(self._lib.qk_dict_ext_ptrs(self._h, C.byref(a), C.byref(b), C.byref(c)))
-            out += [(a.value, int(d.ext_bytes)), (b.value, int(d.ext_bytes)), (c.value, int(d.cont_bytes))]
+            out += [(a.value, int(d.ext_bytes))]      # one array: last / first base and continuation bits per 16 ordinals
         return out
 
     def counters_device_ptr(self):

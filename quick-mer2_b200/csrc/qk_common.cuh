@@ -2,9 +2,11 @@
 //
 // Table layout in HBM (DESIGN.md "data layout"):
 //   bucket  = 4 x uint64 entries = one 32-byte sector, fetched with one LDG.E.256
-//   entry   = (remainder << ord_bits) | (ordinal + 1), 0 = empty; bit 63 is spare (rem_bits +
-//              ord_bits <= 63, ord_bits <= 32), so the probe compares the high words with one
-//              32-bit op and the low words with another
+//   entry   = (remainder << ord_bits) | (ordinal + 1), 0 = empty; rem_bits + ord_bits <= 62 and
+//              ord_bits <= 32, so the probe compares the high words with one 32-bit op and the low
+//              words with another; bit 63 = strand of the k-mer's walking orientation; bit 62 of the
+//              LAST entry of a bucket = "a key of this bucket went to the stash" (a miss in a full
+//              bucket needs the stash only then)
 //   key     -> h = mix60(key) (a bijection on [0, 2^60)); bucket = top bucket_bits of h,
 //              remainder = low rem_bits = 60 - bucket_bits of h (quotienting: the bucket
 //              index is implied, so remainder + ordinal fit one 64-bit word)
@@ -26,6 +28,8 @@
 #define QK_BUCKET_ENTRIES 4
 #define QK_FRAME_MAX_CTAS 2048   // CTAs of the device framing passes (per chunk)
 #define QK_STATS_WORDS 8
+#define QK_ENTRY_OVERFLOW 0x4000000000000000ull // bit 62 of a bucket's last entry
+#define QK_EXT_GROUP_WORDS 3
 
 struct __align__(32) qk_bucket { unsigned long long e[QK_BUCKET_ENTRIES]; };
 struct __align__(16) qk_stash_entry { unsigned long long key; uint32_t ord1; uint32_t pad; };
@@ -40,7 +44,7 @@ struct qk_table_view {
     uint32_t rem_bits;        // 60 - bucket_bits
     uint32_t ord_bits;
     uint32_t has_stash;       // stash_used != 0
-    const uint32_t *ext_last, *ext_first, *ext_cont; // NULL unless k = 30
+    const uint32_t *ext;      // dictionary-order extension array (12 bytes per 16 ordinals), NULL unless k = 30
     uint64_t n_kmers;
 };
 
@@ -73,7 +77,8 @@ struct qk_ctx {
 
     qk_bucket *buckets;
     qk_stash_entry *stash;
-    uint32_t *ext_last, *ext_first, *ext_cont; // dictionary-order extension arrays (k = 30), else NULL
+    uint32_t *ext;            // dictionary-order extension array (k = 30), else NULL: per 16 ordinals three words --
+                              // last base (2 bits each), first base (2 bits each), continuation bits (low 16)
     qk_table_desc desc;
 
     uint32_t *counters;       // n_kmers x u32, indexed by ordinal: the buffer jobs currently count into

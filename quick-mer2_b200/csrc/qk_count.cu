@@ -284,12 +284,12 @@ __global__ void __launch_bounds__(QK_THREADS, 3) qk_count_kernel(const qk_count_
                 const uint32_t qhi = (uint32_t)(q[u] >> 32), qlo = (uint32_t)q[u];
 #pragma unroll
                 for (int e = 0; e < QK_BUCKET_ENTRIES; ++e) {
-                    const uint32_t dhi = ((uint32_t)(bk[u].e[e] >> 32) ^ qhi) & 0x7FFFFFFFu;
+                    const uint32_t dhi = ((uint32_t)(bk[u].e[e] >> 32) ^ qhi) & 0x3FFFFFFFu;
                     const uint32_t dlo = (uint32_t)bk[u].e[e] ^ qlo;
                     if (dhi == 0 && dlo - 1 < ord_mask) ord1 = dlo;
                 }
-                // entries fill a bucket in order, so it is full iff the last one is taken
-                if (ord1 == 0 && bk[u].e[QK_BUCKET_ENTRIES - 1] != 0 && tv.has_stash) ord1 = qk_stash_find(tv, key[u]);
+                // a key of this bucket is in the stash only if the bucket says so (bit 62 of its last entry)
+                if (ord1 == 0 && (bk[u].e[QK_BUCKET_ENTRIES - 1] & QK_ENTRY_OVERFLOW)) ord1 = qk_stash_find(tv, key[u]);
                 if (ord1) {
                     ++n_hit;
                     atomicAdd(a.counters + (ord1 - 1), 1u);
@@ -337,17 +337,23 @@ __device__ __forceinline__ uint32_t qk_rev16pairs(uint32_t c)
     uint32_t z = __brev(c);
     return ((z & 0x55555555u) << 1) | ((z >> 1) & 0x55555555u);
 }
-// 15 two-bit fields starting at ordinal q of a packed array (ordinal q in bits 1:0)
-__device__ __forceinline__ uint32_t qk_extract30(const uint32_t *__restrict__ arr, uint64_t q)
+// The extension array holds, per group of 16 ordinals, three adjacent words: last bases (2 bits per
+// ordinal), first bases (2 bits per ordinal), continuation bits (low 16 bits).  A walk reads the fields
+// of 15 consecutive ordinals: two groups = 24 contiguous bytes, one L2 line, where three separate arrays
+// cost two or three random DRAM sectors per walk.
+// 15 two-bit fields starting at ordinal q (ordinal q in bits 1:0); which = 0: last base, 1: first base
+__device__ __forceinline__ uint32_t qk_extract30(const uint32_t *__restrict__ ext, uint64_t q, uint32_t which)
 {
-    const uint32_t lo = __ldg(arr + (q >> 4)), hi = __ldg(arr + (q >> 4) + 1);
+    const uint32_t *g = ext + (q >> 4) * QK_EXT_GROUP_WORDS + which;
+    const uint32_t lo = __ldg(g), hi = __ldg(g + QK_EXT_GROUP_WORDS);
     return __funnelshift_r(lo, hi, 2 * (uint32_t)(q & 15)) & 0x3FFFFFFFu;
 }
-// 15 one-bit fields starting at ordinal q
-__device__ __forceinline__ uint32_t qk_extract15(const uint32_t *__restrict__ arr, uint64_t q)
+// 15 continuation bits starting at ordinal q
+__device__ __forceinline__ uint32_t qk_extract15(const uint32_t *__restrict__ ext, uint64_t q)
 {
-    const uint32_t lo = __ldg(arr + (q >> 5)), hi = __ldg(arr + (q >> 5) + 1);
-    return __funnelshift_r(lo, hi, (uint32_t)(q & 31)) & 0x7FFFu;
+    const uint32_t *g = ext + (q >> 4) * QK_EXT_GROUP_WORDS + 2;
+    const uint32_t both = (__ldg(g) & 0xFFFFu) | (__ldg(g + QK_EXT_GROUP_WORDS) << 16);
+    return (both >> (uint32_t)(q & 15)) & 0x7FFFu;
 }
 
 struct qk_probe {
@@ -373,12 +379,13 @@ __device__ __forceinline__ uint32_t qk_probe_resolve(const qk_table_view &tv, co
     for (int e = 0; e < QK_BUCKET_ENTRIES; ++e) {
         const uint32_t ehi = (uint32_t)(bk.e[e] >> 32);
         const uint32_t dlo = (uint32_t)bk.e[e] ^ qlo;
-        if (((ehi ^ qhi) & 0x7FFFFFFFu) == 0 && dlo - 1 < ord_mask) {
+        if (((ehi ^ qhi) & 0x3FFFFFFFu) == 0 && dlo - 1 < ord_mask) {
             ord1 = dlo;
             *strand = ehi >> 31;
         }
     }
-    if (ord1 == 0 && bk.e[QK_BUCKET_ENTRIES - 1] != 0 && tv.has_stash) ord1 = qk_stash_find(tv, p.key, strand);
+    // a key of this bucket is in the stash only if the bucket says so (bit 62 of its last entry)
+    if (ord1 == 0 && (bk.e[QK_BUCKET_ENTRIES - 1] & QK_ENTRY_OVERFLOW)) ord1 = qk_stash_find(tv, p.key, strand);
     return ord1;
 }
 
@@ -520,11 +527,11 @@ __global__ void __launch_bounds__(QK_THREADS, MINB) qk_count_ext_kernel(const qk
                 uint32_t R = qk_rev16pairs(my_codes) >> (2 * (ja + 1));
                 uint32_t D, Cb;
                 if (plus) {
-                    D = qk_extract30(tv.ext_last, oa + 1);
-                    Cb = qk_extract15(tv.ext_cont, oa + 1);
+                    D = qk_extract30(tv.ext, oa + 1, 0);
+                    Cb = qk_extract15(tv.ext, oa + 1);
                 } else {
-                    D = qk_rev16pairs(qk_extract30(tv.ext_first, oa - 15)) >> 2;
-                    Cb = __brev(qk_extract15(tv.ext_cont, oa - 14)) >> 17;
+                    D = qk_rev16pairs(qk_extract30(tv.ext, oa - 15, 1)) >> 2;
+                    Cb = __brev(qk_extract15(tv.ext, oa - 14)) >> 17;
                     R ^= 0xAAAAAAAAu;
                 }
                 const uint32_t X = D ^ R;
@@ -640,9 +647,7 @@ static int qk_table_view_of(qk_ctx *ctx, qk_table_view *tv)
     tv->rem_bits = d->rem_bits;
     tv->ord_bits = d->ord_bits;
     tv->has_stash = d->stash_used != 0;
-    tv->ext_last = d->has_ext ? ctx->ext_last : NULL;
-    tv->ext_first = d->has_ext ? ctx->ext_first : NULL;
-    tv->ext_cont = d->has_ext ? ctx->ext_cont : NULL;
+    tv->ext = d->has_ext ? ctx->ext : NULL;
     tv->n_kmers = d->n_kmers;
     return QK_OK;
 }
@@ -662,7 +667,7 @@ int qk_launch_count(qk_ctx *ctx, qk_slot *sl, const uint8_t *dev_bytes, size_t n
     }
     // classic kernel: 3 CTAs/SM, 4 waves; extension kernel: 4 CTAs/SM, 2 waves (longer warp spans
     // amortise the span-start search; measured +3 %)
-    uint32_t target_ctas = (uint32_t)ctx->sm_count * (a.tv.ext_last ? 8 : 12);
+    uint32_t target_ctas = (uint32_t)ctx->sm_count * (a.tv.ext ? 8 : 12);
     uint32_t tpc = (a.n_tiles + target_ctas - 1) / target_ctas;
     if (tpc < 4) tpc = 4;
     if (tiles_env > 0) tpc = (uint32_t)tiles_env;
@@ -678,7 +683,7 @@ int qk_launch_count(qk_ctx *ctx, qk_slot *sl, const uint8_t *dev_bytes, size_t n
     if (classic < 0) classic = getenv("QK_CLASSIC_KERNEL") != NULL;
     static int plain_loads = -1; // QK_EXT_PLAIN_LOADS=1: bucket loads without the .L2::64B hint (A/B knob, -2 %)
     if (plain_loads < 0) plain_loads = getenv("QK_EXT_PLAIN_LOADS") != NULL;
-    if (a.tv.ext_last && !classic) {
+    if (a.tv.ext && !classic) {
         // 4 CTAs/SM at 64 registers: 5 and 6 CTAs/SM spill and measured 2-5 % slower (profiles/README.md)
         if (plain_loads) qk_count_ext_kernel<4, false><<<grid, QK_THREADS, 0, sl->stream>>>(a);
         else qk_count_ext_kernel<4, true><<<grid, QK_THREADS, 0, sl->stream>>>(a);

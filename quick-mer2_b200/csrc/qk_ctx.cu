@@ -112,9 +112,7 @@ extern "C" void qk_ctx_destroy(qk_ctx *ctx)
     cudaFree(ctx->raw_next);
     cudaFree(ctx->buckets);
     cudaFree(ctx->stash);
-    cudaFree(ctx->ext_last);
-    cudaFree(ctx->ext_first);
-    cudaFree(ctx->ext_cont);
+    cudaFree(ctx->ext);
     cudaFree(ctx->counters_buf[0]);
     cudaFree(ctx->counters_buf[1]);
     cudaFree(ctx->stats);

@@ -203,9 +203,10 @@ __device__ __forceinline__ void qk_table_insert(const qk_build_params &bp, uint6
     unsigned long long *e = bp.buckets[bucket].e;
 #pragma unroll
     for (int i = 0; i < QK_BUCKET_ENTRIES; ++i) {
-        if (e[i] == 0 && atomicCAS(&e[i], 0ull, entry) == 0ull) return;
+        if (e[i] == 0 && atomicCAS(&e[i], 0ull, entry) == 0ull) return;   // (entries are never 0 again once set)
     }
-    // home bucket full: stash
+    // home bucket full: stash, and say so in the bucket (its last entry is taken and final)
+    atomicOr(&e[QK_BUCKET_ENTRIES - 1], QK_ENTRY_OVERFLOW);
     unsigned long long used = atomicAdd(&info->stash_used, 1ull);
     if (used >= bp.stash_limit) { atomicOr(&info->flags, QK_FLAG_STASH_FULL); return; }
     uint64_t s = qk_mix_stash(key) & bp.stash_mask;
@@ -264,8 +265,7 @@ __device__ __forceinline__ uint64_t qk_rc30(uint64_t x)
 // first ordinal of a block never continues (the price of not chaining the blocks).
 #define QK_EXT_BLOCK 256
 __global__ void qk_orient_insert_kernel(const unsigned long long *__restrict__ kbo, uint64_t n, int with_ext, qk_build_params bp,
-                                        uint32_t *__restrict__ ext_last, uint32_t *__restrict__ ext_first,
-                                        uint32_t *__restrict__ ext_cont, qk_build_info *info)
+                                        uint32_t *__restrict__ ext, qk_build_info *info)
 {
     const uint64_t blk = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t begin = blk * QK_EXT_BLOCK;
@@ -308,15 +308,13 @@ __global__ void qk_orient_insert_kernel(const unsigned long long *__restrict__ k
             const uint32_t i = (uint32_t)(o - begin);
             wl |= (uint32_t)(F & 3) << (2 * (i & 15));
             wf |= (uint32_t)((F >> 58) & 3) << (2 * (i & 15));
-            wc |= cont << (i & 31);
-            if ((i & 15) == 15 || o + 1 == end) {
-                ext_last[o >> 4] = wl;
-                ext_first[o >> 4] = wf;
-                wl = wf = 0;
-            }
-            if ((i & 31) == 31 || o + 1 == end) {
-                ext_cont[o >> 5] = wc;
-                wc = 0;
+            wc |= cont << (i & 15);
+            if ((i & 15) == 15 || o + 1 == end) {                // one group of 16 ordinals: three adjacent words
+                uint32_t *g = ext + (o >> 4) * QK_EXT_GROUP_WORDS;
+                g[0] = wl;
+                g[1] = wf;
+                g[2] = wc;
+                wl = wf = wc = 0;
             }
         }
     }
@@ -346,7 +344,7 @@ static void qk_geometry(uint64_t n, uint32_t k, uint64_t stash_slots_min, qk_tab
     d->rem_bits = QK_KEY_BITS - d->bucket_bits;
     d->ord_bits = qk_bits_for(n); // holds ordinal + 1 <= n
     if (d->ord_bits == 0) d->ord_bits = 1;
-    while (d->rem_bits + d->ord_bits > 63) { // keep bit 63 of an entry spare: small dictionaries get more buckets
+    while (d->rem_bits + d->ord_bits > 62) { // keep bits 63 and 62 of an entry spare: small dictionaries get more buckets
         nb <<= 1;
         d->n_buckets = nb;
         d->bucket_bits = qk_bits_for(nb - 1);
@@ -369,12 +367,12 @@ static void qk_geometry(uint64_t n, uint32_t k, uint64_t stash_slots_min, qk_tab
     // dictionary-order extension arrays (k = 30 only: for other k the reference's canonical key
     // mixes a k-mer with a 30-base reverse complement, Q.c:415-420, and is not a walkable k-mer)
     d->has_ext = (k == 30 && getenv("QK_NO_EXT") == NULL) ? 1 : 0;
-    d->ext_bytes = d->has_ext ? ((n + 15) / 16 + 4) * sizeof(uint32_t) : 0;   // 2 bits per ordinal, padded
-    d->cont_bytes = d->has_ext ? ((n + 31) / 32 + 4) * sizeof(uint32_t) : 0;  // 1 bit per ordinal, padded
+    d->ext_bytes = d->has_ext ? ((n + 15) / 16 + 4) * QK_EXT_GROUP_WORDS * sizeof(uint32_t) : 0; // 5 bits per ordinal in groups of 16, padded
+    d->cont_bytes = 0;                                                        // (the continuation bits live in the same array)
 }
 
 // Geometry a dictionary of n k-mers will get, without a device: lets a host size the job
-// (table_bytes + stash_bytes + 2 x ext_bytes + cont_bytes + 4 (n + 1) bytes of counters).
+// (table_bytes + stash_bytes + ext_bytes + 4 (n + 1) bytes of counters).
 extern "C" int qk_table_geometry(uint64_t n_kmers, uint32_t k, qk_table_desc *desc)
 {
     if (!desc || n_kmers == 0 || n_kmers >= ((uint64_t)1 << 32) || k < 1 || k > 32) return QK_ERR_ARG;
@@ -389,20 +387,14 @@ static int qk_alloc_table(qk_ctx *ctx, const qk_table_desc *d)
     cudaFree(ctx->counters_buf[0]);
     cudaFree(ctx->counters_buf[1]);
     ctx->counters_buf[0] = ctx->counters_buf[1] = NULL;
-    cudaFree(ctx->ext_last);
-    cudaFree(ctx->ext_first);
-    cudaFree(ctx->ext_cont);
+    cudaFree(ctx->ext);
     ctx->buckets = NULL; ctx->stash = NULL; ctx->counters = NULL;
-    ctx->ext_last = ctx->ext_first = ctx->ext_cont = NULL;
+    ctx->ext = NULL;
     QK_CUDA(ctx, cudaMalloc((void **)&ctx->buckets, d->table_bytes));
     QK_CUDA(ctx, cudaMalloc((void **)&ctx->stash, d->stash_bytes));
     if (d->has_ext) {
-        QK_CUDA(ctx, cudaMalloc((void **)&ctx->ext_last, d->ext_bytes));
-        QK_CUDA(ctx, cudaMalloc((void **)&ctx->ext_first, d->ext_bytes));
-        QK_CUDA(ctx, cudaMalloc((void **)&ctx->ext_cont, d->cont_bytes));
-        QK_CUDA(ctx, cudaMemset(ctx->ext_last, 0, d->ext_bytes));
-        QK_CUDA(ctx, cudaMemset(ctx->ext_first, 0, d->ext_bytes));
-        QK_CUDA(ctx, cudaMemset(ctx->ext_cont, 0, d->cont_bytes));
+        QK_CUDA(ctx, cudaMalloc((void **)&ctx->ext, d->ext_bytes));
+        QK_CUDA(ctx, cudaMemset(ctx->ext, 0, d->ext_bytes));
     }
     QK_CUDA(ctx, cudaMalloc((void **)&ctx->counters_buf[0], (d->n_kmers + 1) * sizeof(uint32_t)));
     ctx->counters = ctx->counters_buf[0];
@@ -500,7 +492,7 @@ extern "C" int qk_dict_build(qk_ctx *ctx, uint64_t *n_kmers_out)
 
     for (int attempt = 0; attempt < 4; ++attempt) {
         qk_geometry(total, ctx->k, stash_min, &d);
-        if (d.rem_bits + d.ord_bits > 63 || d.ord_bits > 32) {
+        if (d.rem_bits + d.ord_bits > 62 || d.ord_bits > 32) {
             rc = qk_fail(ctx, QK_ERR_FORMAT, "entry needs %u bits", d.rem_bits + d.ord_bits);
             goto done;
         }
@@ -517,8 +509,7 @@ extern "C" int qk_dict_build(qk_ctx *ctx, uint64_t *n_kmers_out)
         bp.rem_bits = d.rem_bits;
         bp.ord_bits = d.ord_bits;
         const uint64_t n_blocks = (total + QK_EXT_BLOCK - 1) / QK_EXT_BLOCK;
-        qk_orient_insert_kernel<<<(unsigned)((n_blocks + 63) / 64), 64>>>(kbo, total, (int)d.has_ext, bp, ctx->ext_last,
-                                                                          ctx->ext_first, ctx->ext_cont, info);
+        qk_orient_insert_kernel<<<(unsigned)((n_blocks + 63) / 64), 64>>>(kbo, total, (int)d.has_ext, bp, ctx->ext, info);
         QK_TRY(cudaGetLastError());
         QK_TRY(cudaMemcpy(&hinfo, info, sizeof hinfo, cudaMemcpyDeviceToHost));
         if (!(hinfo.flags & QK_FLAG_STASH_FULL)) break;
@@ -563,9 +554,8 @@ extern "C" int qk_dict_adopt(qk_ctx *ctx, const qk_table_desc *desc)
     if (!ctx || !desc) return QK_ERR_ARG;
     if (desc->n_buckets == 0 || (desc->n_buckets & (desc->n_buckets - 1)) || desc->stash_slots == 0 ||
         (desc->stash_slots & (desc->stash_slots - 1)) || desc->table_bytes != desc->n_buckets * sizeof(qk_bucket) ||
-        desc->stash_bytes != desc->stash_slots * sizeof(qk_stash_entry) || desc->rem_bits + desc->ord_bits > 63 ||
-        desc->ord_bits > 32 || (desc->has_ext && (desc->k != 30 || desc->ext_bytes < (desc->n_kmers + 15) / 16 * 4 + 16 ||
-                                                  desc->cont_bytes < (desc->n_kmers + 31) / 32 * 4 + 16)) ||
+        desc->stash_bytes != desc->stash_slots * sizeof(qk_stash_entry) || desc->rem_bits + desc->ord_bits > 62 ||
+        desc->ord_bits > 32 || (desc->has_ext && (desc->k != 30 || desc->ext_bytes < ((desc->n_kmers + 15) / 16 + 4) * QK_EXT_GROUP_WORDS * 4)) ||
         desc->rem_bits + desc->bucket_bits != QK_KEY_BITS || desc->k < 1 || desc->k > 32)
         return qk_fail(ctx, QK_ERR_ARG, "inconsistent table descriptor");
     QK_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -581,9 +571,9 @@ extern "C" int qk_dict_ext_ptrs(const qk_ctx *ctx, void **last, void **first, vo
 {
     if (!ctx) return QK_ERR_ARG;
     if (ctx->dict_state != 2) return QK_ERR_STATE;
-    if (last) *last = ctx->ext_last;
-    if (first) *first = ctx->ext_first;
-    if (cont) *cont = ctx->ext_cont;
+    if (last) *last = ctx->ext;      /* one array since round 2: 12 bytes per 16 ordinals (last, first, continuation) */
+    if (first) *first = NULL;
+    if (cont) *cont = NULL;
     return QK_OK;
 }
 

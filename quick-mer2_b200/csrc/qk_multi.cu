@@ -146,9 +146,9 @@ extern "C" int qk_multi_replicate(qk_multi *m)
         qk_dict_device_ptrs(m->ctx[i], &p[0][i], &p[1][i]);
         qk_dict_ext_ptrs(m->ctx[i], &p[2][i], &p[3][i], &p[4][i]);
     }
-    const size_t bytes[5] = {d.table_bytes, d.stash_bytes, d.has_ext ? d.ext_bytes : 0, d.has_ext ? d.ext_bytes : 0,
-                             d.has_ext ? d.cont_bytes : 0};
+    const size_t bytes[5] = {d.table_bytes, d.stash_bytes, d.has_ext ? d.ext_bytes : 0, 0, 0}; // (one extension array)
     for (int a = 0; a < 5; ++a) {
+        if (!bytes[a]) continue;
         rc = qk_multi_bcast(m, p[a], bytes[a]);
         if (rc) return rc;
     }

@@ -153,7 +153,7 @@ int qk_count_main(int argc, char **argv)
          * -t N: framer threads in all / reader threads per GPU (0 = default). */
         const char *pol = getenv("QK_FRAMER");
         const long cpus = sysconf(_SC_NPROCESSORS_ONLN);
-        const int by_host = pol ? !strcmp(pol, "host") : cpus / (long)n_dev >= 6;
+        const int by_host = pol ? !strcmp(pol, "host") : cpus / (long)n_dev >= 12; /* measured: 12+ framer threads beat the link-bound device path */
         if (by_host) {
             qk_ctx *ctxs[QK_HOST_MAX_SLOTS];
             for (uint32_t i = 0; i < n_dev; ++i) ctxs[i] = qk_multi_ctx(m, i);

@@ -224,7 +224,7 @@ def test_table_geometry_invariants(n, k, qk):
     assert d.stash_slots & (d.stash_slots - 1) == 0 and d.stash_bytes == d.stash_slots * 16
     assert d.has_ext == (1 if k == 30 else 0)
     if d.has_ext:
-        assert d.ext_bytes >= (n + 15) // 16 * 4 + 16 and d.cont_bytes >= (n + 31) // 32 * 4 + 16
+        assert d.ext_bytes >= ((n + 15) // 16 + 4) * 12 and d.cont_bytes == 0
     else:
         assert d.ext_bytes == 0 and d.cont_bytes == 0
 
@@ -240,7 +240,7 @@ def test_human_scale_fits_one_gpu(qk):
     d = qk.TableDesc()
     n = 2_200_000_000
     qk.lib().qk_table_geometry(n, 30, C.byref(d))
-    resident = d.table_bytes + d.stash_bytes + 2 * d.ext_bytes + d.cont_bytes + 4 * (n + 1)
+    resident = d.table_bytes + d.stash_bytes + d.ext_bytes + d.cont_bytes + 4 * (n + 1)
     raw = (1 << 32) * 12                      # keys + chain while the chain is ranked
     kbo = 8 * (n + 1)                         # keys by ordinal while the table is filled
     assert max(raw + kbo, kbo + resident) < 170e9
