@@ -635,6 +635,314 @@ __global__ void __launch_bounds__(QK_THREADS, MINB) qk_count_ext_kernel(const qk
     }
 }
 
+// =============================================================================================
+// qk_count_ext32_kernel -- the walk carried over 32 positions per lane.
+//
+// What bounds the kernel at human scale is the number of random L2 -> DRAM requests (ncu: 37 G
+// requests/s = the rate of the random-sector micro-benchmark over a 32 GiB table), so the way to go
+// faster is to issue fewer: a lane owns 32 consecutive positions (two halves of 16); the second
+// half starts from the ordinal its first half's walk ENDED on -- no probe -- and walks 16 more
+// steps; only when the first half's walk did not reach its last position does the second half
+// probe an anchor of its own.  Where a read follows the dictionary that is one probe and two
+// extension-array reads per 32 k-mers instead of per 16.  Everything else is as in
+// qk_count_ext_kernel: warp-private 1 KiB sub-tiles, pooled probes for what the walks leave
+// open, position-parallel depth increments.
+#define QK_SUB2 1024
+#define QK_SUB2_WORDS (QK_SUB2 / 32)
+
+struct qk_warp_smem2 {
+    uint64_t codes[QK_SUB2_WORDS + 1]; // [0] = halo: the 32 bases before the sub-tile
+    uint32_t mask[QK_SUB2_WORDS + 1];  // reset flags; [0] = halo word
+    uint32_t pad;
+    uint32_t ord[QK_SUB2];             // ordinal + 1 per position (0 = no hit), rows of 32 swizzled by 16-byte column
+    uint16_t queue[QK_SUB2];           // positions that need a probe of their own
+};
+
+// where position idx of the sub-tile lives in ord[]: row = owning lane, 16-byte columns XOR-swizzled by the
+// row so that the lanes' uint4 stores (row stride 128 B) and the position-parallel reads are both conflict-free
+__device__ __forceinline__ uint32_t qk_ord_slot(uint32_t idx)
+{
+    const uint32_t row = idx >> 5, j = idx & 31;
+    return row * 32 + ((((j >> 2) ^ (row & 7)) << 2) | (j & 3));
+}
+
+// 16 two-bit fields starting at ordinal q (ordinal q in bits 1:0); which = 0: last base, 1: first base
+__device__ __forceinline__ uint32_t qk_extract32(const uint32_t *__restrict__ ext, uint64_t q, uint32_t which)
+{
+    const uint32_t *g = ext + (q >> 4) * QK_EXT_GROUP_WORDS + which;
+    return __funnelshift_r(__ldg(g), __ldg(g + QK_EXT_GROUP_WORDS), 2 * (uint32_t)(q & 15));
+}
+// 16 continuation bits starting at ordinal q
+__device__ __forceinline__ uint32_t qk_extract16(const uint32_t *__restrict__ ext, uint64_t q)
+{
+    const uint32_t *g = ext + (q >> 4) * QK_EXT_GROUP_WORDS + 2;
+    const uint32_t both = (__ldg(g) & 0xFFFFu) | (__ldg(g + QK_EXT_GROUP_WORDS) << 16);
+    return (both >> (uint32_t)(q & 15)) & 0xFFFFu;
+}
+
+// Walk from position ja (-1 = the position just before this half) with ordinal oa on strand `plus` over the
+// 16 positions of a half: c16 = their codes (first base in the top pair), resets16 = their reset flags.
+// Returns the positions (bits 0..15) whose k-mer is PROVEN to be dictionary ordinal oa +- (j - ja).
+__device__ __forceinline__ uint32_t qk_walk16(const qk_table_view &tv, uint64_t oa, bool plus, int ja, uint32_t c16, uint32_t resets16)
+{
+    const uint32_t nsteps = (uint32_t)(15 - ja);          // 0..16
+    if (nsteps == 0 || !(plus || oa >= 16)) return 0;
+    const uint32_t sh = (uint32_t)(ja + 1);               // 0..15
+    uint32_t R = qk_rev16pairs(c16) >> (2 * sh);          // read base of step i (position ja + i) in bits 2i-1 : 2i-2
+    uint32_t D, Cb;
+    if (plus) {
+        D = qk_extract32(tv.ext, oa + 1, 0);
+        Cb = qk_extract16(tv.ext, oa + 1);
+    } else {
+        D = qk_rev16pairs(qk_extract32(tv.ext, oa - 16, 1));
+        Cb = __brev(qk_extract16(tv.ext, oa - 15)) >> 16;
+        R ^= 0xAAAAAAAAu;
+    }
+    const uint32_t X = D ^ R;
+    const uint32_t mism = (X | (X >> 1)) & 0x55555555u;
+    uint32_t len = mism ? (uint32_t)(__ffs(mism) - 1) >> 1 : 16u;
+    const uint32_t brk = ~Cb & 0xFFFFu;
+    if (brk) len = min(len, (uint32_t)__ffs(brk) - 1);
+    const uint32_t rs = (resets16 & 0xFFFFu) >> sh;
+    if (rs) len = min(len, (uint32_t)__ffs(rs) - 1);
+    len = min(len, nsteps);
+    return ((1u << len) - 1) << sh;
+}
+
+template <int MINB, bool L64>
+__global__ void __launch_bounds__(QK_THREADS, MINB) qk_count_ext32_kernel(const qk_count_args a)
+{
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    qk_warp_smem2 *s_all = reinterpret_cast<qk_warp_smem2 *>(s_raw);
+    const uint32_t lane = threadIdx.x & 31;
+    qk_warp_smem2 &sm = s_all[threadIdx.x >> 5];
+    const uint32_t FULL = 0xffffffffu;
+
+    const uint32_t n = a.n_bytes;
+    const uint32_t n_subs = (n + QK_SUB2 - 1) / QK_SUB2;
+    const uint32_t subs_per_warp = max(1u, a.tiles_per_cta * (QK_TILE / QK_SUB2) / QK_WARPS);
+    const uint32_t sub0 = (blockIdx.x * QK_WARPS + (threadIdx.x >> 5)) * subs_per_warp;
+    if (sub0 >= n_subs) return;
+    const uint32_t sub_end = min(sub0 + subs_per_warp, n_subs);
+    const uint8_t *__restrict__ bytes = a.bytes;
+
+    // ---- span start: last reset before the span (for the 16-bit run counter), halo -------------
+    int carry_last;
+    uint64_t halo_c = 0;
+    uint32_t halo_m = 0xFFFFFFFFu; // before the chunk: as good as resets
+    {
+        int found = QK_NONE;
+        uint32_t pos = sub0 * QK_SUB2;
+        while (pos > 0 && found == QK_NONE) {
+            pos -= 512;
+            const uint32_t at = pos + lane * 16;
+            const uint32_t m = qk_resets16(qk_load16(bytes, at, n));
+            found = __reduce_max_sync(FULL, m ? (int)(at + 31 - __clz(m)) : QK_NONE);
+        }
+        carry_last = (found == QK_NONE) ? -1 : found;
+        const uint32_t base = sub0 * QK_SUB2;
+        if (base >= 32) {
+            const uint4 h0 = qk_load16(bytes, base - 32, n), h1 = qk_load16(bytes, base - 16, n);
+            halo_c = ((uint64_t)qk_codes16(h0) << 32) | qk_codes16(h1);
+            halo_m = qk_resets16(h0) | (qk_resets16(h1) << 16);
+        }
+    }
+
+    const qk_table_view tv = a.tv;
+    const uint32_t ord_mask = tv.ord_bits >= 32 ? 0xFFFFFFFFu : (1u << tv.ord_bits) - 1;
+    uint32_t n_emit = 0, n_hit = 0, n_ext = 0, n_probe = 0, n_walk = 0;
+
+    auto key_at = [&](uint32_t idx, bool *is_fwd) -> uint64_t { // canonical 30-mer ending at position idx of the sub-tile
+        const uint64_t A = sm.codes[idx >> 5], B = sm.codes[(idx >> 5) + 1];
+        const uint32_t sh = 2 * (31 - (idx & 31));
+        const uint64_t x = ((B >> sh) | ((A << 1) << (63 - sh))) & QK_M60;
+        const uint64_t rc = (qk_rev_pairs(x) >> 4) ^ 0x0AAAAAAAAAAAAAAAull;
+        *is_fwd = x <= rc;
+        return min(x, rc);
+    };
+
+    // the warp loads 1 KiB as two fully coalesced 512-byte rows; ownership (32 contiguous positions per lane)
+    // is taken from shared memory afterwards
+    uint4 cur0 = qk_load16(bytes, sub0 * QK_SUB2 + lane * 16, n), cur1 = qk_load16(bytes, sub0 * QK_SUB2 + 512 + lane * 16, n);
+    for (uint32_t sub = sub0; sub < sub_end; ++sub) {
+        const uint32_t base = sub * QK_SUB2;
+        __syncwarp(); // everybody is done reading the previous sub-tile
+        {
+            uint32_t *c32 = reinterpret_cast<uint32_t *>(sm.codes);
+            uint16_t *m16 = reinterpret_cast<uint16_t *>(sm.mask);
+            const uint32_t r0 = qk_resets16(cur0), r1 = qk_resets16(cur1);
+            c32[2 + (lane ^ 1)] = qk_codes16(cur0);            // first base of a 32-base word in its top pair
+            c32[2 + 32 + (lane ^ 1)] = qk_codes16(cur1);
+            m16[2 + lane] = (uint16_t)r0;
+            m16[2 + 32 + lane] = (uint16_t)r1;
+            if (lane == 0) {
+                sm.codes[0] = halo_c;
+                sm.mask[0] = halo_m;
+            }
+            // last reset seen so far, for the next sub-tile
+            const int own0 = r0 ? (int)(base + 16 * lane + 31 - __clz(r0)) : QK_NONE;
+            const int own1 = r1 ? (int)(base + 512 + 16 * lane + 31 - __clz(r1)) : QK_NONE;
+            const int seen = __reduce_max_sync(FULL, max(own0, own1));
+            if (sub + 1 < sub_end) {
+                cur0 = qk_load16(bytes, base + QK_SUB2 + lane * 16, n); // prefetch
+                cur1 = qk_load16(bytes, base + QK_SUB2 + 512 + lane * 16, n);
+            }
+            __syncwarp();
+            // ---- which of my 32 positions end a 30-mer: no reset among the 30 bytes ending there ----
+            const uint32_t my_mask = sm.mask[lane + 1];
+            const uint64_t M64 = ((uint64_t)my_mask << 32) | sm.mask[lane];
+            uint64_t S = M64 | (M64 << 1);
+            S |= S << 2; S |= S << 4; S |= S << 8; S |= S << 14; // bit p: a reset in [p-29, p]
+            uint32_t emit = ~(uint32_t)(S >> 32);
+            const uint32_t p0 = base + 32 * lane;
+            if (emit && p0 + 31 - (uint32_t)carry_last >= 65536u) {
+                // uint16 cur_chars (Q.c:402): a position whose run length mod 65,536 is below k emits nothing.
+                // Only lines longer than 65 k get here: find the exact last reset before p0.
+                int last0 = carry_last;
+                for (int ww = (int)lane - 1; ww >= 0 && last0 == carry_last; --ww) {
+                    const uint32_t m = sm.mask[ww + 1];
+                    if (m) last0 = (int)(base + ww * 32 + 31 - __clz(m));
+                }
+                const uint32_t run0 = (uint32_t)((int)p0 - last0);
+                for (uint32_t j = 0; j < 32; ++j)   // (a reset inside my own word restarts the run: no wrap there)
+                    if (!(my_mask & ((2u << j) - 1)) && ((run0 + j) & 0xFFFFu) < 30u) emit &= ~(1u << j);
+            }
+            carry_last = max(carry_last, seen);
+            n_emit += __popc(emit);
+
+            const uint64_t W = sm.codes[lane + 1];      // my 32 bases
+            uint32_t verified = 0, anchors = 0;
+            // ---- first half: anchor = my first emitting position; walk the dictionary order from it -------
+            uint32_t e0 = emit & 0xFFFFu, e1 = emit >> 16;
+            uint64_t end_ord = 0;       // ordinal of position 15 when the first half's walk (or anchor) settled it
+            bool end_known = false, end_plus = false;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const uint32_t eh = half ? e1 : e0;
+                const uint32_t c16 = half ? (uint32_t)W : (uint32_t)(W >> 32);
+                const uint32_t r16 = (my_mask >> (16 * half)) & 0xFFFFu;
+                int ja = -1;
+                uint32_t a_ord1 = 0;
+                uint64_t oa = 0;
+                bool plus = true;
+                if (half == 1 && end_known) {               // carry on from where the first half ended: no probe
+                    oa = end_ord;
+                    plus = end_plus;
+                    a_ord1 = 1;                             // (only "known" matters below)
+                } else if (eh) {
+                    ja = __ffs(eh) - 1;
+                    bool a_fwd = false;
+                    uint32_t a_strand = 0;
+                    const qk_probe ap = qk_probe_prepare(tv, key_at(32 * lane + 16 * half + ja, &a_fwd));
+                    const qk_bucket abk = L64 ? qk_ld_bucket64(ap.bp) : qk_ld_bucket(ap.bp);
+                    a_ord1 = qk_probe_resolve(tv, ap, abk, ord_mask, &a_strand);
+                    ++n_probe;
+                    anchors |= 1u << (16 * half + ja);
+                    oa = a_ord1 ? a_ord1 - 1 : 0;
+                    plus = (a_strand != 0) == a_fwd;
+                }
+                uint32_t ve = 0;
+                if (a_ord1 && eh) {
+                    ve = qk_walk16(tv, oa, plus, ja, c16, r16) & eh;
+                    n_walk += ja < 15;
+                }
+                n_ext += __popc(ve);
+                verified |= ve << (16 * half);
+                {   // ordinal + 1 of the 16 positions of this half as far as known now
+                    uint32_t o[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int step = j - ja;
+                        const uint32_t walked = (uint32_t)(plus ? oa + step : oa - step) + 1;
+                        o[j] = (ve >> j) & 1u ? walked : (j == ja ? a_ord1 : 0u);
+                    }
+#pragma unroll
+                    for (int v = 0; v < 4; ++v)
+                        *reinterpret_cast<uint4 *>(sm.ord + lane * 32 + (((4 * half + v) ^ (lane & 7)) << 2)) =
+                            make_uint4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
+                    if (half == 0) {
+                        end_known = (e0 >> 15) & 1u && o[15] != 0;
+                        end_plus = plus;
+                        end_ord = (uint64_t)o[15] - 1;
+                    }
+                }
+            }
+
+            // ---- positions the walks could not settle: pool them over the warp ------------------------
+            uint32_t todo = emit & ~verified & ~anchors;
+            const uint32_t cnt = __popc(todo);
+            n_probe += cnt;
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t up = __shfl_up_sync(FULL, incl, o);
+                if (lane >= (uint32_t)o) incl += up;
+            }
+            const uint32_t total = __shfl_sync(FULL, incl, 31);
+            {
+                uint32_t off = incl - cnt;
+                while (todo) {
+                    sm.queue[off++] = (uint16_t)(32 * lane + __ffs(todo) - 1);
+                    todo &= todo - 1;
+                }
+            }
+            __syncwarp();
+            for (uint32_t q0 = 0; q0 < total; q0 += 32 * QK_POOL_UNROLL) {
+                qk_probe pr[QK_POOL_UNROLL];
+                qk_bucket bk[QK_POOL_UNROLL];
+                uint32_t idx[QK_POOL_UNROLL];
+                bool on[QK_POOL_UNROLL];
+#pragma unroll
+                for (int u = 0; u < QK_POOL_UNROLL; ++u) {
+                    const uint32_t e = q0 + 32 * u + lane;
+                    on[u] = e < total;
+                    idx[u] = on[u] ? sm.queue[e] : 0;
+                    bool f;
+                    pr[u] = qk_probe_prepare(tv, key_at(idx[u], &f));
+                    bk[u].e[0] = bk[u].e[1] = bk[u].e[2] = bk[u].e[3] = 0;
+                }
+#pragma unroll
+                for (int u = 0; u < QK_POOL_UNROLL; ++u)
+                    if (on[u]) bk[u] = L64 ? qk_ld_bucket64(pr[u].bp) : qk_ld_bucket(pr[u].bp);
+#pragma unroll
+                for (int u = 0; u < QK_POOL_UNROLL; ++u) {
+                    if (!on[u]) continue;
+                    uint32_t st;
+                    sm.ord[qk_ord_slot(idx[u])] = qk_probe_resolve(tv, pr[u], bk[u], ord_mask, &st);
+                }
+            }
+            __syncwarp();
+
+            // ---- depth increments, position-parallel: consecutive lanes, consecutive counters --------
+#pragma unroll 4
+            for (uint32_t it = 0; it < QK_SUB2 / 32; ++it) {
+                const uint32_t o1 = sm.ord[it * 32 + ((((lane >> 2) ^ (it & 7)) << 2) | (lane & 3))];
+                if (o1) {
+                    ++n_hit;
+                    atomicAdd(a.counters + (o1 - 1), 1u);
+                }
+            }
+            halo_c = sm.codes[QK_SUB2_WORDS];
+            halo_m = sm.mask[QK_SUB2_WORDS];
+        }
+    }
+
+    for (int o = 16; o; o >>= 1) {
+        n_emit += __shfl_xor_sync(FULL, n_emit, o);
+        n_hit += __shfl_xor_sync(FULL, n_hit, o);
+        n_ext += __shfl_xor_sync(FULL, n_ext, o);
+        n_probe += __shfl_xor_sync(FULL, n_probe, o);
+        n_walk += __shfl_xor_sync(FULL, n_walk, o);
+    }
+    if (lane == 0) {
+        atomicAdd(a.stats + 0, (unsigned long long)n_emit);
+        atomicAdd(a.stats + 1, (unsigned long long)n_hit);
+        atomicAdd(a.stats + 2, (unsigned long long)n_ext);
+        atomicAdd(a.stats + 4, (unsigned long long)n_probe);
+        atomicAdd(a.stats + 6, (unsigned long long)n_walk);
+    }
+}
+
 static int qk_table_view_of(qk_ctx *ctx, qk_table_view *tv)
 {
     if (ctx->dict_state != 2) return qk_fail(ctx, QK_ERR_STATE, "no dictionary built on this context");
@@ -670,7 +978,8 @@ int qk_launch_count(qk_ctx *ctx, qk_slot *sl, const uint8_t *dev_bytes, size_t n
     uint32_t target_ctas = (uint32_t)ctx->sm_count * (a.tv.ext ? 8 : 12);
     uint32_t tpc = (a.n_tiles + target_ctas - 1) / target_ctas;
     if (tpc < 4) tpc = 4;
-    if (tiles_env > 0) tpc = (uint32_t)tiles_env;
+    tpc = (tpc + 1) & ~1u;       // whole 1 KiB sub-tiles per warp (8 warps per CTA, 4 KiB tiles)
+    if (tiles_env > 0) tpc = ((uint32_t)tiles_env + 1) & ~1u;
     a.tiles_per_cta = tpc;
     a.counters = ctx->counters;
     a.stats = ctx->stats;
@@ -683,7 +992,19 @@ int qk_launch_count(qk_ctx *ctx, qk_slot *sl, const uint8_t *dev_bytes, size_t n
     if (classic < 0) classic = getenv("QK_CLASSIC_KERNEL") != NULL;
     static int plain_loads = -1; // QK_EXT_PLAIN_LOADS=1: bucket loads without the .L2::64B hint (A/B knob, -2 %)
     if (plain_loads < 0) plain_loads = getenv("QK_EXT_PLAIN_LOADS") != NULL;
-    if (a.tv.ext && !classic) {
+    static int run16 = -1;       // QK_EXT_RUN16=1: the 16-positions-per-lane walk (A/B knob)
+    if (run16 < 0) run16 = getenv("QK_EXT_RUN16") != NULL;
+    if (a.tv.ext && !classic && !run16) {
+        const size_t smem = QK_WARPS * sizeof(qk_warp_smem2);
+        static int attr_set[64];
+        if (ctx->device < 64 && !attr_set[ctx->device]) {
+            QK_CUDA(ctx, cudaFuncSetAttribute(qk_count_ext32_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            QK_CUDA(ctx, cudaFuncSetAttribute(qk_count_ext32_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set[ctx->device] = 1;
+        }
+        if (plain_loads) qk_count_ext32_kernel<4, false><<<grid, QK_THREADS, smem, sl->stream>>>(a);
+        else qk_count_ext32_kernel<4, true><<<grid, QK_THREADS, smem, sl->stream>>>(a);
+    } else if (a.tv.ext && !classic) {
         // 4 CTAs/SM at 64 registers: 5 and 6 CTAs/SM spill and measured 2-5 % slower (profiles/README.md)
         if (plain_loads) qk_count_ext_kernel<4, false><<<grid, QK_THREADS, 0, sl->stream>>>(a);
         else qk_count_ext_kernel<4, true><<<grid, QK_THREADS, 0, sl->stream>>>(a);

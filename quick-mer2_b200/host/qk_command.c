@@ -29,6 +29,8 @@ typedef struct {
     char path[65536];
     uint64_t n;
     uint16_t *data;      /* n entries, zero where the file is short; NULL if the allocation failed */
+    uint64_t got;        /* entries really read */
+    uint64_t big_bins;   /* entries whose GC bin is beyond the 401 the curve has */
     int opened;
 } qgc_prefetch;
 
@@ -38,9 +40,9 @@ static void *qgc_reader(void *arg)
     j->data = calloc(j->n ? j->n : 1, sizeof(uint16_t));
     FILE *f = j->data ? fopen(j->path, "rb") : NULL;
     if (f) {
-        size_t got = fread(j->data, sizeof(uint16_t), j->n, f);
-        (void)got;
+        j->got = fread(j->data, sizeof(uint16_t), j->n, f);
         fclose(f);
+        for (uint64_t i = 0; i < j->got; ++i) j->big_bins += (j->data[i] & 0x1FFu) >= QK_GC_BINS;
     }
     return NULL;
 }
@@ -201,6 +203,14 @@ int qk_count_main(int argc, char **argv)
         pthread_join(qgc_thread, NULL);                 /* the .qgc was read while the reads were counted */
         uint16_t *qgc = qgc_job.data;
         if (!qgc) { puts("Memory allocation failed"); qk_multi_destroy(m); return 1; }
+        /* Inputs on which the reference itself is undefined (it reuses stale buffer contents for a short
+         * .qgc and indexes past its 401 bins, Q.c:499-508): handled deterministically here, and said aloud. */
+        if (qgc_job.got < n_kmers)
+            fprintf(stderr, "quicKmer2_b200: %s holds %llu entries, the dictionary %llu: the missing ones are taken as non-control\n",
+                    path, (unsigned long long)qgc_job.got, (unsigned long long)n_kmers);
+        if (qgc_job.big_bins)
+            fprintf(stderr, "quicKmer2_b200: %s has %llu entries with a GC bin above 400: ignored in the curve\n", path,
+                    (unsigned long long)qgc_job.big_bins);
         uint64_t sum[QK_GC_BINS], cnt[QK_GC_BINS];
         int64_t sq[QK_GC_BINS];
         rc = qk_gc_curve(ctx, qgc, n_kmers, sum, sq, cnt);

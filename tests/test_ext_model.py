@@ -1,4 +1,4 @@
-"""The dictionary-order walk of qk_count_ext_kernel, restated in Python for ANY k and checked
+"""The dictionary-order walk of qk_count_ext32_kernel, restated in Python for ANY k and checked
 against a plain key -> ordinal lookup on adversarial inputs (CPU only).
 
 The CUDA kernel only exists for k = 30, where coincidences are astronomically rare.  The
@@ -9,8 +9,9 @@ orientations occur all the time.  If the walk ever assigned an ordinal that the 
 lookup does not, the identities the kernel relies on would be wrong.
 
 Mirrors quick-mer2_b200/csrc/qk_dict.cu (qk_orient_insert_kernel) and qk_count.cu
-(qk_count_ext_kernel): block-wise orientation with look-ahead at run starts, cont / last /
-first / strand per ordinal, one anchor per run of 16 positions, steps checked in order.
+(qk_count_ext32_kernel): block-wise orientation with look-ahead at run starts, cont / last /
+first / strand per ordinal, one anchor per lane of 32 positions (the second half of 16 carries on
+from where the first half's walk ended), steps checked in order.
 """
 import numpy as np
 import pytest
@@ -85,43 +86,59 @@ def orient(keys, k):
 
 
 def walk_counts(read_codes, keys, k, lookup, cont, last, first, strand):
-    """Ordinal per emitting position the way the kernel derives it; also how many came from the walk."""
+    """Ordinal per emitting position the way qk_count_ext32_kernel derives it; also how many came from
+    the walk.  A lane owns 32 positions = two halves of 16: the first half probes an anchor (its first
+    emitting position) and walks; the second half carries on from the ordinal position 15 was settled
+    with -- no probe -- and only probes an anchor of its own when position 15 was not settled."""
     stream = canonical_stream(read_codes, k)
     n = len(keys)
-    got, walked = {}, 0
-    for base in range(0, len(read_codes), RUN):
-        run = [p for p in range(base, min(base + RUN, len(read_codes))) if stream[p] is not None]
-        if not run:
-            continue
-        ja = run[0]
-        key, is_fwd, _ = stream[ja]
-        oa = lookup.get(key)
-        verified = {}
-        if oa is not None:
-            plus = bool(strand[oa]) == is_fwd
-            o = oa
-            for p in range(ja + 1, min(base + RUN, len(read_codes))):
-                b = read_codes[p]
-                if plus:
-                    if o + 1 >= n or not cont[o + 1] or last[o + 1] != b:
-                        break
-                    o += 1
-                else:
-                    if o - 1 < 0 or not cont[o] or first[o - 1] != (b ^ 2):
-                        break
-                    o -= 1
-                verified[p] = o
-        for p in run:
-            if p == ja:
-                if oa is not None:
-                    got[p] = oa
-            elif p in verified:
-                got[p] = verified[p]
-                walked += 1
+    got, walked, probes = {}, 0, 0
+    L = len(read_codes)
+    for base in range(0, L, 2 * RUN):
+        end = None                                   # (ordinal, plus) of position base + 15, when settled
+        for half in (0, 1):
+            hb = base + RUN * half
+            run = [p for p in range(hb, min(hb + RUN, L)) if stream[p] is not None]
+            if not run:
+                continue
+            settled, probed_anchor = {}, None
+            if half == 1 and end is not None:
+                ja, (oa, plus) = hb - 1, end
             else:
-                o = lookup.get(stream[p][0])
-                if o is not None:
-                    got[p] = o
+                ja = run[0]
+                key, is_fwd, _ = stream[ja]
+                oa = lookup.get(key)
+                probes += 1
+                probed_anchor = ja
+                if oa is not None:
+                    plus = bool(strand[oa]) == is_fwd
+                    settled[ja] = oa
+            if oa is not None:
+                o = oa
+                for p in range(ja + 1, min(hb + RUN, L)):
+                    b = read_codes[p]
+                    if plus:
+                        if o + 1 >= n or not cont[o + 1] or last[o + 1] != b:
+                            break
+                        o += 1
+                    else:
+                        if o - 1 < 0 or not cont[o] or first[o - 1] != (b ^ 2):
+                            break
+                        o -= 1
+                    if stream[p] is not None:
+                        settled[p] = o
+                        walked += 1
+            for p in run:
+                if p in settled:
+                    got[p] = settled[p]
+                elif p != probed_anchor:
+                    o = lookup.get(stream[p][0])     # pooled probe
+                    probes += 1
+                    if o is not None:
+                        got[p] = o
+            if half == 0:
+                last_p = hb + RUN - 1
+                end = (settled[last_p], plus) if last_p in settled else None
     return got, walked
 
 
