@@ -785,7 +785,9 @@ def gpu_arm(args):
 
     cpus = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     framer_threads = args.framer_threads or max(1, cpus // max(1, world))
-    host_framing = args.framer == "host" or (args.framer == "auto" and framer_threads >= 12)   # measured: profiles/README.md
+    # auto: the host frames FASTQ when it has the cores (it halves the bytes on the link); FASTA gains nothing from it
+    is_fastq = w["fastq"]
+    host_framing = args.framer == "host" or (args.framer == "auto" and framer_threads >= 12 and is_fastq)   # measured: profiles/README.md
 
     def job_raw_device():
         ctx.reset()
@@ -902,12 +904,18 @@ def gpu_arm(args):
             job(); finish_step()
         barrier()
         t0 = time.perf_counter()
+        marks = []
         for _ in range(steps):
             job(); finish_step()
+            marks.append(time.perf_counter())
             if rank == 0:
                 ctx.finish(result_np)             # D2H of the step's result: uint16 depths in .bin order (pinned)
+            marks.append(time.perf_counter())
         barrier()
         dt = all_max(time.perf_counter() - t0)
+        if rank == 0:
+            log(f"{job.__name__}: per step [count ms, result D2H ms] = "
+                + str([round(1e3 * (b - a), 1) for a, b in zip([t0] + marks[:-1], marks)]))
         (k,) = all_sum([ctx.stats()["total_kmers"]])
         return dt / steps, k
 

@@ -155,7 +155,15 @@ int qk_count_main(int argc, char **argv)
          * -t N: framer threads in all / reader threads per GPU (0 = default). */
         const char *pol = getenv("QK_FRAMER");
         const long cpus = sysconf(_SC_NPROCESSORS_ONLN);
-        const int by_host = pol ? !strcmp(pol, "host") : cpus / (long)n_dev >= 12; /* measured: 12+ framer threads beat the link-bound device path */
+        /* measured: 12+ framer threads beat the link-bound device path on FASTQ (half the bytes to ship);
+         * FASTA is nearly all sequence already, shipping it raw costs the host nothing */
+        int by_host = pol ? !strcmp(pol, "host") : cpus / (long)n_dev >= 12;
+        if (!pol && by_host) {
+            int fd0 = open(reads, O_RDONLY);
+            char c0 = 0;
+            if (fd0 < 0 || read(fd0, &c0, 1) != 1 || c0 != '@') by_host = 0;
+            if (fd0 >= 0) close(fd0);
+        }
         if (by_host) {
             qk_ctx *ctxs[QK_HOST_MAX_SLOTS];
             for (uint32_t i = 0; i < n_dev; ++i) ctxs[i] = qk_multi_ctx(m, i);
