@@ -1133,7 +1133,7 @@ __global__ void qk_narrow_kernel(const uint32_t *__restrict__ counters, uint16_t
 // D2H of the depths, piece by piece: narrow on the device, copy into one of two pinned staging
 // buffers, hand the piece to the consumer while the next one is in flight (a direct pageable
 // cudaMemcpy runs at a few GB/s).  qk_finish with a pinned destination skips the staging.
-#define QK_FINISH_PIECE ((uint64_t)4 << 20) // entries per staged piece (8 MiB)
+#define QK_FINISH_PIECE ((uint64_t)16 << 20) // entries per staged piece (32 MiB)
 extern "C" int qk_finish_pieces(qk_ctx *ctx, qk_piece_fn consume, void *user)
 {
     if (!ctx || !consume) return QK_ERR_ARG;
