@@ -13,10 +13,7 @@
  * Threading: one submitting thread per context (the reference has exactly one producer,
  * Q.c:397-456); qk_wait_slot and qk_slot_host_buffer may be called from other threads (the
  * host's reader threads fill slot buffers that way).  One context drives one GPU.
- *
- * Measured, cause not established (profiles/README.md): count kernels run 6-7 % faster when the
- * context is the first thing in the process to allocate CUDA memory -- create it before other
- * libraries (NCCL, a tensor framework) allocate.
+
  */
 #ifndef QUICKMER2_B200_H
 #define QUICKMER2_B200_H
