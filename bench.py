@@ -155,7 +155,8 @@ def cache_dir(arg):
     if arg:
         d = Path(arg)
     else:
-        base = Path("/dev/shm") if Path("/dev/shm").is_dir() and shutil.disk_usage("/dev/shm").free > 48 << 30 else Path("/tmp")
+        # the human-scale dictionary files need ~60 GB (tmpfs counts against RAM: ask for headroom)
+        base = Path("/dev/shm") if Path("/dev/shm").is_dir() and shutil.disk_usage("/dev/shm").free > 100 << 30 else Path("/tmp")
         d = base / "qk_bench_cache"
     d.mkdir(parents=True, exist_ok=True)
     return d
