@@ -92,7 +92,8 @@ typedef struct qk_table_desc {
                                 shadowed duplicates; their ordinals stay 0       */
     uint64_t ext_bytes;      /* bytes of the dictionary-order extension array: 12 bytes per 16 ordinals */
     uint64_t cont_bytes;     /* 0 (the continuation bits live in the same array)  */
-    uint32_t has_ext;        /* 1: dictionary-order extension arrays present (k = 30) */
+    uint32_t has_ext;        /* dictionary-order extension array: 0 none, 1 canonical 30-mers (k = 30),
+                                2 forward k-mers (k < 30), 3 30-base reverse complements (k = 31) */
     uint32_t reserved;
 } qk_table_desc;
 
@@ -186,6 +187,13 @@ int qk_counters_download(qk_ctx *ctx, uint64_t offset, uint32_t *out, uint64_t c
  * chain, already in .bin order, wrapped to 16 bits exactly as uint16_t Kmer_depth does.
  */
 int qk_finish(qk_ctx *ctx, uint16_t *counts_out, uint64_t n_kmers);
+/* The same without blocking: the download of the counter buffer selected at the time of the call is
+ * enqueued after everything submitted so far; the caller then selects the other counter buffer
+ * (qk_counters_select) and counts the next sample while this one's depths travel.  counts_out must be
+ * page-locked; it is complete when qk_finish_wait returns.  The buffer being downloaded must not be reset
+ * or counted into before that. */
+int qk_finish_async(qk_ctx *ctx, uint16_t *counts_out, uint64_t n_kmers);
+int qk_finish_wait(qk_ctx *ctx);
 /* The same in pieces, in order, without a full-size host array: `consume` gets `count` depths
  * starting at .bin index `offset` (pinned memory, valid until it returns; non-zero aborts) while
  * the next piece is still on its way -- e.g. to write the .bin as it arrives (Q.c:510-513

@@ -128,6 +128,8 @@ SIGNATURES = {
     "qk_counters_download": (C.c_int, [_P, C.c_uint64, _P, C.c_uint64]),
     "qk_finish": (C.c_int, [_P, _P, C.c_uint64]),
     "qk_finish_pieces": (C.c_int, [_P, _P, _P]),
+    "qk_finish_async": (C.c_int, [_P, _P, C.c_uint64]),
+    "qk_finish_wait": (C.c_int, [_P]),
     "qk_gc_curve": (C.c_int, [_P, _P, C.c_uint64, _P, _P, _P]),
     "qk_timing": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), _U64P]),
     "qk_span_begin": (C.c_int, [_P]),
@@ -388,6 +390,14 @@ class Context:
         assert out.dtype == np.uint16 and out.size == self.n_kmers and out.flags.c_contiguous
         self._check(self._lib.qk_finish(self._h, _np_ptr(out), self.n_kmers))
         return out
+
+    def finish_async(self, out: np.ndarray):
+        """Enqueue the download of the selected counter buffer into page-locked `out`; finish_wait() completes it."""
+        assert out.dtype == np.uint16 and out.size == self.n_kmers and out.flags.c_contiguous
+        self._check(self._lib.qk_finish_async(self._h, _np_ptr(out), self.n_kmers))
+
+    def finish_wait(self):
+        self._check(self._lib.qk_finish_wait(self._h))
 
     def write_bin(self, path):
         """Depths straight from the device to a .bin file, piece by piece."""

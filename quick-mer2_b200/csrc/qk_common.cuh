@@ -91,6 +91,9 @@ struct qk_ctx {
     uint64_t launches;
     cudaEvent_t span_a, span_b, span_join;
     uint16_t *narrow_dev, *narrow_host; // qk_finish staging (device / pinned), allocated on first use
+    cudaStream_t finish_stream;         // qk_finish_async: the result download runs here, beside the slot streams
+    cudaEvent_t finish_done;
+    int finish_pending;
 
     // device-side record framing (qk_frame.cu)
     unsigned long long *frame_stream;   // device: [0] FSM state, [1] read lines, [2] bases, [3] raw lines

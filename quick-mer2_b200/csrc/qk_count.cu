@@ -680,17 +680,33 @@ __device__ __forceinline__ uint32_t qk_extract16(const uint32_t *__restrict__ ex
     return (both >> (uint32_t)(q & 15)) & 0xFFFFu;
 }
 
-// Walk from position ja (-1 = the position just before this half) with ordinal oa on strand `plus` over the
-// 16 positions of a half: c16 = their codes (first base in the top pair), resets16 = their reset flags.
-// Returns the positions (bits 0..15) whose k-mer is PROVEN to be dictionary ordinal oa +- (j - ja).
-__device__ __forceinline__ uint32_t qk_walk16(const qk_table_view &tv, uint64_t oa, bool plus, int ja, uint32_t c16, uint32_t resets16)
+// Walk from position ja (-1 = the position just before this half) with ordinal oa over the 16 positions of a
+// half: c16 = their codes (first base in the top pair), resets16 = their reset flags.  Returns the positions
+// (bits 0..15) whose k-mer is PROVEN to be dictionary ordinal oa +- (j - ja).
+//   MODE 0 (k = 30, canonical 30-mers): on strand `plus` ordinals go up and the read base is compared with the last
+//          base of the next dictionary k-mer; on the other strand they go down and its complement is compared with
+//          the first base of the previous one.
+//   MODE 1 (k < 30, keys = forward k-mers): ordinals go up, read base against the last base of the next key.
+//   MODE 2 (k = 31, keys = 30-base reverse complements): ordinals go up, complemented read base against the TOP
+//          base of the next key.
+// In modes 1 and 2 the reference's key is min(forward k-mer, 30-base reverse complement) (Q.c:415-420): the walk
+// may only step onto a position whose key is certainly of the chain's type -- unc16 flags (even bit of each pair,
+// first position in the top pair) the positions where the read itself cannot settle that; they end the walk and
+// are probed like any other open position.
+template <int MODE>
+__device__ __forceinline__ uint32_t qk_walk16(const qk_table_view &tv, uint64_t oa, bool plus, int ja, uint32_t c16, uint32_t resets16,
+                                              uint32_t unc16)
 {
     const uint32_t nsteps = (uint32_t)(15 - ja);          // 0..16
     if (nsteps == 0 || !(plus || oa >= 16)) return 0;
     const uint32_t sh = (uint32_t)(ja + 1);               // 0..15
     uint32_t R = qk_rev16pairs(c16) >> (2 * sh);          // read base of step i (position ja + i) in bits 2i-1 : 2i-2
     uint32_t D, Cb;
-    if (plus) {
+    if (MODE == 2) {
+        D = qk_extract32(tv.ext, oa + 1, 1);
+        Cb = qk_extract16(tv.ext, oa + 1);
+        R ^= 0xAAAAAAAAu;
+    } else if (MODE == 1 || plus) {
         D = qk_extract32(tv.ext, oa + 1, 0);
         Cb = qk_extract16(tv.ext, oa + 1);
     } else {
@@ -705,11 +721,15 @@ __device__ __forceinline__ uint32_t qk_walk16(const qk_table_view &tv, uint64_t 
     if (brk) len = min(len, (uint32_t)__ffs(brk) - 1);
     const uint32_t rs = (resets16 & 0xFFFFu) >> sh;
     if (rs) len = min(len, (uint32_t)__ffs(rs) - 1);
+    if (MODE != 0) {
+        const uint32_t U = (qk_rev16pairs(unc16) >> (2 * sh)) & 0x55555555u;
+        if (U) len = min(len, (uint32_t)(__ffs(U) - 1) >> 1);
+    }
     len = min(len, nsteps);
     return ((1u << len) - 1) << sh;
 }
 
-template <int MINB, bool L64>
+template <int MINB, bool L64, int MODE>
 __global__ void __launch_bounds__(QK_THREADS, MINB) qk_count_ext32_kernel(const qk_count_args a)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -752,13 +772,26 @@ __global__ void __launch_bounds__(QK_THREADS, MINB) qk_count_ext32_kernel(const 
     const uint32_t ord_mask = tv.ord_bits >= 32 ? 0xFFFFFFFFu : (1u << tv.ord_bits) - 1;
     uint32_t n_emit = 0, n_hit = 0, n_ext = 0, n_probe = 0, n_walk = 0;
 
-    auto key_at = [&](uint32_t idx, bool *is_fwd) -> uint64_t { // canonical 30-mer ending at position idx of the sub-tile
+    const uint32_t k = tv.k;
+    // key of the k-mer ending at position idx of the sub-tile (Q.c:412-420); *is_fwd = it is the forward k-mer
+    auto key_at = [&](uint32_t idx, bool *is_fwd) -> uint64_t {
         const uint64_t A = sm.codes[idx >> 5], B = sm.codes[(idx >> 5) + 1];
         const uint32_t sh = 2 * (31 - (idx & 31));
-        const uint64_t x = ((B >> sh) | ((A << 1) << (63 - sh))) & QK_M60;
-        const uint64_t rc = (qk_rev_pairs(x) >> 4) ^ 0x0AAAAAAAAAAAAAAAull;
-        *is_fwd = x <= rc;
-        return min(x, rc);
+        const uint64_t x32 = (B >> sh) | ((A << 1) << (63 - sh));   // the 32 bases ending at idx
+        uint64_t rc = (qk_rev_pairs(x32 & QK_M60) >> 4) ^ 0x0AAAAAAAAAAAAAAAull;
+        if (MODE == 0) {
+            const uint64_t x = x32 & QK_M60;
+            *is_fwd = x <= rc;
+            return min(x, rc);
+        }
+        if (MODE == 1) {   // k < 30: the register holds min(run length, 30) bases, zero-filled below (Q.c:414-416)
+            const uint64_t M = ((uint64_t)sm.mask[(idx >> 5) + 1] << 32) | sm.mask[idx >> 5];
+            const uint32_t win = (uint32_t)(M >> ((idx & 31) + 3)) & 0x3FFFFFFFu;   // reset flags of the 30 bytes ending at idx
+            if (win) rc &= ~(((uint64_t)1 << (2 * (32 - __clz(win)) )) - 1);        // run = 29 - top flag: keep the top `run` bases
+        }
+        const uint64_t f = x32 & tv.kmask;
+        *is_fwd = f <= rc;
+        return min(f, rc);
     };
 
     // the warp loads 1 KiB as two fully coalesced 512-byte rows; ownership (32 contiguous positions per lane)
@@ -792,7 +825,13 @@ __global__ void __launch_bounds__(QK_THREADS, MINB) qk_count_ext32_kernel(const 
             const uint32_t my_mask = sm.mask[lane + 1];
             const uint64_t M64 = ((uint64_t)my_mask << 32) | sm.mask[lane];
             uint64_t S = M64 | (M64 << 1);
-            S |= S << 2; S |= S << 4; S |= S << 8; S |= S << 14; // bit p: a reset in [p-29, p]
+            if (MODE == 0) { S |= S << 2; S |= S << 4; S |= S << 8; S |= S << 14; } // bit p: a reset in [p-29, p]
+            else
+                for (uint32_t have = 2; have < k;) {                                 // bit p: a reset in [p-k+1, p]
+                    const uint32_t step = min(have, k - have);
+                    S |= S << step;
+                    have += step;
+                }
             uint32_t emit = ~(uint32_t)(S >> 32);
             const uint32_t p0 = base + 32 * lane;
             if (emit && p0 + 31 - (uint32_t)carry_last >= 65536u) {
@@ -805,12 +844,29 @@ __global__ void __launch_bounds__(QK_THREADS, MINB) qk_count_ext32_kernel(const 
                 }
                 const uint32_t run0 = (uint32_t)((int)p0 - last0);
                 for (uint32_t j = 0; j < 32; ++j)   // (a reset inside my own word restarts the run: no wrap there)
-                    if (!(my_mask & ((2u << j) - 1)) && ((run0 + j) & 0xFFFFu) < 30u) emit &= ~(1u << j);
+                    if (!(my_mask & ((2u << j) - 1)) && ((run0 + j) & 0xFFFFu) < k) emit &= ~(1u << j);
             }
             carry_last = max(carry_last, seen);
             n_emit += __popc(emit);
 
             const uint64_t W = sm.codes[lane + 1];      // my 32 bases
+            uint64_t unc = 0;                           // modes 1, 2: positions whose key type the read does not settle
+            if (MODE == 1) {   // the key is the forward k-mer unless the newest min(k, 30 - k) bases are all T (code 2)
+                const uint64_t Wp = sm.codes[lane];
+                uint64_t lo = (W >> 1) & ~W & 0x5555555555555555ull, hi = (Wp >> 1) & ~Wp & 0x5555555555555555ull;
+                const uint32_t need = min(k, 30u - k);
+                for (uint32_t have = 1; have < need;) {   // AND over a window of `need` bases; older bases sit at higher bits
+                    const uint32_t step = min(have, need - have), sft = 2 * step;
+                    lo &= (lo >> sft) | (hi << (64 - sft));
+                    hi &= hi >> sft;
+                    have += step;
+                }
+                unc = lo;
+            } else if (MODE == 2) {   // the key is the 30-base reverse complement unless the oldest of the 31 bases is A (code 0)
+                const uint64_t Wp = sm.codes[lane];
+                const uint64_t lo = ~(W | (W >> 1)) & 0x5555555555555555ull, hi = ~(Wp | (Wp >> 1)) & 0x5555555555555555ull;
+                unc = (lo >> 60) | (hi << 4);             // the flag of the base 30 positions back
+            }
             uint32_t verified = 0, anchors = 0;
             // ---- first half: anchor = my first emitting position; walk the dictionary order from it -------
             uint32_t e0 = emit & 0xFFFFu, e1 = emit >> 16;
@@ -820,11 +876,12 @@ __global__ void __launch_bounds__(QK_THREADS, MINB) qk_count_ext32_kernel(const 
             for (int half = 0; half < 2; ++half) {
                 const uint32_t eh = half ? e1 : e0;
                 const uint32_t c16 = half ? (uint32_t)W : (uint32_t)(W >> 32);
+                const uint32_t u16 = half ? (uint32_t)unc : (uint32_t)(unc >> 32);
                 const uint32_t r16 = (my_mask >> (16 * half)) & 0xFFFFu;
                 int ja = -1;
                 uint32_t a_ord1 = 0;
                 uint64_t oa = 0;
-                bool plus = true;
+                bool plus = true, walkable = true;
                 if (half == 1 && end_known) {               // carry on from where the first half ended: no probe
                     oa = end_ord;
                     plus = end_plus;
@@ -839,11 +896,12 @@ __global__ void __launch_bounds__(QK_THREADS, MINB) qk_count_ext32_kernel(const 
                     ++n_probe;
                     anchors |= 1u << (16 * half + ja);
                     oa = a_ord1 ? a_ord1 - 1 : 0;
-                    plus = (a_strand != 0) == a_fwd;
+                    if (MODE == 0) plus = (a_strand != 0) == a_fwd;
+                    else walkable = MODE == 1 ? a_fwd : !a_fwd;   // the anchor's key is of the chain's type (exact compare)
                 }
                 uint32_t ve = 0;
-                if (a_ord1 && eh) {
-                    ve = qk_walk16(tv, oa, plus, ja, c16, r16) & eh;
+                if (a_ord1 && eh && walkable) {
+                    ve = qk_walk16<MODE>(tv, oa, plus, ja, c16, r16, u16) & eh;
                     n_walk += ja < 15;
                 }
                 n_ext += __popc(ve);
@@ -861,7 +919,7 @@ __global__ void __launch_bounds__(QK_THREADS, MINB) qk_count_ext32_kernel(const 
                         *reinterpret_cast<uint4 *>(sm.ord + lane * 32 + (((4 * half + v) ^ (lane & 7)) << 2)) =
                             make_uint4(o[4 * v], o[4 * v + 1], o[4 * v + 2], o[4 * v + 3]);
                     if (half == 0) {
-                        end_known = (e0 >> 15) & 1u && o[15] != 0;
+                        end_known = (e0 >> 15) & 1u && o[15] != 0 && (walkable || ja != 15);
                         end_plus = plus;
                         end_ord = (uint64_t)o[15] - 1;
                     }
@@ -994,17 +1052,21 @@ int qk_launch_count(qk_ctx *ctx, qk_slot *sl, const uint8_t *dev_bytes, size_t n
     if (plain_loads < 0) plain_loads = getenv("QK_EXT_PLAIN_LOADS") != NULL;
     static int run16 = -1;       // QK_EXT_RUN16=1: the 16-positions-per-lane walk (A/B knob)
     if (run16 < 0) run16 = getenv("QK_EXT_RUN16") != NULL;
-    if (a.tv.ext && !classic && !run16) {
+    if (a.tv.ext && !classic && (!run16 || ctx->desc.has_ext != 1)) {
         const size_t smem = QK_WARPS * sizeof(qk_warp_smem2);
         static int attr_set[64];
         if (ctx->device < 64 && !attr_set[ctx->device]) {
-            QK_CUDA(ctx, cudaFuncSetAttribute(qk_count_ext32_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            QK_CUDA(ctx, cudaFuncSetAttribute(qk_count_ext32_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            QK_CUDA(ctx, cudaFuncSetAttribute(qk_count_ext32_kernel<4, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            QK_CUDA(ctx, cudaFuncSetAttribute(qk_count_ext32_kernel<4, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            QK_CUDA(ctx, cudaFuncSetAttribute(qk_count_ext32_kernel<4, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            QK_CUDA(ctx, cudaFuncSetAttribute(qk_count_ext32_kernel<4, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_set[ctx->device] = 1;
         }
-        if (plain_loads) qk_count_ext32_kernel<4, false><<<grid, QK_THREADS, smem, sl->stream>>>(a);
-        else qk_count_ext32_kernel<4, true><<<grid, QK_THREADS, smem, sl->stream>>>(a);
-    } else if (a.tv.ext && !classic) {
+        if (ctx->desc.has_ext == 2) qk_count_ext32_kernel<4, true, 1><<<grid, QK_THREADS, smem, sl->stream>>>(a);
+        else if (ctx->desc.has_ext == 3) qk_count_ext32_kernel<4, true, 2><<<grid, QK_THREADS, smem, sl->stream>>>(a);
+        else if (plain_loads) qk_count_ext32_kernel<4, false, 0><<<grid, QK_THREADS, smem, sl->stream>>>(a);
+        else qk_count_ext32_kernel<4, true, 0><<<grid, QK_THREADS, smem, sl->stream>>>(a);
+    } else if (a.tv.ext && ctx->desc.has_ext == 1 && !classic) {
         // 4 CTAs/SM at 64 registers: 5 and 6 CTAs/SM spill and measured 2-5 % slower (profiles/README.md)
         if (plain_loads) qk_count_ext_kernel<4, false><<<grid, QK_THREADS, 0, sl->stream>>>(a);
         else qk_count_ext_kernel<4, true><<<grid, QK_THREADS, 0, sl->stream>>>(a);
@@ -1201,6 +1263,46 @@ extern "C" int qk_finish(qk_ctx *ctx, uint16_t *counts_out, uint64_t n_kmers)
         QK_CUDA(ctx, cudaMemcpyAsync(counts_out + at, dev, m * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
     }
     QK_CUDA(ctx, cudaStreamSynchronize(st));
+    return QK_OK;
+}
+
+// The same without blocking the caller: the download of the counter buffer selected NOW is enqueued on a
+// stream of its own, after everything enqueued on the slot streams so far, so that the next job -- counting
+// into the OTHER counter buffer (qk_counters_select) -- overlaps it.  counts_out must be page-locked.
+extern "C" int qk_finish_async(qk_ctx *ctx, uint16_t *counts_out, uint64_t n_kmers)
+{
+    if (!ctx || !counts_out) return QK_ERR_ARG;
+    if (ctx->dict_state != 2) return qk_fail(ctx, QK_ERR_STATE, "no dictionary built on this context");
+    if (n_kmers != ctx->desc.n_kmers) return qk_fail(ctx, QK_ERR_ARG, "n_kmers does not match the dictionary");
+    if (!qk_host_is_pinned(counts_out)) return qk_fail(ctx, QK_ERR_ARG, "qk_finish_async needs page-locked host memory");
+    int rc = qk_finish_wait(ctx);
+    if (rc) return rc;
+    QK_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->finish_stream;
+    for (uint32_t s = 0; s < ctx->n_slots; ++s) {
+        QK_CUDA(ctx, cudaEventRecord(ctx->span_join, ctx->slots[s].stream));
+        QK_CUDA(ctx, cudaStreamWaitEvent(st, ctx->span_join, 0));
+    }
+    if (!ctx->narrow_dev) QK_CUDA(ctx, cudaMalloc((void **)&ctx->narrow_dev, 2 * QK_FINISH_PIECE * sizeof(uint16_t)));
+    const uint32_t *src = ctx->counters;
+    int b = 0;
+    for (uint64_t at = 0; at < n_kmers; at += QK_FINISH_PIECE, b ^= 1) { // stream order keeps the two device buffers safe
+        const uint64_t m = n_kmers - at < QK_FINISH_PIECE ? n_kmers - at : QK_FINISH_PIECE;
+        uint16_t *dev = ctx->narrow_dev + (uint64_t)b * QK_FINISH_PIECE;
+        qk_narrow_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(src + at, dev, m);
+        QK_CUDA(ctx, cudaMemcpyAsync(counts_out + at, dev, m * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
+    }
+    QK_CUDA(ctx, cudaEventRecord(ctx->finish_done, st));
+    ctx->finish_pending = 1;
+    return QK_OK;
+}
+
+extern "C" int qk_finish_wait(qk_ctx *ctx)
+{
+    if (!ctx) return QK_ERR_ARG;
+    if (!ctx->finish_pending) return QK_OK;
+    QK_CUDA(ctx, cudaEventSynchronize(ctx->finish_done));
+    ctx->finish_pending = 0;
     return QK_OK;
 }
 

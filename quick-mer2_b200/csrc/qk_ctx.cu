@@ -79,6 +79,8 @@ extern "C" int qk_ctx_create(qk_ctx **out, int device, uint32_t n_slots, size_t 
     QK_CUDA(ctx, cudaEventCreate(&ctx->span_a));
     QK_CUDA(ctx, cudaEventCreate(&ctx->span_b));
     QK_CUDA(ctx, cudaEventCreateWithFlags(&ctx->span_join, cudaEventDisableTiming));
+    QK_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->finish_stream, cudaStreamNonBlocking));
+    QK_CUDA(ctx, cudaEventCreateWithFlags(&ctx->finish_done, cudaEventDisableTiming));
     QK_CUDA(ctx, cudaMalloc((void **)&ctx->stats, QK_STATS_WORDS * sizeof(unsigned long long)));
     QK_CUDA(ctx, cudaMemset(ctx->stats, 0, QK_STATS_WORDS * sizeof(unsigned long long)));
     QK_CUDA(ctx, cudaMalloc((void **)&ctx->frame_stream, QK_STATS_WORDS * sizeof(unsigned long long)));
@@ -108,6 +110,8 @@ extern "C" void qk_ctx_destroy(qk_ctx *ctx)
     if (ctx->span_a) cudaEventDestroy(ctx->span_a);
     if (ctx->span_b) cudaEventDestroy(ctx->span_b);
     if (ctx->span_join) cudaEventDestroy(ctx->span_join);
+    if (ctx->finish_done) cudaEventDestroy(ctx->finish_done);
+    if (ctx->finish_stream) cudaStreamDestroy(ctx->finish_stream);
     cudaFree(ctx->raw_keys);
     cudaFree(ctx->raw_next);
     cudaFree(ctx->buckets);

@@ -264,8 +264,8 @@ __device__ __forceinline__ uint64_t qk_rc30(uint64_t x)
 // walk is exact whatever produced the dictionary.  One thread per QK_EXT_BLOCK ordinals; the
 // first ordinal of a block never continues (the price of not chaining the blocks).
 #define QK_EXT_BLOCK 256
-__global__ void qk_orient_insert_kernel(const unsigned long long *__restrict__ kbo, uint64_t n, int with_ext, qk_build_params bp,
-                                        uint32_t *__restrict__ ext, qk_build_info *info)
+__global__ void qk_orient_insert_kernel(const unsigned long long *__restrict__ kbo, uint64_t n, int with_ext, uint64_t kmask,
+                                        qk_build_params bp, uint32_t *__restrict__ ext, qk_build_info *info)
 {
     const uint64_t blk = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t begin = blk * QK_EXT_BLOCK;
@@ -283,7 +283,15 @@ __global__ void qk_orient_insert_kernel(const unsigned long long *__restrict__ k
         if (raw & QK_KBO_SKIP) {
             have_prev = false;
         } else {
-            if (with_ext) {
+            if (with_ext == 2) {          // forward chain: F_o = K_o; continues iff K_o = ((K_{o-1} << 2) | base) & mask
+                cont = have_prev && (K >> 2) == (prevF & (kmask >> 2));
+                prevF = K;
+                have_prev = true;
+            } else if (with_ext == 3) {   // reverse-complement chain: continues iff K_o = (K_{o-1} >> 2) | base << 58
+                cont = have_prev && (K & M58) == (prevF >> 2);
+                prevF = K;
+                have_prev = true;
+            } else if (with_ext) {
                 const uint64_t Kr = qk_rc30(K);
                 if (have_prev) {
                     const uint64_t want = prevF & M58;
@@ -366,7 +374,10 @@ static void qk_geometry(uint64_t n, uint32_t k, uint64_t stash_slots_min, qk_tab
     d->stash_bytes = ss * sizeof(qk_stash_entry);
     // dictionary-order extension arrays (k = 30 only: for other k the reference's canonical key
     // mixes a k-mer with a 30-base reverse complement, Q.c:415-420, and is not a walkable k-mer)
-    d->has_ext = (k == 30 && getenv("QK_NO_EXT") == NULL) ? 1 : 0;
+    // which dictionary-order chain the keys form (qk_count.cu, qk_count_ext32_kernel): 1 = canonical 30-mers (k = 30);
+    // 2 = forward k-mers (k < 30: the key is the forward k-mer unless the newest bases are all T); 3 = 30-base
+    // reverse complements (k = 31: unless the oldest base is A); 0 = none (k = 32: every read key is 0, Q.c:419)
+    d->has_ext = getenv("QK_NO_EXT") != NULL ? 0 : k == 30 ? 1 : (k >= 3 && k < 30) ? 2 : k == 31 ? 3 : 0;
     d->ext_bytes = d->has_ext ? ((n + 15) / 16 + 4) * QK_EXT_GROUP_WORDS * sizeof(uint32_t) : 0; // 5 bits per ordinal in groups of 16, padded
     d->cont_bytes = 0;                                                        // (the continuation bits live in the same array)
 }
@@ -509,7 +520,8 @@ extern "C" int qk_dict_build(qk_ctx *ctx, uint64_t *n_kmers_out)
         bp.rem_bits = d.rem_bits;
         bp.ord_bits = d.ord_bits;
         const uint64_t n_blocks = (total + QK_EXT_BLOCK - 1) / QK_EXT_BLOCK;
-        qk_orient_insert_kernel<<<(unsigned)((n_blocks + 63) / 64), 64>>>(kbo, total, (int)d.has_ext, bp, ctx->ext, info);
+        qk_orient_insert_kernel<<<(unsigned)((n_blocks + 63) / 64), 64>>>(kbo, total, (int)d.has_ext,
+                                                                          ctx->k >= 32 ? 0 : (((uint64_t)1 << (2 * ctx->k)) - 1), bp, ctx->ext, info);
         QK_TRY(cudaGetLastError());
         QK_TRY(cudaMemcpy(&hinfo, info, sizeof hinfo, cudaMemcpyDeviceToHost));
         if (!(hinfo.flags & QK_FLAG_STASH_FULL)) break;
@@ -555,7 +567,7 @@ extern "C" int qk_dict_adopt(qk_ctx *ctx, const qk_table_desc *desc)
     if (desc->n_buckets == 0 || (desc->n_buckets & (desc->n_buckets - 1)) || desc->stash_slots == 0 ||
         (desc->stash_slots & (desc->stash_slots - 1)) || desc->table_bytes != desc->n_buckets * sizeof(qk_bucket) ||
         desc->stash_bytes != desc->stash_slots * sizeof(qk_stash_entry) || desc->rem_bits + desc->ord_bits > 62 ||
-        desc->ord_bits > 32 || (desc->has_ext && (desc->k != 30 || desc->ext_bytes < ((desc->n_kmers + 15) / 16 + 4) * QK_EXT_GROUP_WORDS * 4)) ||
+        desc->ord_bits > 32 || (desc->has_ext && ((desc->has_ext == 1) != (desc->k == 30) || desc->has_ext > 3 || desc->k > 31 || desc->ext_bytes < ((desc->n_kmers + 15) / 16 + 4) * QK_EXT_GROUP_WORDS * 4)) ||
         desc->rem_bits + desc->bucket_bits != QK_KEY_BITS || desc->k < 1 || desc->k > 32)
         return qk_fail(ctx, QK_ERR_ARG, "inconsistent table descriptor");
     QK_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -213,3 +213,142 @@ def test_orientation_is_consistent():
             assert (F[o] >> 2) == (F[o - 1] & Mlow) and last[o] == (F[o] & 3) and first[o - 1] == F[o - 1] >> (2 * (k - 1))
         assert o % BLOCK != 0 or cont[o] == 0
     assert sum(cont) > 0.5 * len(keys)                       # a random reference is mostly walkable
+
+
+# ------------------------------------------------------------------------------------------------
+# k != 30.  The reference's key is min(fwd_k, rc_W) with a reverse-complement register of W = 30 bases
+# WHATEVER k is (Q.c:415-420).  For k < W the key is the forward k-mer unless the newest bases are all
+# T; for k = W + 1 it is the W-base reverse complement unless the oldest base is A.  Both are chains in
+# dictionary order (forward: K' = ((K << 2) | b) & mask; reverse: K' = (K >> 2) | comp(b) << 2(W-1)), so the
+# same walk applies -- in one direction only, and only over positions whose key TYPE the read itself
+# settles.  Modelled here with W = 6 so that coincidences are common.
+W = 6
+
+
+def mixed_stream(codes, k):
+    """(key, fwd_k, rc_W, run length) per emitting position: the reference's codec with a W-base rc register."""
+    M = (1 << (2 * k)) - 1
+    fwd = rcv = 0
+    out = []
+    for i, c in enumerate(codes):
+        fwd = ((fwd << 2) | c) & ((1 << 64) - 1)
+        rcv = (rcv | ((c ^ 2) << (2 * W))) >> 2
+        if i + 1 >= k:
+            f = fwd & M
+            out.append((min(f, rcv), f, rcv))
+        else:
+            out.append(None)
+    return out
+
+
+def build_mixed_dictionary(ref_codes, k):
+    stream = [s for s in mixed_stream(ref_codes, k) if s is not None]
+    counts = {}
+    for key, _, _ in stream:
+        counts[key] = counts.get(key, 0) + 1
+    return [key for key, _, _ in stream if counts[key] == 1 and key != 0]
+
+
+def mixed_ext(keys, k):
+    """cont / last2 (forward chain, k < W) or cont / top2 (reverse chain, k = W + 1) per ordinal."""
+    n = len(keys)
+    M = (1 << (2 * k)) - 1
+    cont, sym = [0] * n, [0] * n
+    for begin in range(0, n, BLOCK):
+        for o in range(begin, min(n, begin + BLOCK)):
+            if k < W:
+                sym[o] = keys[o] & 3
+                cont[o] = int(o > begin and (keys[o] >> 2) == (keys[o - 1] & (M >> 2)))
+            else:
+                sym[o] = keys[o] >> (2 * (W - 1))
+                cont[o] = int(o > begin and (keys[o] & ((1 << (2 * (W - 1))) - 1)) == (keys[o - 1] >> 2))
+    return cont, sym
+
+
+def type_certain(read_codes, p, k):
+    """What the kernel can tell from the read alone, conservatively: the key at p is the forward k-mer
+    (k < W: one of the newest min(k, W - k) bases is not T) / the W-base reverse complement (k = W + 1:
+    the oldest of the k bases is not A)."""
+    if k < W:
+        w = min(k, W - k)
+        return any(read_codes[p - i] != 2 for i in range(w))
+    return read_codes[p - W] != 0
+
+
+def mixed_walk_counts(read_codes, keys, k, lookup, cont, sym):
+    stream = mixed_stream(read_codes, k)
+    n = len(keys)
+    got, walked = {}, 0
+    L = len(read_codes)
+    for base in range(0, L, 2 * RUN):
+        end = None
+        for half in (0, 1):
+            hb = base + RUN * half
+            run = [p for p in range(hb, min(hb + RUN, L)) if stream[p] is not None]
+            if not run:
+                continue
+            settled, probed_anchor, oa = {}, None, None
+            if half == 1 and end is not None:
+                ja, oa = hb - 1, end
+            else:
+                ja = run[0]
+                key, f, r = stream[ja]
+                o = lookup.get(key)
+                probed_anchor = ja
+                if o is not None:
+                    settled[ja] = o
+                    if (key == f) if k < W else (key == r):      # the anchor's key is of the walkable type (exact compare)
+                        oa = o
+            if oa is not None:
+                o = oa
+                for p in range(ja + 1, min(hb + RUN, L)):
+                    b = read_codes[p]
+                    want = b if k < W else b ^ 2
+                    if stream[p] is None or not type_certain(read_codes, p, k) or o + 1 >= n or not cont[o + 1] or sym[o + 1] != want:
+                        break
+                    o += 1
+                    settled[p] = o
+                    walked += 1
+            for p in run:
+                if p in settled:
+                    got[p] = settled[p]
+                elif p != probed_anchor:
+                    o = lookup.get(stream[p][0])
+                    if o is not None:
+                        got[p] = o
+            if half == 0:
+                last_p = hb + RUN - 1
+                # the second half may carry on only from a position whose key type is known to be the walkable one
+                ok = last_p in settled and (last_p != probed_anchor or oa is not None)
+                end = settled[last_p] if ok else None
+    return got, walked
+
+
+@pytest.mark.parametrize("flavour", ["uniform", "at_rich", "tandem", "palindromic"])
+@pytest.mark.parametrize("k", [2, 3, 4, 5, 7])
+def test_mixed_key_walk_equals_lookup(k, flavour):
+    rng = np.random.default_rng(77 * k + len(flavour))
+    total_walked = total = 0
+    for trial in range(12):
+        ref = make_reference(rng, 600, flavour)
+        keys = build_mixed_dictionary(ref, k)
+        if len(keys) < 4:
+            continue
+        lookup = {key: o for o, key in enumerate(keys)}
+        cont, sym = mixed_ext(keys, k)
+        for _ in range(40):
+            span = min(90, len(ref))
+            a = int(rng.integers(0, len(ref) - span + 1))
+            read = list(ref[a:a + int(rng.integers(k + 1, span + 1))])
+            if rng.integers(0, 3) == 0:
+                read = [c ^ 2 for c in reversed(read)]
+            for i in rng.integers(0, len(read), int(rng.integers(0, 3))):
+                read[i] = int(rng.integers(0, 4))
+            got, walked = mixed_walk_counts(read, keys, k, lookup, cont, sym)
+            want = {p: lookup[s[0]] for p, s in enumerate(mixed_stream(read, k)) if s is not None and s[0] in lookup}
+            assert got == want
+            total_walked += walked
+            total += len(got)
+    if total == 0:
+        pytest.skip("no unique k-mers in these references")
+    assert total_walked > 0

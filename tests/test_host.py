@@ -222,7 +222,7 @@ def test_table_geometry_invariants(n, k, qk):
     assert d.rem_bits + d.ord_bits <= 63
     assert d.table_bytes == d.n_buckets * 32
     assert d.stash_slots & (d.stash_slots - 1) == 0 and d.stash_bytes == d.stash_slots * 16
-    assert d.has_ext == (1 if k == 30 else 0)
+    assert d.has_ext == (1 if k == 30 else 2 if 3 <= k < 30 else 3 if k == 31 else 0)
     if d.has_ext:
         assert d.ext_bytes >= ((n + 15) // 16 + 4) * 12 and d.cont_bytes == 0
     else:
