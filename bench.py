@@ -780,7 +780,7 @@ def gpu_arm(args):
                 pending[b] = None
 
     def job_preframed():
-        ctx.reset()
+        ctx.reset_async()
         for i, (o, sz) in enumerate(zip(data.h_offs, data.h_sizes)):
             ctx.submit_host(data.host_base + o, sz, slot=i % ctx.n_slots)
 
@@ -791,11 +791,11 @@ def gpu_arm(args):
     host_framing = args.framer == "host" or (args.framer == "auto" and framer_threads >= 12 and is_fastq)   # measured: profiles/README.md
 
     def job_raw_device():
-        ctx.reset()
+        ctx.reset_async()
         ctx.count_mem(data.raw_ptr, data.raw_bytes)
 
     def job_raw_host():
-        ctx.reset()
+        ctx.reset_async()
         ctx.count_mem_mt(data.raw_ptr, data.raw_bytes, threads=framer_threads)
 
     job_raw = job_raw_host if host_framing else job_raw_device
@@ -891,33 +891,53 @@ def gpu_arm(args):
     ctx.select_counters(0)
 
     # ---- e2e_preframed and e2e: host buffers, copies inside the timed region --------------
-    result_np = None
-    if rank == 0:                                   # (own pinned allocation: given back before the CPU leg)
+    result_np, result_ptr = [None, None], [None, None]
+    if rank == 0:                                   # (own pinned allocations: given back before the CPU leg)
         import ctypes
         qsl = load_synth_gpu().lib()
-        result_ptr = qsl.qs_pinned_alloc(2 * n_kmers + 64)
-        if not result_ptr:
-            raise MemoryError("cannot pin the result buffer")
-        result_np = np.ctypeslib.as_array(ctypes.cast(result_ptr, ctypes.POINTER(ctypes.c_uint16)), shape=(n_kmers,))
+        for i in (0, 1):                            # two: the read-back of one step overlaps the counting of the next
+            result_ptr[i] = qsl.qs_pinned_alloc(2 * n_kmers + 64)
+            if not result_ptr[i]:
+                raise MemoryError("cannot pin the result buffer")
+            result_np[i] = np.ctypeslib.as_array(ctypes.cast(result_ptr[i], ctypes.POINTER(ctypes.c_uint16)), shape=(n_kmers,))
 
     def timed_host(job, steps, warm):
-        for _ in range(warm):
-            job(); finish_step()
-        barrier()
-        t0 = time.perf_counter()
-        marks = []
-        for _ in range(steps):
-            job(); finish_step()
+        """Host-buffer legs.  Every step: inputs from host memory (H2D inside), count, (N > 1: reduce), and the
+        read-back of the step's uint16 depths into pinned memory.  Steps alternate between the two counter
+        buffers so that the read-back of step s (qk_finish_async, its own stream) runs while step s + 1 is being
+        counted; the timer stops only when the last read-back has landed."""
+        def one(step):
+            b = step & 1
+            ctx.select_counters(b)
+            job()
+            ctx.sync()
+            if world > 1:
+                dist.reduce(counters_ab[b], 0, op=dist.ReduceOp.SUM)
+                torch.cuda.synchronize()
             marks.append(time.perf_counter())
             if rank == 0:
-                ctx.finish(result_np)             # D2H of the step's result: uint16 depths in .bin order (pinned)
+                ctx.finish_wait()                 # the previous step's depths (normally long there)
+                ctx.finish_async(result_np[b])    # this step's: uint16, .bin order, pinned
             marks.append(time.perf_counter())
+        marks = []
+        for i in range(warm):
+            one(i)
+        if rank == 0:
+            ctx.finish_wait()
+        barrier()
+        marks = []
+        t0 = time.perf_counter()
+        for i in range(steps):
+            one(warm + i)
+        if rank == 0:
+            ctx.finish_wait()
         barrier()
         dt = all_max(time.perf_counter() - t0)
         if rank == 0:
-            log(f"{job.__name__}: per step [count ms, result D2H ms] = "
-                + str([round(1e3 * (b - a), 1) for a, b in zip([t0] + marks[:-1], marks)]))
+            log(f"{job.__name__}: per step [count ms, hand the result to the read-back ms] = "
+                + str([round(1e3 * (b - a), 1) for a, b in zip([t0] + marks[:-1], marks)]) + f"; total {1e3 * dt:.1f} ms")
         (k,) = all_sum([ctx.stats()["total_kmers"]])
+        ctx.select_counters(0)
         return dt / steps, k
 
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
@@ -926,8 +946,9 @@ def gpu_arm(args):
         pre_s = raw_s = float("nan")
         h2d_ms_step = None
     else:
+        h2d_before = ctx.timing()["h2d_ms"]
         pre_s, h_kmers = timed_host(job_preframed, e2e_steps, 1)
-        h2d_ms_step = ctx.timing()["h2d_ms"]
+        h2d_ms_step = (ctx.timing()["h2d_ms"] - h2d_before) / (e2e_steps + 1)
         raw_s, h_kmers_raw = timed_host(job_raw, e2e_steps, 1)
         assert h_kmers_raw == h_kmers, (h_kmers_raw, h_kmers)
         other_s = None
@@ -943,7 +964,7 @@ def gpu_arm(args):
         file_reads = prepare_synth(args.workload, cdir, sample=True)[2]      # the CPU arm's sample (already cached)
     if world == 1 and not args.kernel_only and file_reads is not None:
         def job_file():
-            ctx.reset()
+            ctx.reset_async()
             if host_framing:
                 ctx.count_file_mt(file_reads, threads=framer_threads)
             else:
@@ -955,8 +976,9 @@ def gpu_arm(args):
     if rank == 0 and not args.kernel_only:
         framer_gbs = qk.bench_framer(data.raw_ptr, min(data.raw_bytes, 4 << 30), threads=framer_threads, repeats=2)
     if rank == 0:
-        result_np = None
-        qsl.qs_pinned_free(result_ptr)
+        result_np = [None, None]
+        for p in result_ptr:
+            qsl.qs_pinned_free(p)
     if synth:
         data.free_host()
         data.devbuf.free()                          # the micro-benchmarks below need the HBM

@@ -694,3 +694,45 @@ def test_dictionary_written_by_reference_search_and_sparse(tool, qk, ref_binary,
     assert ours == theirs and len(ours) > 1000
     assert otxt == ttxt
     assert np.frombuffer(ours, dtype=np.uint16).sum() > 0
+
+
+def test_finish_async_overlaps_the_next_sample(qk, tmp_path):
+    """qk_finish_async: the depths of one sample travel to (page-locked) host memory while the next sample is
+    counted into the other counter buffer; both results are what the reference wrote."""
+    import ctypes
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, str(ROOT / "tools"))
+    import qk_synth_gpu as qs
+    d = GOLDEN / "k30_fastq_t3"
+    want = np.fromfile(d / "expect.bin", dtype=np.uint16)
+    raw = (d / "reads.fq").read_bytes()
+    half = raw[: raw.index(b"\n@", len(raw) // 2) + 1]          # a second, different sample: the first half of the reads
+    (tmp_path / "half.fq").write_bytes(half)
+    with qk.Context(device=0, n_slots=3, chunk_capacity=1 << 20) as ctx:
+        n = ctx.load_dictionary(d / "ref.fa.qm")
+        ctx.count_file(tmp_path / "half.fq")
+        want_half = ctx.finish().copy()
+        ptrs = [qs.lib().qs_pinned_alloc(2 * n + 64) for _ in range(2)]
+        outs = [np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint16)), shape=(n,)) for p in ptrs]
+        try:
+            for rep in range(3):
+                ctx.select_counters(0)
+                ctx.reset_async()
+                ctx.count_file(d / "reads.fq")
+                ctx.finish_async(outs[0])
+                ctx.select_counters(1)
+                ctx.reset_async()
+                ctx.count_file(tmp_path / "half.fq")          # runs while the first result is on its way
+                ctx.finish_wait()
+                assert np.array_equal(outs[0], want)
+                ctx.finish_async(outs[1])
+                ctx.finish_wait()
+                assert np.array_equal(outs[1], want_half)
+            with pytest.raises(qk.QkError):
+                ctx.finish_async(np.empty(n, dtype=np.uint16))  # pageable memory is refused
+        finally:
+            ctx.finish_wait()
+            ctx.select_counters(0)
+            for p in ptrs:
+                qs.lib().qs_pinned_free(p)
