@@ -915,6 +915,8 @@ def gpu_arm(args):
                 dist.reduce(counters_ab[b], 0, op=dist.ReduceOp.SUM)
                 torch.cuda.synchronize()
             marks.append(time.perf_counter())
+            if os.environ.get("QK_BENCH_DEBUG"):
+                log(f"  {job.__name__} step {step} buffer {b}: {ctx.stats()}")
             if rank == 0:
                 ctx.finish_wait()                 # the previous step's depths (normally long there)
                 ctx.finish_async(result_np[b])    # this step's: uint16, .bin order, pinned

@@ -301,8 +301,12 @@ extern "C" int qk_raw_begin_state(qk_ctx *ctx, int fastq, uint32_t line_state)
     int rc = qk_sync(ctx);
     if (rc) return rc;
     QK_CUDA(ctx, cudaSetDevice(ctx->device));
+    // On a slot stream and waited for there: a plain cudaMemcpy from pageable memory returns once the bytes are
+    // STAGED, and the slot streams (non-blocking) do not order against the default stream -- with another DMA in
+    // flight (qk_finish_async) the state landed ~10 ms into the job and re-phased the framer mid-stream.
     unsigned long long init[4] = {line_state, 0, 0, 0};
-    QK_CUDA(ctx, cudaMemcpy(ctx->frame_stream, init, sizeof init, cudaMemcpyHostToDevice));
+    QK_CUDA(ctx, cudaMemcpyAsync(ctx->frame_stream, init, sizeof init, cudaMemcpyHostToDevice, ctx->slots[0].stream));
+    QK_CUDA(ctx, cudaStreamSynchronize(ctx->slots[0].stream));
     ctx->raw_fastq = fastq ? 1 : 0;
     ctx->raw_active = 1;
     ctx->raw_prev_slot = -1;
