@@ -73,7 +73,7 @@ void qk_framer_close(qk_framer *f);
 /* ---- byte streams: plain or gzip, regular file or pipe -----------------------------------
  * Everything that reads a reads stream sequentially goes through these: the gzip magic is
  * recognised on files and pipes alike and the data inflated on the fly (concatenated members
- * included).  The reference itself reads plain text only (its documented route for compressed
+ * included); a BAM container is recognised after inflation and turned into the text of its reads.  The reference itself reads plain text only (its documented route for compressed
  * input is a pipe, README.md:89-90). */
 typedef struct qk_stream qk_stream;
 qk_stream *qk_stream_open(const char *path);        /* NULL if it cannot be opened */
@@ -81,6 +81,9 @@ qk_stream *qk_stream_open_fd(int fd, int seekable); /* takes ownership of fd    
 /* Up to `cap` bytes; short only at the end of the stream; 0 = end, -1 = I/O or format error. */
 ssize_t qk_stream_read(qk_stream *s, uint8_t *dst, size_t cap);
 int qk_stream_is_gzip(const qk_stream *s);
+/* 1 once the first read has found a BAM container (BGZF that inflates to "BAM\1"): qk_stream_read then delivers
+ * the FASTA text `samtools view -F 3840 | awk '{print ">\n"$10}'` would (README.md:89-90) -- no samtools, no pipe. */
+int qk_stream_is_bam(const qk_stream *s);
 int qk_stream_seekable(const qk_stream *s);
 void qk_stream_close(qk_stream *s);
 

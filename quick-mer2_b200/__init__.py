@@ -156,6 +156,7 @@ SIGNATURES = {
     "qk_stream_open_fd": (_P, [C.c_int, C.c_int]),
     "qk_stream_read": (C.c_ssize_t, [_P, _P, C.c_size_t]),
     "qk_stream_is_gzip": (C.c_int, [_P]),
+    "qk_stream_is_bam": (C.c_int, [_P]),
     "qk_stream_seekable": (C.c_int, [_P]),
     "qk_stream_close": (None, [_P]),
     "qk_count_raw_stream": (C.c_int, [_P, _P, C.POINTER(FramerStats)]),

@@ -34,6 +34,16 @@ struct qk_stream {
     uint32_t threads;
     uint8_t *out;
     size_t out_cap, out_pos, out_have;
+    /* BAM: the inflated stream is a BAM container; what the readers get is the text the documented pipe
+     * `samtools view -F 3840 | awk '{print ">\n"$10}'` (README.md:89-90, tutorial.md:144-146) would deliver */
+    int bam;                /* 0 = not probed yet, 1 = BAM, -1 = not BAM */
+    int bam_phase;          /* 0 = header, 1 = records */
+    uint32_t bam_exclude;   /* records with any of these flag bits are dropped (-F) */
+    uint8_t *raw;           /* inflated bytes waiting to be parsed (also the pushback of the 4 probe bytes) */
+    size_t raw_cap, raw_pos, raw_have;
+    int raw_eof;
+    uint8_t *txt;           /* FASTA text ready to be handed out */
+    size_t txt_cap, txt_pos, txt_have;
 };
 
 typedef struct {
@@ -213,8 +223,8 @@ qk_stream *qk_stream_open(const char *path)
 int qk_stream_is_gzip(const qk_stream *s) { return s ? s->gz : 0; }
 int qk_stream_seekable(const qk_stream *s) { return s ? s->seekable : 0; }
 
-/* Up to `cap` bytes of (decompressed) stream; short only at the end.  0 = end, -1 = error. */
-ssize_t qk_stream_read(qk_stream *s, uint8_t *dst, size_t cap)
+/* Up to `cap` bytes of the plain or inflated stream; short only at the end.  0 = end, -1 = error. */
+static ssize_t stream_read_bytes(qk_stream *s, uint8_t *dst, size_t cap)
 {
     if (!s || !dst || s->failed) return -1;
     size_t out = 0;
@@ -273,9 +283,148 @@ ssize_t qk_stream_read(qk_stream *s, uint8_t *dst, size_t cap)
     return (ssize_t)out;
 }
 
+/* ---- BAM ------------------------------------------------------------------------------------------
+ * The production entry of the reference is a pipe: samtools decodes the BAM/CRAM, awk prints ">" and the SEQ
+ * column (README.md:89-90), and `count` reads that FASTA from /dev/fd/0 -- a few hundred MB/s of text through
+ * two processes.  A BAM file (BGZF blocks, inflated above by several threads) is taken directly: its
+ * alignment records are walked here and the same text is produced -- ">", newline, the sequence as stored
+ * (4-bit codes -> "=ACMGRSVTWYHKDBN", SAM spec 4.2), newline -- for every record that `-F 3840` keeps
+ * (not secondary, QC-fail, duplicate or supplementary; QK_BAM_EXCLUDE overrides the mask).  CRAM needs the
+ * reference genome to decode and stays with samtools. */
+static int raw_need(qk_stream *s, size_t n)   /* 1 = n bytes available at raw_pos, 0 = clean end of stream, -1 = error / truncated */
+{
+    if (s->raw_have - s->raw_pos >= n) return 1;
+    if (s->raw_pos) {
+        memmove(s->raw, s->raw + s->raw_pos, s->raw_have - s->raw_pos);
+        s->raw_have -= s->raw_pos;
+        s->raw_pos = 0;
+    }
+    if (n > s->raw_cap) {
+        size_t cap = s->raw_cap ? s->raw_cap : (size_t)1 << 20;
+        while (cap < n) cap <<= 1;
+        uint8_t *nb = realloc(s->raw, cap);
+        if (!nb) return -1;
+        s->raw = nb;
+        s->raw_cap = cap;
+    }
+    while (s->raw_have < n && !s->raw_eof) {
+        ssize_t got = stream_read_bytes(s, s->raw + s->raw_have, s->raw_cap - s->raw_have);
+        if (got < 0) return -1;
+        if (got == 0) s->raw_eof = 1;
+        s->raw_have += (size_t)got;
+    }
+    if (s->raw_have >= n) return 1;
+    return s->raw_have == 0 ? 0 : -1;
+}
+
+static uint32_t le32(const uint8_t *p) { return p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+
+/* more text into s->txt; 1 = some, 0 = end of the BAM, -1 = error */
+static int bam_fill(qk_stream *s)
+{
+    static const char code[16] = "=ACMGRSVTWYHKDBN";
+    s->txt_pos = s->txt_have = 0;
+    if (!s->txt) {
+        s->txt_cap = (size_t)4 << 20;
+        s->txt = malloc(s->txt_cap);
+        if (!s->txt) return -1;
+    }
+    if (s->bam_phase == 0) {                       /* magic, header text, reference names */
+        if (raw_need(s, 12) != 1) return -1;
+        const uint32_t l_text = le32(s->raw + s->raw_pos + 4);
+        if (raw_need(s, 12 + (size_t)l_text) != 1) return -1;
+        uint32_t n_ref = le32(s->raw + s->raw_pos + 8 + l_text);
+        s->raw_pos += 12 + (size_t)l_text;
+        while (n_ref--) {
+            if (raw_need(s, 4) != 1) return -1;
+            const uint32_t l_name = le32(s->raw + s->raw_pos);
+            if (raw_need(s, 8 + (size_t)l_name) != 1) return -1;
+            s->raw_pos += 8 + (size_t)l_name;
+        }
+        s->bam_phase = 1;
+    }
+    while (s->txt_have < s->txt_cap / 2) {
+        int r = raw_need(s, 4);
+        if (r <= 0) return r < 0 ? -1 : (s->txt_have ? 1 : 0);
+        const uint32_t block = le32(s->raw + s->raw_pos);
+        if (block < 32 || raw_need(s, 4 + (size_t)block) != 1) return -1;
+        const uint8_t *b = s->raw + s->raw_pos + 4;
+        const uint32_t l_read_name = b[8], n_cigar = b[12] | ((uint32_t)b[13] << 8), flag = b[14] | ((uint32_t)b[15] << 8);
+        const uint32_t l_seq = le32(b + 16);
+        const size_t seq_off = 32 + (size_t)l_read_name + 4 * (size_t)n_cigar;
+        if (seq_off + ((size_t)l_seq + 1) / 2 + l_seq > block) return -1;
+        s->raw_pos += 4 + (size_t)block;
+        if ((flag & s->bam_exclude) || l_seq == 0) continue;
+        if (s->txt_have + l_seq + 3 > s->txt_cap) {
+            size_t cap = s->txt_cap;
+            while (s->txt_have + l_seq + 3 > cap) cap <<= 1;
+            uint8_t *nb = realloc(s->txt, cap);
+            if (!nb) return -1;
+            s->txt = nb;
+            s->txt_cap = cap;
+        }
+        uint8_t *o = s->txt + s->txt_have;
+        const uint8_t *q = s->raw + s->raw_pos - block + seq_off;   /* (raw_pos already points past the record) */
+        *o++ = '>';
+        *o++ = '\n';
+        for (uint32_t i = 0; i < l_seq; ++i) *o++ = (uint8_t)code[(q[i >> 1] >> ((~i & 1) << 2)) & 15];
+        *o++ = '\n';
+        s->txt_have += (size_t)l_seq + 3;
+    }
+    return 1;
+}
+
+int qk_stream_is_bam(const qk_stream *s) { return s ? s->bam == 1 : 0; }
+
+/* Up to `cap` bytes of reads TEXT: the plain or inflated stream, or the FASTA made from a BAM. */
+ssize_t qk_stream_read(qk_stream *s, uint8_t *dst, size_t cap)
+{
+    if (!s || !dst || s->failed) return -1;
+    if (s->bam == 0) {                                /* probe: a BAM is a BGZF/gzip stream that inflates to "BAM\1" */
+        s->bam = -1;
+        if (s->gz) {
+            int r = raw_need(s, 4);
+            if (r < 0 && s->raw_have == 0) { s->failed = 1; return -1; }
+            if (r == 1 && !memcmp(s->raw, "BAM\1", 4)) {
+                const char *e = getenv("QK_BAM_EXCLUDE");
+                s->bam = 1;
+                s->bam_exclude = e ? (uint32_t)strtoul(e, NULL, 0) : 3840u;
+            }
+        }
+    }
+    size_t out = 0;
+    if (s->bam == 1) {
+        while (out < cap) {
+            if (s->txt_pos == s->txt_have) {
+                int r = bam_fill(s);
+                if (r < 0) { s->failed = 1; return -1; }
+                if (r == 0) break;
+            }
+            size_t m = s->txt_have - s->txt_pos < cap - out ? s->txt_have - s->txt_pos : cap - out;
+            memcpy(dst + out, s->txt + s->txt_pos, m);
+            s->txt_pos += m;
+            out += m;
+        }
+        return (ssize_t)out;
+    }
+    if (s->raw_pos < s->raw_have) {                   /* the probe bytes go out first */
+        size_t m = s->raw_have - s->raw_pos < cap ? s->raw_have - s->raw_pos : cap;
+        memcpy(dst, s->raw + s->raw_pos, m);
+        s->raw_pos += m;
+        out = m;
+        if (out == cap) return (ssize_t)out;
+    }
+    if (s->raw_eof) return (ssize_t)out;
+    ssize_t got = stream_read_bytes(s, dst + out, cap - out);
+    if (got < 0) return -1;
+    return (ssize_t)(out + (size_t)got);
+}
+
 void qk_stream_close(qk_stream *s)
 {
     if (!s) return;
+    free(s->raw);
+    free(s->txt);
     if (s->gz && !s->bgzf) inflateEnd(&s->z);
     close(s->fd);
     free(s->in);

@@ -736,3 +736,23 @@ def test_finish_async_overlaps_the_next_sample(qk, tmp_path):
             ctx.select_counters(0)
             for p in ptrs:
                 qs.lib().qs_pinned_free(p)
+
+
+def test_bam_input(qk, tmp_path):
+    """A BAM of the golden reads (file and pipe): same .bin / .txt as the reference wrote for the FASTA --
+    what tutorial.md:144-146 gets through `samtools view | awk`."""
+    from test_host import bgzf_compress, make_bam
+    d = GOLDEN / "k30_fasta_t0"
+    seqs = [l for l in (d / "reads.fa").read_text().split("\n") if l and not l.startswith(">")]
+    reads = [(f"q{i}", 16 if i % 2 else 0, s) for i, s in enumerate(seqs)]
+    reads.insert(5, ("dup", 1024, seqs[0]))                       # dropped by -F 3840
+    reads.insert(9, ("sec", 256, seqs[1]))
+    (tmp_path / "r.bam").write_bytes(bgzf_compress(make_bam(reads), block=40000) + bgzf_compress(b""))
+    res = qk.run_cli(["count", "-t", "3", d / "ref.fa", tmp_path / "r.bam", tmp_path / "b"])
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert (tmp_path / "b.bin").read_bytes() == (d / "expect.bin").read_bytes()
+    assert (tmp_path / "b.txt").read_bytes() == (d / "expect.txt").read_bytes()
+    res = subprocess.run([str(qk.CLI_PATH), "count", str(d / "ref.fa"), "/dev/stdin", str(tmp_path / "p")],
+                         input=(tmp_path / "r.bam").read_bytes(), capture_output=True)
+    assert res.returncode == 0, res.stdout
+    assert (tmp_path / "p.bin").read_bytes() == (d / "expect.bin").read_bytes()

@@ -414,3 +414,69 @@ def test_mt_framer_edges(qk):
     # a line longer than a chunk is an error, not a hang
     with pytest.raises(qk.QkError):
         qk.frame_mt(b">x\n" + base(300000) + b"\n", threads=2, cap=200000)
+
+
+# ---------------------------------------------------------------------------- BAM input
+def make_bam(reads, refs=(("chr1", 1000000),), text="@HD\tVN:1.6\n"):
+    """A minimal BAM (SAM spec 4.2), uncompressed bytes: reads = [(name, flag, sequence)]."""
+    import struct
+    out = bytearray(b"BAM\1" + struct.pack("<I", len(text)) + text.encode() + struct.pack("<I", len(refs)))
+    for name, length in refs:
+        out += struct.pack("<I", len(name) + 1) + name.encode() + b"\0" + struct.pack("<I", length)
+    codes = {c: i for i, c in enumerate("=ACMGRSVTWYHKDBN")}
+    for i, (name, flag, seq) in enumerate(reads):
+        n = len(seq)
+        packed = bytearray((n + 1) // 2)
+        for j, ch in enumerate(seq):
+            packed[j >> 1] |= codes[ch] << (4 if j % 2 == 0 else 0)
+        cigar = struct.pack("<I", (n << 4) | 0) if n else b""            # nM
+        tags = b"NMC\x00" if i % 3 == 0 else b""
+        body = struct.pack("<iiBBHHHIiii", 0, 100 + i, len(name) + 1, 30, 4680, 1 if n else 0, flag, n, -1, -1, 0)
+        body += name.encode() + b"\0" + cigar + bytes(packed) + b"\x28" * n + tags
+        out += struct.pack("<I", len(body)) + body
+    return bytes(out)
+
+
+def test_bam_is_turned_into_the_text_of_its_reads(qk, tmp_path):
+    """tutorial.md:144-146 feeds `samtools view -F 3840 s.cram | awk '{print ">\\n"$10}'` to count.  A BAM file is
+    taken directly: same text, no samtools -- secondary / QC-fail / duplicate / supplementary records dropped."""
+    rng = np.random.default_rng(3)
+    reads = []
+    for i in range(4000):
+        n = int(rng.choice([0, 1, 2, 75, 150, 151, 2000, 70001])) if i % 50 == 0 else 150
+        seq = "".join(rng.choice(list("ACGTN"), size=n, p=[0.245, 0.245, 0.245, 0.245, 0.02])) if n else ""
+        if i % 97 == 0 and n:
+            seq = seq[: n // 2] + "RYM" + seq[n // 2 + 3:]                # IUPAC codes travel as they are
+        flag = int(rng.choice([0, 16, 99, 147, 256, 272, 512, 1024, 2048, 2064, 4]))
+        reads.append((f"r{i}", flag, seq))
+    raw = make_bam(reads)
+    want = "".join(f">\n{s}\n" for _, f, s in reads if not (f & 3840) and s).encode()
+    (tmp_path / "a.bam").write_bytes(bgzf_compress(raw, block=20000) + bgzf_compress(b""))     # + the BGZF end marker
+    for piece in (777, 1 << 16, 1 << 22):
+        got, gz = qk.read_stream(tmp_path / "a.bam", piece=piece)
+        assert got == want and gz
+    import gzip
+    (tmp_path / "plain_gzip.bam").write_bytes(gzip.compress(raw))                                # not BGZF: one gzip member
+    assert qk.read_stream(tmp_path / "plain_gzip.bam")[0] == want
+    os.environ["QK_BAM_EXCLUDE"] = "0"                                                            # keep every record
+    try:
+        assert qk.read_stream(tmp_path / "a.bam")[0] == "".join(f">\n{s}\n" for _, f, s in reads if s).encode()
+    finally:
+        del os.environ["QK_BAM_EXCLUDE"]
+    r, w = os.pipe()
+    if os.fork() == 0:
+        os.close(r)
+        data = bgzf_compress(raw, block=30000)
+        while data:
+            data = data[os.write(w, data[:65536]):]
+        os._exit(0)
+    os.close(w)
+    assert qk.read_stream(fd=r, seekable=False)[0] == want
+    os.wait()
+    (tmp_path / "cut.bam").write_bytes(bgzf_compress(raw[:-40]))                                  # ends inside a record
+    with pytest.raises(qk.QkError):
+        qk.read_stream(tmp_path / "cut.bam")
+    (tmp_path / "tiny.gz").write_bytes(gzip.compress(b"AC"))                                      # gzip text shorter than the probe
+    assert qk.read_stream(tmp_path / "tiny.gz")[0] == b"AC"
+    (tmp_path / "text.gz").write_bytes(gzip.compress(b"BAM is not what this is\n"))
+    assert qk.read_stream(tmp_path / "text.gz")[0] == b"BAM is not what this is\n"
