@@ -1010,7 +1010,7 @@ def gpu_arm(args):
         gather = ctx.bench_gather(int(desc.table_bytes), gran=32, loads_in_flight=8, n_gathers=1 << 30)
         h2d = ctx.bench_h2d(min(chunk_cap, 64 << 20), repeats=16)
     ext = bool(desc.has_ext) and not os.environ.get("QK_CLASSIC_KERNEL")
-    kernel_name = "qk_count_ext_kernel" if ext else "qk_count_kernel"
+    kernel_name = "qk_count_ext32_kernel" if ext else "qk_count_kernel"
     traffic, traffic_src = profile_traffic(kernel_name, args.workload, args.chunk_mib)
     probe_rate = stats["bucket_probes"] / max(1, launches) / (avg_launch_ms * 1e-3)
     roofline = {

@@ -91,6 +91,11 @@ void qk_stream_close(qk_stream *s);
 int qk_write_bin(const char *path, const uint16_t *counts, uint64_t n);
 /* Device -> .bin without a host copy of the whole array (qk_finish_pieces + fwrite). */
 int qk_write_bin_from_device(qk_ctx *ctx, const char *path);
+/* The GC control curve (Q.c:495-509) straight from the .qgc FILE: streamed through the pinned slots to the device
+ * by the reader threads (4.5 GB at human scale).  *entries_read < n_kmers = the file is short (the rest count as
+ * non-control); *bins_out_of_range = entries whose GC bin is above 400 (ignored). */
+int qk_gc_curve_file(qk_ctx *ctx, const char *qgc_path, uint64_t n_kmers, uint64_t sum[QK_GC_BINS], int64_t sumsq[QK_GC_BINS],
+                     uint64_t count[QK_GC_BINS], uint64_t *entries_read, uint64_t *bins_out_of_range);
 /* 401 lines "%.2f\t%f\t%i\t%f\n" of bin/4, mean, count, variance; *mean_depth receives the
  * figure printed as "Mean sequencing depth" (Q.c:539-540). */
 int qk_write_gc_txt(const char *path, const uint64_t sum[QK_GC_BINS], const int64_t sumsq[QK_GC_BINS],

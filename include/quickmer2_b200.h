@@ -206,6 +206,14 @@ int qk_finish_pieces(qk_ctx *ctx, qk_piece_fn consume, void *user);
 int qk_gc_curve(qk_ctx *ctx, const uint16_t *qgc, uint64_t n_kmers, uint64_t sum[QK_GC_BINS],
                 int64_t sumsq[QK_GC_BINS], uint64_t count[QK_GC_BINS]);
 
+/* The same from .qgc pieces in the slots' pinned buffers (qk_slot_host_buffer; count entries for the ordinals
+ * starting at ordinal_offset), H2D + histogram per piece on the slot's stream: what qk_gc_curve_file (qk_host.h)
+ * drives with its reader threads.  qk_wait_slot tells when a buffer may be refilled. */
+int qk_gc_begin(qk_ctx *ctx);
+int qk_gc_from_slot(qk_ctx *ctx, uint32_t slot, uint64_t ordinal_offset, uint64_t count);
+int qk_gc_end(qk_ctx *ctx, uint64_t sum[QK_GC_BINS], int64_t sumsq[QK_GC_BINS], uint64_t count[QK_GC_BINS],
+              uint64_t *bins_out_of_range);
+
 /* ------------------------------------------------------------------ several GPUs -----
  * One process, one context per device: the dictionary built on context 0 is
  * replicated with ncclBroadcast, every context counts its share of the reads, the u32 counters

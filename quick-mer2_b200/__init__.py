@@ -131,6 +131,10 @@ SIGNATURES = {
     "qk_finish_async": (C.c_int, [_P, _P, C.c_uint64]),
     "qk_finish_wait": (C.c_int, [_P]),
     "qk_gc_curve": (C.c_int, [_P, _P, C.c_uint64, _P, _P, _P]),
+    "qk_gc_begin": (C.c_int, [_P]),
+    "qk_gc_from_slot": (C.c_int, [_P, C.c_uint32, C.c_uint64, C.c_uint64]),
+    "qk_gc_end": (C.c_int, [_P, _P, _P, _P, _U64P]),
+    "qk_gc_curve_file": (C.c_int, [_P, C.c_char_p, C.c_uint64, _P, _P, _P, _U64P, _U64P]),
     "qk_timing": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), _U64P]),
     "qk_span_begin": (C.c_int, [_P]),
     "qk_span_end": (C.c_int, [_P, C.POINTER(C.c_double)]),

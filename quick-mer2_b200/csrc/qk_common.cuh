@@ -94,6 +94,7 @@ struct qk_ctx {
     cudaStream_t finish_stream;         // qk_finish_async: the result download runs here, beside the slot streams
     cudaEvent_t finish_done;
     int finish_pending;
+    unsigned long long *gc_acc;         // qk_gc_begin .. qk_gc_end: 3 x 401 sums + 1 count of out-of-range bins
 
     // device-side record framing (qk_frame.cu)
     unsigned long long *frame_stream;   // device: [0] FSM state, [1] read lines, [2] bases, [3] raw lines

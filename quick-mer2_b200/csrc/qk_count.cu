@@ -1313,7 +1313,7 @@ extern "C" int qk_finish_wait(qk_ctx *ctx)
 #define QK_GC_PER_CTA 16384
 __global__ void __launch_bounds__(256) qk_gc_kernel(const uint32_t *__restrict__ counters, const uint16_t *__restrict__ qgc,
                                                     uint64_t n, unsigned long long *sum, long long *sumsq,
-                                                    unsigned long long *count)
+                                                    unsigned long long *count, unsigned long long *big)
 {
     __shared__ uint32_t h_cnt[QK_GC_BINS], h_sum[QK_GC_BINS], h_lo[QK_GC_BINS], h_hi[QK_GC_BINS], h_neg[QK_GC_BINS];
     for (int i = threadIdx.x; i < QK_GC_BINS; i += blockDim.x) h_cnt[i] = h_sum[i] = h_lo[i] = h_hi[i] = h_neg[i] = 0;
@@ -1324,7 +1324,10 @@ __global__ void __launch_bounds__(256) qk_gc_kernel(const uint32_t *__restrict__
         const uint32_t g = qgc[i];
         if (!(g & 0x8000u)) continue;
         const uint32_t bin = g & 0x1FFu;
-        if (bin >= QK_GC_BINS) continue;
+        if (bin >= QK_GC_BINS) {                  // the reference indexes past its arrays here (Q.c:504-507): dropped, and counted
+            if (big) atomicAdd(big, 1ull);
+            continue;
+        }
         const uint32_t d = counters[i] & 0xFFFFu;
         const uint32_t u = d * d;
         atomicAdd(&h_cnt[bin], 1u);
@@ -1363,7 +1366,7 @@ extern "C" int qk_gc_curve(qk_ctx *ctx, const uint16_t *qgc, uint64_t n_kmers, u
         e = cudaMemcpy(dq, qgc + at, m * sizeof(uint16_t), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) break;
         qk_gc_kernel<<<(unsigned)((m + QK_GC_PER_CTA - 1) / QK_GC_PER_CTA), 256>>>(
-            ctx->counters + at, dq, m, acc, reinterpret_cast<long long *>(acc + QK_GC_BINS), acc + 2 * QK_GC_BINS);
+            ctx->counters + at, dq, m, acc, reinterpret_cast<long long *>(acc + QK_GC_BINS), acc + 2 * QK_GC_BINS, nullptr);
         e = cudaGetLastError();
     }
     unsigned long long host[3 * QK_GC_BINS];
@@ -1378,3 +1381,55 @@ extern "C" int qk_gc_curve(qk_ctx *ctx, const uint16_t *qgc, uint64_t n_kmers, u
     }
     return QK_OK;
 }
+
+// The curve from .qgc pieces that sit in the slots' pinned buffers (the host's reader threads put them there):
+// H2D + histogram kernel per piece on the slot's stream, so the 4.5 GB .qgc of a human-scale dictionary goes through
+// at ingest speed instead of through one fread and a pageable copy.
+extern "C" int qk_gc_begin(qk_ctx *ctx)
+{
+    if (!ctx) return QK_ERR_ARG;
+    if (ctx->dict_state != 2) return qk_fail(ctx, QK_ERR_STATE, "no dictionary built on this context");
+    int rc = qk_sync(ctx);
+    if (rc) return rc;
+    QK_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->gc_acc) QK_CUDA(ctx, cudaMalloc((void **)&ctx->gc_acc, (3 * QK_GC_BINS + 1) * sizeof(unsigned long long)));
+    QK_CUDA(ctx, cudaMemsetAsync(ctx->gc_acc, 0, (3 * QK_GC_BINS + 1) * sizeof(unsigned long long), ctx->slots[0].stream));
+    QK_CUDA(ctx, cudaStreamSynchronize(ctx->slots[0].stream));
+    return QK_OK;
+}
+
+extern "C" int qk_gc_from_slot(qk_ctx *ctx, uint32_t slot, uint64_t ordinal_offset, uint64_t count)
+{
+    if (!ctx || slot >= ctx->n_slots || !ctx->gc_acc) return QK_ERR_ARG;
+    if (ordinal_offset + count > ctx->desc.n_kmers || count * sizeof(uint16_t) > ctx->chunk_capacity)
+        return qk_fail(ctx, QK_ERR_ARG, ".qgc piece outside the dictionary or larger than a slot");
+    if (count == 0) return QK_OK;
+    QK_CUDA(ctx, cudaSetDevice(ctx->device));
+    qk_slot *sl = &ctx->slots[slot];
+    QK_CUDA(ctx, cudaMemcpyAsync(sl->dev, sl->host, count * sizeof(uint16_t), cudaMemcpyHostToDevice, sl->stream));
+    QK_CUDA(ctx, cudaEventRecord(sl->h2d_done, sl->stream));
+    unsigned long long *acc = ctx->gc_acc;
+    qk_gc_kernel<<<(unsigned)((count + QK_GC_PER_CTA - 1) / QK_GC_PER_CTA), 256, 0, sl->stream>>>(
+        ctx->counters + ordinal_offset, reinterpret_cast<const uint16_t *>(sl->dev), count, acc,
+        reinterpret_cast<long long *>(acc + QK_GC_BINS), acc + 2 * QK_GC_BINS, acc + 3 * QK_GC_BINS);
+    QK_CUDA(ctx, cudaGetLastError());
+    return QK_OK;
+}
+
+extern "C" int qk_gc_end(qk_ctx *ctx, uint64_t sum[QK_GC_BINS], int64_t sumsq[QK_GC_BINS], uint64_t count[QK_GC_BINS],
+                         uint64_t *bins_out_of_range)
+{
+    if (!ctx || !sum || !sumsq || !count || !ctx->gc_acc) return QK_ERR_ARG;
+    int rc = qk_sync(ctx);
+    if (rc) return rc;
+    unsigned long long host[3 * QK_GC_BINS + 1];
+    QK_CUDA(ctx, cudaMemcpy(host, ctx->gc_acc, sizeof host, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < QK_GC_BINS; ++i) {
+        sum[i] = host[i];
+        sumsq[i] = (int64_t)host[QK_GC_BINS + i];
+        count[i] = host[2 * QK_GC_BINS + i];
+    }
+    if (bins_out_of_range) *bins_out_of_range = host[3 * QK_GC_BINS];
+    return QK_OK;
+}
+

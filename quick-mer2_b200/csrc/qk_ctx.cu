@@ -123,6 +123,7 @@ extern "C" void qk_ctx_destroy(qk_ctx *ctx)
     cudaFree(ctx->frame_stream);
     cudaFree(ctx->frame_elems);
     cudaFree(ctx->narrow_dev);
+    cudaFree(ctx->gc_acc);
     if (ctx->narrow_host) cudaFreeHost(ctx->narrow_host);
     cudaGetLastError();
     free(ctx);

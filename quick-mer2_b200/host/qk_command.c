@@ -25,28 +25,6 @@ static void help_count(void)
     puts("-g [list]\tCUDA device index, or a comma-separated list to shard the reads over several GPUs (default 0)");
 }
 
-typedef struct {
-    char path[65536];
-    uint64_t n;
-    uint16_t *data;      /* n entries, zero where the file is short; NULL if the allocation failed */
-    uint64_t got;        /* entries really read */
-    uint64_t big_bins;   /* entries whose GC bin is beyond the 401 the curve has */
-    int opened;
-} qgc_prefetch;
-
-static void *qgc_reader(void *arg)
-{
-    qgc_prefetch *j = arg;
-    j->data = calloc(j->n ? j->n : 1, sizeof(uint16_t));
-    FILE *f = j->data ? fopen(j->path, "rb") : NULL;
-    if (f) {
-        j->got = fread(j->data, sizeof(uint16_t), j->n, f);
-        fclose(f);
-        for (uint64_t i = 0; i < j->got; ++i) j->big_bins += (j->data[i] & 0x1FFu) >= QK_GC_BINS;
-    }
-    return NULL;
-}
-
 static double now_sec(void)
 {
     struct timespec ts;
@@ -126,18 +104,6 @@ int qk_count_main(int argc, char **argv)
     rc = qk_multi_replicate(m);                          /* ncclBroadcast of the table to the other GPUs */
     if (rc) { printf("Dictionary broadcast failed: %s\n", qk_multi_last_error(m)); qk_multi_destroy(m); return 1; }
     printf("Read 0x%lX hash\n", (unsigned long)hdr.hash_size);            /* Q.c:359 */
-    /* Q.c:484-488: the reference opens ref.qgc after counting; here a thread reads it meanwhile */
-    qgc_prefetch qgc_job = {0};
-    pthread_t qgc_thread;
-    snprintf(qgc_job.path, sizeof qgc_job.path, "%s.qgc", ref_prefix);
-    qgc_job.n = n_kmers;
-    {
-        FILE *probe = fopen(qgc_job.path, "rb");
-        if (probe) {
-            fclose(probe);
-            qgc_job.opened = pthread_create(&qgc_thread, NULL, qgc_reader, &qgc_job) == 0;
-        }
-    }
     double t1 = now_sec();
     time_t start_time, end_time;
     time(&start_time);                                                     /* Q.c:387 */
@@ -180,7 +146,6 @@ int qk_count_main(int argc, char **argv)
     if (!rc) rc = qk_multi_reduce(m);                    /* ncclReduce of the counters into GPU 0 */
     if (rc) {
         printf("Counting failed: %s / %s\n", qk_last_error(ctx), qk_multi_last_error(m));
-        if (qgc_job.opened) { pthread_join(qgc_thread, NULL); free(qgc_job.data); }
         qk_multi_destroy(m);
         return 1;
     }
@@ -200,36 +165,34 @@ int qk_count_main(int argc, char **argv)
     rc = qk_write_bin_from_device(ctx, path);
     if (rc) {
         printf("Cannot write %s: %s\n", path, rc == QK_ERR_IO ? "I/O error" : qk_last_error(ctx));
-        if (qgc_job.opened) { pthread_join(qgc_thread, NULL); free(qgc_job.data); }
         qk_multi_destroy(m);
         return 1;
     }
+    double t_bin = now_sec();
 
     snprintf(path, sizeof path, "%s.qgc", ref_prefix);                     /* Q.c:484-488 */
-    if (!qgc_job.opened) printf("GC control file %s absent. Continue without GC correction!\n", path);
+    uint64_t sum[QK_GC_BINS], cnt[QK_GC_BINS], qgc_entries = 0, big_bins = 0;
+    int64_t sq[QK_GC_BINS];
+    /* the .qgc streams through the pinned slots to the device, like the dictionary did (Q.c:495-509) */
+    rc = qk_gc_curve_file(ctx, path, n_kmers, sum, sq, cnt, &qgc_entries, &big_bins);
+    if (rc == QK_ERR_IO) printf("GC control file %s absent. Continue without GC correction!\n", path);
     else {
-        pthread_join(qgc_thread, NULL);                 /* the .qgc was read while the reads were counted */
-        uint16_t *qgc = qgc_job.data;
-        if (!qgc) { puts("Memory allocation failed"); qk_multi_destroy(m); return 1; }
+        if (rc) { printf("GC curve failed: %s\n", qk_last_error(ctx)); qk_multi_destroy(m); return 1; }
         /* Inputs on which the reference itself is undefined (it reuses stale buffer contents for a short
          * .qgc and indexes past its 401 bins, Q.c:499-508): handled deterministically here, and said aloud. */
-        if (qgc_job.got < n_kmers)
+        if (qgc_entries < n_kmers)
             fprintf(stderr, "quicKmer2_b200: %s holds %llu entries, the dictionary %llu: the missing ones are taken as non-control\n",
-                    path, (unsigned long long)qgc_job.got, (unsigned long long)n_kmers);
-        if (qgc_job.big_bins)
+                    path, (unsigned long long)qgc_entries, (unsigned long long)n_kmers);
+        if (big_bins)
             fprintf(stderr, "quicKmer2_b200: %s has %llu entries with a GC bin above 400: ignored in the curve\n", path,
-                    (unsigned long long)qgc_job.big_bins);
-        uint64_t sum[QK_GC_BINS], cnt[QK_GC_BINS];
-        int64_t sq[QK_GC_BINS];
-        rc = qk_gc_curve(ctx, qgc, n_kmers, sum, sq, cnt);
-        free(qgc);
-        if (rc) { printf("GC curve failed: %s\n", qk_last_error(ctx)); qk_multi_destroy(m); return 1; } /* qgc freed above */
+                    (unsigned long long)big_bins);
         double mean = 0;
         snprintf(path, sizeof path, "%s.txt", out_prefix);                 /* Q.c:523-525 */
         if (qk_write_gc_txt(path, sum, sq, cnt, &mean)) { printf("Cannot write %s\n", path); qk_multi_destroy(m); return 1; }
         printf("Mean sequencing depth: %.2f\n", mean);                     /* Q.c:540 */
     }
     double t3 = now_sec();
+    if (getenv("QK_TIMING")) fprintf(stderr, "[qk] .bin written in %.3f s, GC curve + .txt in %.3f s\n", t_bin - t2, t3 - t_bin);
     double kms = 0, hms = 0;
     uint64_t launches = 0;
     qk_timing(ctx, &kms, &hms, &launches);

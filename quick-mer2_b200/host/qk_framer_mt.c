@@ -76,6 +76,7 @@ typedef struct {
     uint16_t tab[2][256];                /* the line state machine from all four entry states at once */
     size_t stage_cap;                    /* bytes of a worker's staging buffer */
     int nt;                              /* staged non-temporal stores (QK_FRAMER_NT=0 turns them off) */
+    int populate;                        /* the input is a file mapping: populate each block's pages in one call */
 } mt_job;
 
 /* ---- line scan + state machine ------------------------------------------------------------ */
@@ -361,6 +362,12 @@ static void *worker(void *arg)
         const uint64_t i = atomic_fetch_add(&j->next_block, 1);
         if (i >= j->n_blocks) return NULL;
         const size_t a = (size_t)(i * j->block), b = a + j->block < n ? a + j->block : n;
+#ifdef MADV_POPULATE_READ
+        {   /* a mapped file: one call maps the block's pages instead of a fault per 4 KiB (harmless on ordinary memory) */
+            const uintptr_t pg = (uintptr_t)sysconf(_SC_PAGESIZE) - 1, lo = ((uintptr_t)(d + a)) & ~pg, hi = ((uintptr_t)(d + b)) & ~pg;
+            if (j->populate && hi > lo) madvise((void *)lo, hi - lo, MADV_POPULATE_READ);
+        }
+#endif
         /* 1 + 2. the lines that start in [a, b) -- the first one begins at 0 for block 0, else after the first
          * '\n' at or after a - 1 -- and the state machine over them from each entry state */
         size_t first = 0;
@@ -434,6 +441,8 @@ static void *worker(void *arg)
     }
 }
 
+static __thread int qk_mt_input_is_mapping;   /* set by qk_count_file_mt around its call */
+
 static uint32_t default_threads(uint32_t n_ctx)
 {
     const char *e = getenv("QK_FRAMER_THREADS");
@@ -469,6 +478,7 @@ int qk_frame_mem_mt(const qk_chunk_sink *sink, const uint8_t *data, size_t n, in
     j->cur_ctx = j->cur_slot = -1;
     j->avx512 = __builtin_cpu_supports("avx512bw") && !getenv("QK_NO_AVX512");
     { const char *e = getenv("QK_FRAMER_NT"); j->nt = e ? atoi(e) != 0 : 1; }
+    j->populate = qk_mt_input_is_mapping;
     build_table(j->tab, j->fastq);
     j->stage_cap = j->block + ((size_t)128 << 10);
     if (!threads) threads = default_threads(j->n_ctx);
@@ -652,7 +662,9 @@ int qk_count_file_mt(qk_ctx *const *ctxs, uint32_t n_ctx, const char *reads_path
     close(fd);
     if (map == MAP_FAILED) return QK_ERR_IO;
     madvise(map, (size_t)sb.st_size, MADV_SEQUENTIAL);
+    qk_mt_input_is_mapping = getenv("QK_NO_POPULATE") == NULL;
     int rc = qk_count_mem_mt(ctxs, n_ctx, map, (size_t)sb.st_size, 1, threads, st);
+    qk_mt_input_is_mapping = 0;
     munmap(map, (size_t)sb.st_size);
     return rc;
 }

@@ -441,14 +441,17 @@ static int count_range_mt(qk_ctx *ctx, int fd, uint64_t begin, uint64_t end, uin
     return rc ? rc : g.err;
 }
 
-static int qm_upload_array(qk_ctx *ctx, int fd, uint64_t file_off, uint64_t n_elems, int kind, uint32_t threads)
+/* A file range of fixed-size elements through the slots' pinned buffers: reader threads pread() pieces in parallel,
+ * this thread hands them over IN ORDER: handle(ctx, slot, element offset, element count, user). */
+typedef int (*piece_handler)(qk_ctx *ctx, uint32_t slot, uint64_t elem_offset, uint64_t count, void *user);
+static int ingest_elements(qk_ctx *ctx, int fd, uint64_t file_off, uint64_t n_elems, size_t esz, uint32_t threads,
+                           piece_handler handle, void *user)
 {
     qk_ingest g;
     memset(&g, 0, sizeof g);
     size_t cap = 0;
     int rc = qk_ctx_info(ctx, &g.n_slots, &cap);
     if (rc) return rc;
-    const size_t esz = kind ? 4 : 8;
     g.ctx = ctx;
     g.fd = fd;
     g.begin = file_off;
@@ -473,7 +476,7 @@ static int qm_upload_array(qk_ctx *ctx, int fd, uint64_t file_off, uint64_t n_el
         const size_t have = g.filled_len[slot];
         pthread_mutex_unlock(&g.mu);
         if (rc) break;
-        rc = qk_dict_upload_from_slot(ctx, slot, kind, i * (g.body / esz), have / esz);
+        rc = handle(ctx, slot, i * (g.body / esz), have / esz, user);
         pthread_mutex_lock(&g.mu);
         g.submitted = i + 1;
         pthread_cond_broadcast(&g.cv);
@@ -487,6 +490,42 @@ static int qm_upload_array(qk_ctx *ctx, int fd, uint64_t file_off, uint64_t n_el
     pthread_mutex_destroy(&g.mu);
     pthread_cond_destroy(&g.cv);
     return rc ? rc : g.err;
+}
+
+static int qm_piece(qk_ctx *ctx, uint32_t slot, uint64_t elem_offset, uint64_t count, void *user)
+{
+    return qk_dict_upload_from_slot(ctx, slot, *(int *)user, elem_offset, count);
+}
+
+static int qm_upload_array(qk_ctx *ctx, int fd, uint64_t file_off, uint64_t n_elems, int kind, uint32_t threads)
+{
+    return ingest_elements(ctx, fd, file_off, n_elems, kind ? 4 : 8, threads, qm_piece, &kind);
+}
+
+static int gc_piece(qk_ctx *ctx, uint32_t slot, uint64_t elem_offset, uint64_t count, void *user)
+{
+    (void)user;
+    return qk_gc_from_slot(ctx, slot, elem_offset, count);
+}
+
+/* Q.c:484-488, 495-509: the .qgc flags of every dictionary k-mer against the final depths.  The file is streamed
+ * to the device like the dictionary was; entries it lacks are taken as non-control (*entries_read tells). */
+int qk_gc_curve_file(qk_ctx *ctx, const char *qgc_path, uint64_t n_kmers, uint64_t sum[QK_GC_BINS], int64_t sumsq[QK_GC_BINS],
+                     uint64_t count[QK_GC_BINS], uint64_t *entries_read, uint64_t *bins_out_of_range)
+{
+    if (!ctx || !qgc_path) return QK_ERR_ARG;
+    int fd = open(qgc_path, O_RDONLY);
+    if (fd < 0) return QK_ERR_IO;
+    struct stat sb;
+    if (fstat(fd, &sb) != 0) { close(fd); return QK_ERR_IO; }
+    uint64_t n = (uint64_t)sb.st_size / 2;
+    if (n > n_kmers) n = n_kmers;
+    if (entries_read) *entries_read = n;
+    int rc = qk_gc_begin(ctx);
+    if (!rc && n) rc = ingest_elements(ctx, fd, 0, n, 2, qk_reader_threads_default(), gc_piece, NULL);
+    close(fd);
+    if (rc) return rc;
+    return qk_gc_end(ctx, sum, sumsq, count, bins_out_of_range);
 }
 
 static int file_is_gzip(const char *path)
