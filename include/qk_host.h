@@ -170,6 +170,16 @@ int qk_count_raw_range_mt(qk_ctx *ctx, const char *reads_path, uint64_t begin, u
  * context 0 alone.  Call qk_multi_reduce afterwards. */
 int qk_count_file_multi(qk_multi *m, const char *reads_path, uint32_t threads_per_gpu, qk_framer_stats *st);
 
+/* ---- est: main_estimate, Q.c:555-685, with the window reduction on the device -----------------------
+ * quicKmer2 est ref.fa sample_prefix output.bed -- same files, same stdout, same bytes in output.bed; the LOWESS
+ * curve still comes from `smooth_GC_mrsfast.py <sample>.txt` on the PATH (Q.c:642-650).  qk_est_reduce is the
+ * reduction alone for a caller that has the curve: one value per line the reference would print (values_out and
+ * line_window_out are malloc'd, n_lines entries each; line i belongs to window line_window_out[i]). */
+int qk_est_main(int argc, char **argv);
+int qk_est_reduce(qk_ctx *ctx, const char *qgc_path, const char *bin_path, const float correction[QK_GC_BINS], double mean_depth,
+                  const uint32_t *left, const uint32_t *right, uint64_t n_windows, double **values_out, uint64_t **line_window_out,
+                  uint64_t *n_lines);
+
 /* ---- the command: main_count, Q.c:304-545 -----------------------------------------------
  * quicKmer2 count [-h] [-t N] [-g device[,device...]] ref_prefix reads out_prefix
  * Same positional-from-the-end convention, same stdout lines, same files. */

@@ -214,6 +214,18 @@ int qk_gc_from_slot(qk_ctx *ctx, uint32_t slot, uint64_t ordinal_offset, uint64_
 int qk_gc_end(qk_ctx *ctx, uint64_t sum[QK_GC_BINS], int64_t sumsq[QK_GC_BINS], uint64_t count[QK_GC_BINS],
               uint64_t *bins_out_of_range);
 
+/* ------------------------------------------------------------------ est: window depths -
+ * Q.c:660-682 on the device.  qk_est_begin allocates two arrays of n_entries uint16 (a sample's depths,
+ * the .qgc flags); qk_est_upload_from_slot fills them from the pinned slot buffers (kind 0 = depths,
+ * 1 = flags); qk_est_windows returns, per window w, the sum over k-mers lo[w] .. hi[w]-1 of
+ * correction[flags & 0x1FF] * depth -- float product, double accumulation, ordinal order: the reference's
+ * arithmetic, so the results print to the same bytes.  No dictionary is needed on the context. */
+int qk_est_begin(qk_ctx *ctx, uint64_t n_entries);
+int qk_est_upload_from_slot(qk_ctx *ctx, uint32_t slot, int kind, uint64_t elem_offset, uint64_t count);
+int qk_est_windows(qk_ctx *ctx, const float correction[QK_GC_BINS], const uint64_t *lo, const uint64_t *hi,
+                   uint64_t n_windows, double *sums_out);
+int qk_est_end(qk_ctx *ctx);
+
 /* ------------------------------------------------------------------ several GPUs -----
  * One process, one context per device: the dictionary built on context 0 is
  * replicated with ncclBroadcast, every context counts its share of the reads, the u32 counters

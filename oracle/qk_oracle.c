@@ -358,11 +358,77 @@ int qko_count(const char *ref_prefix, const char *reads_path, const char *out_pr
     return 0;
 }
 
+/* ---- est: window depths (Q.c:555-685), given the correction curve ----------------------------------
+ * The reference gets its 401-float correction curve from `popen("smooth_GC_mrsfast.py <sample>.txt")`
+ * (Q.c:642-650: LOWESS in Python); everything else of main_estimate is restated here with the curve as
+ * an input: mean depth from <sample>.txt (Q.c:626-638), then one pass over <ref>.qgc / <sample>.bin in
+ * blocks of 1 MiB BYTES, accumulating correction[gc & 0x1FF] * depth (a float product added to a double)
+ * into the current <ref>.bed window [left, right) and printing a window when the first k-mer index
+ * >= right comes by (Q.c:660-682) -- including what that loop does after the last window: it leaves the
+ * inner loop only, so every further block prints that window once more, its value divided again. */
+#define QKO_EST_BLOCK (1024 * 1024)
+int qko_est(const char *ref_prefix, const char *sample_prefix, const char *out_path, const float *correction /* 401 */)
+{
+    char path[4096];
+    snprintf(path, sizeof path, "%s.qgc", ref_prefix);
+    FILE *fg = fopen(path, "rb");
+    snprintf(path, sizeof path, "%s.bed", ref_prefix);
+    FILE *fw = fopen(path, "r");
+    snprintf(path, sizeof path, "%s.bin", sample_prefix);
+    FILE *fd = fopen(path, "rb");
+    snprintf(path, sizeof path, "%s.txt", sample_prefix);
+    FILE *ft = fopen(path, "r");
+    FILE *fo = fopen(out_path, "w");
+    if (!fg || !fw || !fd || !ft || !fo) return 1;
+    char word[255];
+    double total_depth = 0;
+    uint64_t total_count = 0;
+    float percent, depth_f;
+    uint32_t n;
+    while (fscanf(ft, "%f\t%f\t%i\t%254s\n", &percent, &depth_f, &n, word) == 4) { /* Q.c:633-636 */
+        total_depth += depth_f * n;                                                    /* float * uint32 -> float */
+        total_count += n;
+    }
+    total_depth /= total_count;
+    fclose(ft);
+    static uint16_t gc[QKO_EST_BLOCK], dep[QKO_EST_BLOCK];
+    double cur = 0.0;
+    uint64_t idx = 0;
+    char chrom[64], wb[64], we[64];
+    uint32_t left = 0, right = 0;
+    int have = fscanf(fw, "%63s\t%63s\t%63s\t%u\t%u\n", chrom, wb, we, &left, &right) == 5;   /* Q.c:657 */
+    (void)have;
+    uint32_t got;
+    while ((got = (uint32_t)fread(gc, 1, QKO_EST_BLOCK, fg)) != 0) {
+        if (fread(dep, 1, got, fd) != got) { /* short .bin: the reference uses what is in the buffer */ }
+        got >>= 1;
+        for (uint32_t i = 0; i < got; ++i, ++idx) {
+            if (idx >= right) {                                                            /* Q.c:667-675 */
+                cur /= right - left;
+                cur /= total_depth / 2;
+                fprintf(fo, "%s\t%s\t%s\t%f\n", chrom, wb, we, cur);
+                if (fscanf(fw, "%63s\t%63s\t%63s\t%u\t%u\n", chrom, wb, we, &left, &right) != 5) break;
+                cur = 0.0;
+            }
+            if (idx < right && idx >= left) cur += correction[gc[i] & 0x1FF] * dep[i];    /* Q.c:677-679 */
+        }
+    }
+    fclose(fo); fclose(fg); fclose(fw); fclose(fd);
+    return 0;
+}
+
 #ifdef QKO_MAIN
 int main(int argc, char **argv)
 {
+    if (argc == 6 && !strcmp(argv[1], "est")) {        /* qk_oracle est ref_prefix sample_prefix out.bed curve.f32 */
+        float corr[512] = {0};
+        FILE *f = fopen(argv[5], "rb");
+        if (!f || fread(corr, 4, 401, f) != 401) { fprintf(stderr, "qk_oracle: cannot read the 401-float curve\n"); return 1; }
+        fclose(f);
+        return qko_est(argv[2], argv[3], argv[4], corr);
+    }
     if (argc < 5 || strcmp(argv[1], "count")) {
-        fprintf(stderr, "usage: qk_oracle count ref_prefix reads out_prefix\n");
+        fprintf(stderr, "usage: qk_oracle count ref_prefix reads out_prefix | qk_oracle est ref_prefix sample_prefix out.bed curve.f32\n");
         return 1;
     }
     qko_stats st;

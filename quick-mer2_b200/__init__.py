@@ -134,6 +134,10 @@ SIGNATURES = {
     "qk_gc_begin": (C.c_int, [_P]),
     "qk_gc_from_slot": (C.c_int, [_P, C.c_uint32, C.c_uint64, C.c_uint64]),
     "qk_gc_end": (C.c_int, [_P, _P, _P, _P, _U64P]),
+    "qk_est_begin": (C.c_int, [_P, C.c_uint64]),
+    "qk_est_upload_from_slot": (C.c_int, [_P, C.c_uint32, C.c_int, C.c_uint64, C.c_uint64]),
+    "qk_est_windows": (C.c_int, [_P, _P, _P, _P, C.c_uint64, _P]),
+    "qk_est_end": (C.c_int, [_P]),
     "qk_gc_curve_file": (C.c_int, [_P, C.c_char_p, C.c_uint64, _P, _P, _P, _U64P, _U64P]),
     "qk_timing": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), _U64P]),
     "qk_span_begin": (C.c_int, [_P]),
@@ -186,6 +190,8 @@ SIGNATURES = {
                                         C.POINTER(FramerStats), C.POINTER(C.c_uint32)]),
     "qk_count_file_multi": (C.c_int, [_P, C.c_char_p, C.c_uint32, C.POINTER(FramerStats)]),
     "qk_count_main": (C.c_int, [C.c_int, C.POINTER(C.c_char_p)]),
+    "qk_est_main": (C.c_int, [C.c_int, C.POINTER(C.c_char_p)]),
+    "qk_est_reduce": (C.c_int, [_P, C.c_char_p, C.c_char_p, _P, C.c_double, _P, _P, C.c_uint64, C.POINTER(_P), C.POINTER(_P), _U64P]),
 }
 
 _lib = None

@@ -94,6 +94,8 @@ struct qk_ctx {
     cudaStream_t finish_stream;         // qk_finish_async: the result download runs here, beside the slot streams
     cudaEvent_t finish_done;
     int finish_pending;
+    uint16_t *est_depth, *est_qgc;      // qk_est_begin .. qk_est_end: a sample's depths and the GC flags, by ordinal
+    uint64_t est_n;
     unsigned long long *gc_acc;         // qk_gc_begin .. qk_gc_end: 3 x 401 sums + 1 count of out-of-range bins
 
     // device-side record framing (qk_frame.cu)

@@ -124,6 +124,8 @@ extern "C" void qk_ctx_destroy(qk_ctx *ctx)
     cudaFree(ctx->frame_elems);
     cudaFree(ctx->narrow_dev);
     cudaFree(ctx->gc_acc);
+    cudaFree(ctx->est_depth);
+    cudaFree(ctx->est_qgc);
     if (ctx->narrow_host) cudaFreeHost(ctx->narrow_host);
     cudaGetLastError();
     free(ctx);

@@ -443,9 +443,8 @@ static int count_range_mt(qk_ctx *ctx, int fd, uint64_t begin, uint64_t end, uin
 
 /* A file range of fixed-size elements through the slots' pinned buffers: reader threads pread() pieces in parallel,
  * this thread hands them over IN ORDER: handle(ctx, slot, element offset, element count, user). */
-typedef int (*piece_handler)(qk_ctx *ctx, uint32_t slot, uint64_t elem_offset, uint64_t count, void *user);
-static int ingest_elements(qk_ctx *ctx, int fd, uint64_t file_off, uint64_t n_elems, size_t esz, uint32_t threads,
-                           piece_handler handle, void *user)
+int qk_ingest_elements(qk_ctx *ctx, int fd, uint64_t file_off, uint64_t n_elems, size_t esz, uint32_t threads,
+                       qk_piece_handler handle, void *user)
 {
     qk_ingest g;
     memset(&g, 0, sizeof g);
@@ -499,7 +498,7 @@ static int qm_piece(qk_ctx *ctx, uint32_t slot, uint64_t elem_offset, uint64_t c
 
 static int qm_upload_array(qk_ctx *ctx, int fd, uint64_t file_off, uint64_t n_elems, int kind, uint32_t threads)
 {
-    return ingest_elements(ctx, fd, file_off, n_elems, kind ? 4 : 8, threads, qm_piece, &kind);
+    return qk_ingest_elements(ctx, fd, file_off, n_elems, kind ? 4 : 8, threads, qm_piece, &kind);
 }
 
 static int gc_piece(qk_ctx *ctx, uint32_t slot, uint64_t elem_offset, uint64_t count, void *user)
@@ -522,7 +521,7 @@ int qk_gc_curve_file(qk_ctx *ctx, const char *qgc_path, uint64_t n_kmers, uint64
     if (n > n_kmers) n = n_kmers;
     if (entries_read) *entries_read = n;
     int rc = qk_gc_begin(ctx);
-    if (!rc && n) rc = ingest_elements(ctx, fd, 0, n, 2, qk_reader_threads_default(), gc_piece, NULL);
+    if (!rc && n) rc = qk_ingest_elements(ctx, fd, 0, n, 2, qk_reader_threads_default(), gc_piece, NULL);
     close(fd);
     if (rc) return rc;
     return qk_gc_end(ctx, sum, sumsq, count, bins_out_of_range);

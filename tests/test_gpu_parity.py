@@ -14,7 +14,7 @@ import numpy as np
 import pytest
 
 import oracle_binding
-from conftest import GOLDEN, golden_cases, golden_meta, weird_stream
+from conftest import GOLDEN, ROOT as ROOT_DIR, golden_cases, golden_meta, weird_stream
 
 pytestmark = pytest.mark.gpu
 
@@ -738,21 +738,76 @@ def test_finish_async_overlaps_the_next_sample(qk, tmp_path):
                 qs.lib().qs_pinned_free(p)
 
 
-def test_bam_input(qk, tmp_path):
-    """A BAM of the golden reads (file and pipe): same .bin / .txt as the reference wrote for the FASTA --
-    what tutorial.md:144-146 gets through `samtools view | awk`."""
+def test_bam_input(qk, oracle, tmp_path):
+    """A BAM of reads (file and pipe): same .bin / .txt as the FASTA that `samtools view -F 3840 | awk` would
+    make of it (tutorial.md:144-146)."""
     from test_host import bgzf_compress, make_bam
     d = GOLDEN / "k30_fasta_t0"
     seqs = [l for l in (d / "reads.fa").read_text().split("\n") if l and not l.startswith(">")]
+    seqs = [s for s in seqs if set(s) <= set("ACGTN")]          # BAM stores upper-case IUPAC codes only
+    assert len(seqs) > 100
+    (tmp_path / "same.fa").write_text("".join(f">\n{s}\n" for s in seqs))
+    oracle.count(d / "ref.fa", tmp_path / "same.fa", tmp_path / "want")
     reads = [(f"q{i}", 16 if i % 2 else 0, s) for i, s in enumerate(seqs)]
     reads.insert(5, ("dup", 1024, seqs[0]))                       # dropped by -F 3840
     reads.insert(9, ("sec", 256, seqs[1]))
     (tmp_path / "r.bam").write_bytes(bgzf_compress(make_bam(reads), block=40000) + bgzf_compress(b""))
     res = qk.run_cli(["count", "-t", "3", d / "ref.fa", tmp_path / "r.bam", tmp_path / "b"])
     assert res.returncode == 0, res.stdout + res.stderr
-    assert (tmp_path / "b.bin").read_bytes() == (d / "expect.bin").read_bytes()
-    assert (tmp_path / "b.txt").read_bytes() == (d / "expect.txt").read_bytes()
+    assert (tmp_path / "b.bin").read_bytes() == (tmp_path / "want.bin").read_bytes()
+    assert (tmp_path / "b.txt").read_bytes() == (tmp_path / "want.txt").read_bytes()
+    assert np.fromfile(tmp_path / "b.bin", dtype=np.uint16).sum() > 0
     res = subprocess.run([str(qk.CLI_PATH), "count", str(d / "ref.fa"), "/dev/stdin", str(tmp_path / "p")],
                          input=(tmp_path / "r.bam").read_bytes(), capture_output=True)
     assert res.returncode == 0, res.stdout
-    assert (tmp_path / "p.bin").read_bytes() == (d / "expect.bin").read_bytes()
+    assert (tmp_path / "p.bin").read_bytes() == (tmp_path / "want.bin").read_bytes()
+
+
+# ------------------------------------------------------------------ est: window depths on the device
+@pytest.mark.parametrize("windows", ["contiguous", "list_ends_early", "gaps_overlaps_and_beyond"])
+def test_est_window_reduction(windows, qk, oracle, ref_binary, synth, tmp_path):
+    """`quicKmer2_b200 est ref sample out.bed` (Q.c:555-685, window reduction on the device) writes the bytes
+    the oracle's restatement writes -- which is pinned to the compiled reference in tests/test_oracle.py -- on a
+    dictionary of 1.4 M k-mers (three 1 MiB blocks of .qgc), incl. the lines the reference repeats after the
+    last window of the list, windows that overlap, leave gaps or lie beyond the data.  The Python smoother is a stub."""
+    from test_oracle import write_smooth_stub
+    synth("ref", "--out", tmp_path / "ref.fa", "--bases", 1500000, "--contigs", 3, "--seed", 21, "--segdups", 8, "--segdup-len", 4000,
+          "--nblock", 2000)
+    synth("dict", "--ref", tmp_path / "ref.fa", "--k", 30, "--ctrl-block", 25000)
+    synth("reads", "--ref", tmp_path / "ref.fa", "--out", tmp_path / "r.fq", "--n", 150000, "--len", 150, "--seed", 4, "--fastq")
+    res = qk.run_cli(["count", tmp_path / "ref.fa", tmp_path / "r.fq", tmp_path / "samp"])
+    assert res.returncode == 0, res.stdout + res.stderr
+    n = (tmp_path / "samp.bin").stat().st_size // 2
+    assert n > 2 * 524288
+    rng = np.random.default_rng(len(windows))
+    rows, at = [], 0
+    if windows == "contiguous":
+        while at + 700 <= n:
+            rows.append((at, at + 700)); at += 700
+    elif windows == "list_ends_early":                       # the list stops in the first block: two more blocks follow
+        while at + 900 <= 300000:
+            rows.append((at, at + 900)); at += 900
+    else:
+        while at < n + 5000:                                 # overlaps, gaps, empty and reversed ranges, past the end
+            size = int(rng.integers(1, 3000))
+            left = max(0, at + int(rng.integers(-500, 800)))
+            rows.append((left, left + size))
+            at = left + size
+    with open(tmp_path / "ref.fa.bed", "w") as f:
+        for i, (a, b) in enumerate(rows):
+            f.write(f"chr{1 + i % 3}\t{a * 2}\t{b * 2}\t{a}\t{b}\n")
+    env, curve = write_smooth_stub(tmp_path)
+    res = qk.run_cli(["est", tmp_path / "ref.fa", tmp_path / "samp", tmp_path / "ours.bed"], env=env)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "Mean sequencing depth" in res.stdout
+    port = ROOT_DIR / "oracle" / "_build" / "qk_oracle"
+    assert subprocess.run([str(port), "est", str(tmp_path / "ref.fa"), str(tmp_path / "samp"), str(tmp_path / "want.bed"), str(curve)]).returncode == 0
+    ours, want = (tmp_path / "ours.bed").read_bytes(), (tmp_path / "want.bed").read_bytes()
+    assert ours == want and ours.count(b"\n") >= 100
+    if windows == "list_ends_early":
+        assert ours.count(b"\n") == len(rows) + 2            # the last window, printed once more per remaining block
+    if ref_binary is not None:                               # and the reference itself, where it travelled
+        r = subprocess.run([str(ref_binary), "est", str(tmp_path / "ref.fa"), str(tmp_path / "samp"), str(tmp_path / "theirs.bed")],
+                           env=env, capture_output=True, text=True)
+        assert r.returncode == 0 and (tmp_path / "theirs.bed").read_bytes() == ours
+        assert [l for l in r.stdout.splitlines() if "depth" in l] == [l for l in res.stdout.splitlines() if "depth" in l]

@@ -12,7 +12,9 @@ import subprocess
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, golden_cases, golden_meta, weird_stream
+import os
+
+from conftest import GOLDEN, ROOT, golden_cases, golden_meta, weird_stream
 
 
 @pytest.mark.parametrize("case", golden_cases())
@@ -187,3 +189,44 @@ def test_synthetic_dictionary_equals_search(k, oracle, ref_binary, synth, tmp_pa
     bin_b, sb = oracle.count_bin(b / "ref.fa.qm", tmp_path / "r.fa")
     assert bin_a.size == bin_b.size > 200000
     assert np.array_equal(bin_a, bin_b) and sa["hits"] == sb["hits"] > 0
+
+
+SMOOTH_STUB = """#!/usr/bin/env python3
+# stand-in for the reference's smooth_GC_mrsfast.py (LOWESS; needs numpy.float and matplotlib, absent here):
+# 401 float32 on stdout, a deterministic curve with the same range the real one has (clamped to [1/3, 3])
+import math, struct, sys
+vals = [min(3.0, max(1 / 3, 1.0 + 0.8 * math.sin(i / 37.0) + (i % 11) * 0.013)) for i in range(401)]
+sys.stdout.buffer.write(struct.pack("<401f", *vals))
+"""
+
+
+def write_smooth_stub(d):
+    """smooth_GC_mrsfast.py on a PATH directory; returns (env for subprocesses, the curve as a file for qk_oracle est)."""
+    b = d / "stubbin"
+    b.mkdir(exist_ok=True)
+    (b / "smooth_GC_mrsfast.py").write_text(SMOOTH_STUB)
+    (b / "smooth_GC_mrsfast.py").chmod(0o755)
+    curve = subprocess.run([str(b / "smooth_GC_mrsfast.py")], capture_output=True, check=True).stdout
+    (d / "curve.f32").write_bytes(curve)
+    return dict(os.environ, PATH=f"{b}:{os.environ['PATH']}"), d / "curve.f32"
+
+
+def test_est_restatement_equals_the_reference(oracle, ref_binary, synth, tmp_path):
+    """qko_est (oracle) against the compiled reference's `est` (Q.c:555-685) on the reference's own search /
+    count outputs, the Python smoother replaced by a stub that prints a fixed curve: output.bed byte for byte."""
+    if ref_binary is None:
+        pytest.skip("compiled reference not available")
+    synth("ref", "--out", tmp_path / "ref.fa", "--bases", 400000, "--contigs", 2, "--seed", 12, "--segdups", 3, "--segdup-len", 3000,
+          "--nblock", 500)
+    synth("ctrl", "--ref", tmp_path / "ref.fa", "--out", tmp_path / "ctrl.bed", "--block", 20000)
+    run = lambda *a, **kw: subprocess.run([str(ref_binary), *map(str, a)], cwd=tmp_path, capture_output=True, text=True, **kw)
+    assert run("search", "-k", 30, "-e", 0, "-s", "1M", "-w", 700, "-c", "ctrl.bed", "ref.fa").returncode == 0
+    synth("reads", "--ref", tmp_path / "ref.fa", "--out", tmp_path / "r.fq", "--n", 60000, "--len", 150, "--seed", 4, "--fastq")
+    assert run("count", "-t", 3, "ref.fa", "r.fq", "samp").returncode == 0
+    env, curve = write_smooth_stub(tmp_path)
+    res = run("est", "ref.fa", "samp", "theirs.bed", env=env)
+    assert res.returncode == 0 and "Mean sequencing depth" in res.stdout
+    port = ROOT / "oracle" / "_build" / "qk_oracle"
+    assert subprocess.run([str(port), "est", "ref.fa", "samp", "port.bed", str(curve)], cwd=tmp_path).returncode == 0
+    theirs = (tmp_path / "theirs.bed").read_bytes()
+    assert theirs == (tmp_path / "port.bed").read_bytes() and theirs.count(b"\n") > 500
