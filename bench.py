@@ -421,7 +421,7 @@ def reference_arm(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
     cdir = cache_dir(args.cache_dir)
-    subprocess.run(["make", "-s", "-C", str(PKG_DIR), str(SYNTH)], check=True)
+    subprocess.run(["make", "-s", "-C", str(PKG_DIR), "all"], check=True)      # qk_synth and the GPU data generator (prebuilt files travel)
     if not REF_BIN.exists():                     # the compiled reference did not travel: time the port instead
         subprocess.run(["make", "-s", "-C", str(ROOT / "oracle"), "port"], check=True)
     w = (SYNTH_WORKLOADS if args.workload in SYNTH_WORKLOADS else WORKLOADS)[args.workload]
