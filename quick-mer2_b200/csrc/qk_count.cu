@@ -679,6 +679,13 @@ __device__ __forceinline__ uint32_t qk_extract16(const uint32_t *__restrict__ ex
     const uint32_t both = (__ldg(g) & 0xFFFFu) | (__ldg(g + QK_EXT_GROUP_WORDS) << 16);
     return (both >> (uint32_t)(q & 15)) & 0xFFFFu;
 }
+// 16 strand bits (F_o == K_o) starting at ordinal q: the high halves of the same words
+__device__ __forceinline__ uint32_t qk_extract16s(const uint32_t *__restrict__ ext, uint64_t q)
+{
+    const uint32_t *g = ext + (q >> 4) * QK_EXT_GROUP_WORDS + 2;
+    const uint32_t both = (__ldg(g) >> 16) | (__ldg(g + QK_EXT_GROUP_WORDS) & 0xFFFF0000u);
+    return (both >> (uint32_t)(q & 15)) & 0xFFFFu;
+}
 
 // Walk from position ja (-1 = the position just before this half) with ordinal oa over the 16 positions of a
 // half: c16 = their codes (first base in the top pair), resets16 = their reset flags.  Returns the positions
@@ -687,12 +694,13 @@ __device__ __forceinline__ uint32_t qk_extract16(const uint32_t *__restrict__ ex
 //          base of the next dictionary k-mer; on the other strand they go down and its complement is compared with
 //          the first base of the previous one.
 //   MODE 1 (k < 30, keys = forward k-mers): ordinals go up, read base against the last base of the next key.
-//   MODE 2 (k = 31, keys = 30-base reverse complements): ordinals go up, complemented read base against the TOP
-//          base of the next key.
-// In modes 1 and 2 the reference's key is min(forward k-mer, 30-base reverse complement) (Q.c:415-420): the walk
-// may only step onto a position whose key is certainly of the chain's type -- unc16 flags (even bit of each pair,
-// first position in the top pair) the positions where the read itself cannot settle that; they end the walk and
-// are probed like any other open position.
+//   MODE 2 (k = 31): the keys are 30-mers too -- the newest 30 bases -- stored forward iff the 31st base back is A and
+//          forward <= reverse complement, else reverse-complemented (Q.c:415-420 with a 60-bit register).  The walk
+//          is MODE 0's over the 30-mers, in both directions; a step also needs the read's key to have the FORM the
+//          dictionary stored for that ordinal: form16 = per position, "the read's key is the forward 30-mer".
+// In mode 1 the walk may only step onto a position whose key is certainly the forward k-mer -- unc16 flags (even bit
+// of each pair, first position in the top pair) the positions where the read itself cannot settle that; they end
+// the walk and are probed like any other open position.
 template <int MODE>
 __device__ __forceinline__ uint32_t qk_walk16(const qk_table_view &tv, uint64_t oa, bool plus, int ja, uint32_t c16, uint32_t resets16,
                                               uint32_t unc16)
@@ -701,17 +709,15 @@ __device__ __forceinline__ uint32_t qk_walk16(const qk_table_view &tv, uint64_t 
     if (nsteps == 0 || !(plus || oa >= 16)) return 0;
     const uint32_t sh = (uint32_t)(ja + 1);               // 0..15
     uint32_t R = qk_rev16pairs(c16) >> (2 * sh);          // read base of step i (position ja + i) in bits 2i-1 : 2i-2
-    uint32_t D, Cb;
-    if (MODE == 2) {
-        D = qk_extract32(tv.ext, oa + 1, 1);
-        Cb = qk_extract16(tv.ext, oa + 1);
-        R ^= 0xAAAAAAAAu;
-    } else if (MODE == 1 || plus) {
+    uint32_t D, Cb, St = 0;
+    if (MODE == 1 || plus) {
         D = qk_extract32(tv.ext, oa + 1, 0);
         Cb = qk_extract16(tv.ext, oa + 1);
+        if (MODE == 2) St = qk_extract16s(tv.ext, oa + 1);            // step i: strand bit of ordinal oa + i in bit i - 1
     } else {
         D = qk_rev16pairs(qk_extract32(tv.ext, oa - 16, 1));
         Cb = __brev(qk_extract16(tv.ext, oa - 15)) >> 16;
+        if (MODE == 2) St = ~(__brev(qk_extract16s(tv.ext, oa - 16)) >> 16); // ordinal oa - i; on this strand the forms swap
         R ^= 0xAAAAAAAAu;
     }
     const uint32_t X = D ^ R;
@@ -721,9 +727,13 @@ __device__ __forceinline__ uint32_t qk_walk16(const qk_table_view &tv, uint64_t 
     if (brk) len = min(len, (uint32_t)__ffs(brk) - 1);
     const uint32_t rs = (resets16 & 0xFFFFu) >> sh;
     if (rs) len = min(len, (uint32_t)__ffs(rs) - 1);
-    if (MODE != 0) {
+    if (MODE == 1) {
         const uint32_t U = (qk_rev16pairs(unc16) >> (2 * sh)) & 0x55555555u;
         if (U) len = min(len, (uint32_t)(__ffs(U) - 1) >> 1);
+    }
+    if (MODE == 2) {   // unc16 here: bit j = the read's key at position j is the FORWARD 30-mer; it must be the stored form
+        const uint32_t bad = ((unc16 >> sh) ^ St) & 0xFFFFu;
+        if (bad) len = min(len, (uint32_t)__ffs(bad) - 1);
     }
     len = min(len, nsteps);
     return ((1u << len) - 1) << sh;
@@ -862,10 +872,23 @@ __global__ void __launch_bounds__(QK_THREADS, MINB) qk_count_ext32_kernel(const 
                     have += step;
                 }
                 unc = lo;
-            } else if (MODE == 2) {   // the key is the 30-base reverse complement unless the oldest of the 31 bases is A (code 0)
+            }
+            uint32_t form32 = 0;      // mode 2: bit j = the key at my position j is the FORWARD 30-mer (else its reverse complement)
+            if (MODE == 2) {          // that needs an A 30 positions back AND forward <= reverse complement (Q.c:420)
                 const uint64_t Wp = sm.codes[lane];
                 const uint64_t lo = ~(W | (W >> 1)) & 0x5555555555555555ull, hi = ~(Wp | (Wp >> 1)) & 0x5555555555555555ull;
-                unc = (lo >> 60) | (hi << 4);             // the flag of the base 30 positions back
+                uint64_t isA = (lo >> 60) | (hi << 4);    // pair-indexed, first position in the top pair: the base 30 back is A
+                uint32_t cand = 0;                        // the same, position-indexed
+#pragma unroll
+                for (int j = 0; j < 32; ++j) cand |= (uint32_t)((isA >> (2 * (31 - j))) & 1u) << j;
+                cand &= emit;
+                while (cand) {
+                    const uint32_t j = __ffs(cand) - 1;
+                    cand &= cand - 1;
+                    bool f;
+                    key_at(32 * lane + j, &f);
+                    form32 |= (uint32_t)f << j;
+                }
             }
             uint32_t verified = 0, anchors = 0;
             // ---- first half: anchor = my first emitting position; walk the dictionary order from it -------
@@ -876,7 +899,7 @@ __global__ void __launch_bounds__(QK_THREADS, MINB) qk_count_ext32_kernel(const 
             for (int half = 0; half < 2; ++half) {
                 const uint32_t eh = half ? e1 : e0;
                 const uint32_t c16 = half ? (uint32_t)W : (uint32_t)(W >> 32);
-                const uint32_t u16 = half ? (uint32_t)unc : (uint32_t)(unc >> 32);
+                const uint32_t u16 = MODE == 2 ? (form32 >> (16 * half)) & 0xFFFFu : half ? (uint32_t)unc : (uint32_t)(unc >> 32);
                 const uint32_t r16 = (my_mask >> (16 * half)) & 0xFFFFu;
                 int ja = -1;
                 uint32_t a_ord1 = 0;
@@ -896,8 +919,8 @@ __global__ void __launch_bounds__(QK_THREADS, MINB) qk_count_ext32_kernel(const 
                     ++n_probe;
                     anchors |= 1u << (16 * half + ja);
                     oa = a_ord1 ? a_ord1 - 1 : 0;
-                    if (MODE == 0) plus = (a_strand != 0) == a_fwd;
-                    else walkable = MODE == 1 ? a_fwd : !a_fwd;   // the anchor's key is of the chain's type (exact compare)
+                    if (MODE != 1) plus = (a_strand != 0) == a_fwd;   // the read runs along F_o iff its key has F_o's form
+                    else walkable = a_fwd;                            // mode 1: the anchor's key is the forward k-mer (exact compare)
                 }
                 uint32_t ve = 0;
                 if (a_ord1 && eh && walkable) {

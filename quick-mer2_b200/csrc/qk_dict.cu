@@ -274,7 +274,7 @@ __global__ void qk_orient_insert_kernel(const unsigned long long *__restrict__ k
     const uint64_t M58 = ((uint64_t)1 << 58) - 1;
     bool have_prev = false;
     uint64_t prevF = 0;
-    uint32_t wl = 0, wf = 0, wc = 0;
+    uint32_t wl = 0, wf = 0, wc = 0, ws = 0;
     for (uint64_t o = begin; o < end; ++o) {
         const uint64_t raw = kbo[o];
         const uint64_t K = raw & ~QK_KBO_SKIP;
@@ -287,11 +287,8 @@ __global__ void qk_orient_insert_kernel(const unsigned long long *__restrict__ k
                 cont = have_prev && (K >> 2) == (prevF & (kmask >> 2));
                 prevF = K;
                 have_prev = true;
-            } else if (with_ext == 3) {   // reverse-complement chain: continues iff K_o = (K_{o-1} >> 2) | base << 58
-                cont = have_prev && (K & M58) == (prevF >> 2);
-                prevF = K;
-                have_prev = true;
-            } else if (with_ext) {
+            } else if (with_ext) {        // 1: canonical 30-mers; 3: k = 31, whose keys are 30-mers too -- the newest 30 bases,
+                                          // forward when the 31st base back is A and that is the smaller form, else reverse complement
                 const uint64_t Kr = qk_rc30(K);
                 if (have_prev) {
                     const uint64_t want = prevF & M58;
@@ -317,12 +314,13 @@ __global__ void qk_orient_insert_kernel(const unsigned long long *__restrict__ k
             wl |= (uint32_t)(F & 3) << (2 * (i & 15));
             wf |= (uint32_t)((F >> 58) & 3) << (2 * (i & 15));
             wc |= cont << (i & 15);
+            ws |= ((raw & QK_KBO_SKIP) ? 0u : strand) << (i & 15);
             if ((i & 15) == 15 || o + 1 == end) {                // one group of 16 ordinals: three adjacent words
                 uint32_t *g = ext + (o >> 4) * QK_EXT_GROUP_WORDS;
                 g[0] = wl;
                 g[1] = wf;
-                g[2] = wc;
-                wl = wf = wc = 0;
+                g[2] = wc | (ws << 16);                          // high half: F_o == K_o (read by the k = 31 walk)
+                wl = wf = wc = ws = 0;
             }
         }
     }
@@ -375,8 +373,9 @@ static void qk_geometry(uint64_t n, uint32_t k, uint64_t stash_slots_min, qk_tab
     // dictionary-order extension arrays (k = 30 only: for other k the reference's canonical key
     // mixes a k-mer with a 30-base reverse complement, Q.c:415-420, and is not a walkable k-mer)
     // which dictionary-order chain the keys form (qk_count.cu, qk_count_ext32_kernel): 1 = canonical 30-mers (k = 30);
-    // 2 = forward k-mers (k < 30: the key is the forward k-mer unless the newest bases are all T); 3 = 30-base
-    // reverse complements (k = 31: unless the oldest base is A); 0 = none (k = 32: every read key is 0, Q.c:419)
+    // 2 = forward k-mers (k < 30: the key is the forward k-mer unless the newest bases are all T); 3 = 30-mers in
+    // the form the k = 31 key rule gives them (forward iff the 31st base back is A and forward <= reverse
+    // complement); 0 = none (k = 32: every read key is 0, Q.c:419)
     d->has_ext = getenv("QK_NO_EXT") != NULL ? 0 : k == 30 ? 1 : (k >= 3 && k < 30) ? 2 : k == 31 ? 3 : 0;
     d->ext_bytes = d->has_ext ? ((n + 15) / 16 + 4) * QK_EXT_GROUP_WORDS * sizeof(uint32_t) : 0; // 5 bits per ordinal in groups of 16, padded
     d->cont_bytes = 0;                                                        // (the continuation bits live in the same array)
