@@ -30,7 +30,7 @@ extern "C" {
 #define QK_ERR_ARG 2    /* bad argument                                            */
 #define QK_ERR_NOMEM 3  /* host or device allocation failed (Q.c:354-366 return 1) */
 #define QK_ERR_STATE 4  /* call out of order                                       */
-#define QK_ERR_FORMAT 5 /* dictionary is not a valid QM11 chain                    */
+#define QK_ERR_FORMAT 5 /* the chain does not come back to first_idx                */
 
 #define QK_GC_BINS 401          /* Q.c:495-497 */
 #define QK_MAX_LINE_BYTES 99999 /* Q.c:388,397: fgets(line, 100000) incl. the '\n' */

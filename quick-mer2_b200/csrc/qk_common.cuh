@@ -10,7 +10,7 @@
 //   key     -> h = mix60(key) (a bijection on [0, 2^60)); bucket = top bucket_bits of h,
 //              remainder = low rem_bits = 60 - bucket_bits of h (quotienting: the bucket
 //              index is implied, so remainder + ordinal fit one 64-bit word)
-//   stash   = open-addressed {key, ordinal+1} 16-byte entries for the keys whose home
+//   stash   = open-addressed {key | 2^63, ordinal+1} 16-byte entries for the keys whose home
 //              bucket was full at build time; consulted only when a bucket is full
 // Every key a read can produce is < 2^60 because the reference's reverse-complement
 // register is 60 bits wide for every k (Q.c:415-416,420), so 60-bit keys lose nothing.
@@ -33,6 +33,7 @@
 
 struct __align__(32) qk_bucket { unsigned long long e[QK_BUCKET_ENTRIES]; };
 struct __align__(16) qk_stash_entry { unsigned long long key; uint32_t ord1; uint32_t pad; };
+#define QK_STASH_TAKEN 0x8000000000000000ull   // set in a used stash entry's key (keys are < 2^60, and 0 is a key)
 
 // Everything the count kernel needs, passed by value.
 struct qk_table_view {

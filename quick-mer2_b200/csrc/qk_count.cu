@@ -129,7 +129,7 @@ __device__ __noinline__ uint32_t qk_stash_find(const qk_table_view &tv, uint64_t
     for (;;) {
         const uint4 v = __ldg(reinterpret_cast<const uint4 *>(tv.stash + s));
         const uint64_t sk = ((uint64_t)v.y << 32) | v.x;
-        if (sk == key) {
+        if (sk == (key | QK_STASH_TAKEN)) {
             if (strand) *strand = v.w & 1u;
             return v.z;
         }

@@ -9,16 +9,21 @@
 //     the table is rebuilt with a strong mixer, 32-byte buckets and quotiented entries
 //
 // List ranking (DESIGN.md "dictionary build"):
-//   1. every occupied slot s with s % stride == 0, plus first_idx (the head), is a
-//      splitter; one thread per splitter walks next[] to the following splitter and
-//      records (successor, segment length)                                  [walk kernel]
+//   1. every slot s with s % stride == 0, plus first_idx (the head), is a splitter; one
+//      thread per splitter walks next[] to the following splitter and records
+//      (successor, segment length)                                          [walk kernel]
 //   2. pointer jumping (Wyllie) over the short splitter list gives each splitter its
-//      distance to the end of the chain, hence its ordinal                  [jump kernel]
-//   3. every splitter re-walks its segment handing out consecutive ordinals and inserts
-//      (key -> ordinal) into the new table                                [insert kernel]
-// A valid QM11 chain is a simple cycle through exactly the occupied slots; anything else
-// (chain length != occupied slots, an empty slot on the chain, a walk that never ends) is
-// rejected with QK_ERR_FORMAT.
+//      distance to the end of the chain, hence its ordinal, and marks the splitters the
+//      head reaches                                                         [jump kernel]
+//   3. every marked splitter re-walks its segment handing out consecutive ordinals
+//                                                                        [scatter kernel]
+// What the reference's `count` reads is the cycle that starts at first_idx, whatever else
+// the arrays hold (Q.c:498-516), so that is what is ranked.  Occupied slots that are not on
+// the chain (`sparse` leaves them behind when it thins without resizing, Q.c:1443-1461) take
+// part in Find_hash's probing but never get an ordinal; an EMPTY slot on the chain (an
+// `index` input containing the poly-A k-mer, key 0) gets one, and receives the counts of
+// key-0 k-mers iff it is the slot Find_hash(0) stops at (Q.c:98).  Only a chain that does
+// not come back to first_idx is rejected (QK_ERR_FORMAT).
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -26,7 +31,7 @@
 
 #include "qk_common.cuh"
 
-// A walk ends at the next occupied slot that is a multiple of the stride; chain order is
+// A walk ends at the next slot that is a multiple of the stride; chain order is
 // unrelated to slot order, so segment lengths are geometric with mean = stride (<= 512) and
 // 2^20 steps is unreachable for a valid dictionary placed by hashing.
 #define QK_WALK_CAP (1u << 20)
@@ -39,7 +44,7 @@ static double qk_now(void)
     return ts.tv_sec + ts.tv_nsec * 1e-9;
 }
 
-enum { QK_FLAG_WALK_CAP = 1, QK_FLAG_EMPTY_ON_CHAIN = 2, QK_FLAG_STASH_FULL = 4 };
+enum { QK_FLAG_WALK_CAP = 1, QK_FLAG_STASH_FULL = 4 };
 
 struct qk_build_info {
     unsigned long long occupied;
@@ -113,23 +118,15 @@ extern "C" int qk_dict_upload_from_slot(qk_ctx *ctx, uint32_t slot, int kind, ui
 }
 
 // ---- kernels ---------------------------------------------------------------------------
-__global__ void qk_count_occupied(const uint64_t *__restrict__ keys, uint64_t n, qk_build_info *info)
-{
-    unsigned long long local = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-        local += keys[i] != 0;
-    for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
-    if ((threadIdx.x & 31) == 0 && local) atomicAdd(&info->occupied, local);
-}
 
-// Node ids: 0..n_split-1 = slot id*stride, n_split = head (first_idx), n_split+1 = END.
-__device__ __forceinline__ bool qk_node_slot(uint64_t id, uint64_t n_split, uint32_t stride_log2, uint64_t first,
-                                             const uint64_t *keys, uint64_t *slot)
+// Node ids: 0..n_split-1 = slot id*stride (occupied or not: an empty slot can be on the chain), n_split = head
+// (first_idx), n_split+1 = END.
+__device__ __forceinline__ bool qk_node_slot(uint64_t id, uint64_t n_split, uint32_t stride_log2, uint64_t first, uint64_t *slot)
 {
     if (id == n_split) { *slot = first; return true; }
     uint64_t s = id << stride_log2;
     *slot = s;
-    return s != first && keys[s] != 0;
+    return s != first;
 }
 
 __global__ void qk_walk_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ next, uint64_t n_split,
@@ -140,7 +137,8 @@ __global__ void qk_walk_kernel(const uint64_t *__restrict__ keys, const uint32_t
     if (id > n_split + 1) return;
     const uint32_t END = (uint32_t)(n_split + 1);
     uint64_t slot;
-    if (id == n_split + 1 || !qk_node_slot(id, n_split, stride_log2, first, keys, &slot)) {
+    (void)keys;
+    if (id == n_split + 1 || !qk_node_slot(id, n_split, stride_log2, first, &slot)) {
         succ[id] = END; dist[id] = 0; seg_len[id] = 0;
         return;
     }
@@ -151,21 +149,34 @@ __global__ void qk_walk_kernel(const uint64_t *__restrict__ keys, const uint32_t
         c = next[c];
         ++len;
     } while (c != first && (c & smask) != 0 && len < QK_WALK_CAP);
-    if (len >= QK_WALK_CAP) atomicOr(&info->flags, QK_FLAG_WALK_CAP);
+    (void)info;
     succ[id] = (c == first) ? END : (uint32_t)(c >> stride_log2);
     dist[id] = len;
-    seg_len[id] = len;
+    seg_len[id] = len;      // == QK_WALK_CAP: the walk did not end (fatal only if the head reaches this node)
 }
 
 // One round of pointer jumping: dist = distance (in chain entries) to END.
+// ... and of reachability from the head: succ_in is succ^(2^j) in round j, so marking
+// succ_in[i] for every marked i doubles the marked prefix of the chain each round (a node
+// marked during the round may or may not pass it on in the same round; the nodes it would
+// reach are reached from already-marked ones in the next).
 __global__ void qk_jump_kernel(const uint32_t *__restrict__ succ_in, const unsigned long long *__restrict__ dist_in,
-                               uint32_t *succ_out, unsigned long long *dist_out, uint64_t n_nodes)
+                               uint32_t *succ_out, unsigned long long *dist_out, uint64_t n_nodes, unsigned char *mark)
 {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_nodes) return;
     uint32_t s = succ_in[i];
     dist_out[i] = dist_in[i] + dist_in[s];
     succ_out[i] = succ_in[s];
+    if (mark[i]) mark[s] = 1;
+}
+
+// a walk that hit the cap matters only on the chain
+__global__ void qk_check_caps_kernel(const uint32_t *__restrict__ seg_len, const unsigned char *__restrict__ mark, uint64_t n_nodes,
+                                     qk_build_info *info)
+{
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_nodes && mark[i] && seg_len[i] >= QK_WALK_CAP) atomicOr(&info->flags, QK_FLAG_WALK_CAP);
 }
 
 // Does Find_hash (Q.c:90-99) reach `slot` when asked for its own key?  False only for the
@@ -211,7 +222,7 @@ __device__ __forceinline__ void qk_table_insert(const qk_build_params &bp, uint6
     if (used >= bp.stash_limit) { atomicOr(&info->flags, QK_FLAG_STASH_FULL); return; }
     uint64_t s = qk_mix_stash(key) & bp.stash_mask;
     for (;;) {
-        unsigned long long old = atomicCAS(&bp.stash[s].key, 0ull, (unsigned long long)key);
+        unsigned long long old = atomicCAS(&bp.stash[s].key, 0ull, (unsigned long long)key | QK_STASH_TAKEN);
         if (old == 0ull) { bp.stash[s].ord1 = (uint32_t)ord1; bp.stash[s].pad = strand; return; }
         s = (s + 1) & bp.stash_mask;
     }
@@ -224,10 +235,11 @@ __device__ __forceinline__ void qk_table_insert(const qk_build_params &bp, uint6
 __global__ void qk_scatter_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ next, uint64_t hash_size,
                                   uint64_t n_split, uint32_t stride_log2, uint64_t first,
                                   const unsigned long long *__restrict__ dist, const uint32_t *__restrict__ seg_len,
-                                  unsigned long long total, unsigned long long *__restrict__ kbo, qk_build_info *info)
+                                  const unsigned char *__restrict__ mark, unsigned long long total,
+                                  unsigned long long *__restrict__ kbo, qk_build_info *info)
 {
     uint64_t id = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (id > n_split) return;
+    if (id > n_split || !mark[id]) return;      // only the walkers the head reaches are on the chain
     uint32_t len = seg_len[id];
     if (len == 0) return;
     uint64_t c = (id == n_split) ? first : (id << stride_log2);
@@ -235,7 +247,9 @@ __global__ void qk_scatter_kernel(const uint64_t *__restrict__ keys, const uint3
     for (uint32_t i = 0; i < len; ++i, ++ord) {
         uint64_t key = keys[c];
         uint64_t nx = next[c];
-        if (key == 0) atomicOr(&info->flags, QK_FLAG_EMPTY_ON_CHAIN);
+        // (key 0 = an empty slot on the chain: it gets an ordinal like any other, and is the
+        //  one Find_hash(0) reaches iff it is the first empty slot on key 0's probe path --
+        //  exactly what qk_is_primary checks)
         if ((key >> QK_KEY_BITS) != 0 || !qk_is_primary(keys, hash_size, c, key)) {
             atomicAdd(&info->skipped, 1ull);
             key |= QK_KBO_SKIP;
@@ -436,6 +450,8 @@ extern "C" int qk_dict_build(qk_ctx *ctx, uint64_t *n_kmers_out)
     double tm0 = qk_now(), tm1 = tm0, tm2 = tm0, tm3 = tm0;
     qk_build_info *info = NULL;
     uint32_t *succ[2] = {NULL, NULL}, *seg_len = NULL;
+    unsigned char *mark = NULL;
+    uint32_t head_succ = 0;
     unsigned long long *dist[2] = {NULL, NULL};
     int rc = QK_OK;
 #define QK_TRY(call)                                                               \
@@ -457,16 +473,19 @@ extern "C" int qk_dict_build(qk_ctx *ctx, uint64_t *n_kmers_out)
         QK_TRY(cudaMalloc((void **)&dist[i], n_nodes * sizeof(unsigned long long)));
     }
     QK_TRY(cudaMalloc((void **)&seg_len, n_nodes * sizeof(uint32_t)));
+    QK_TRY(cudaMalloc((void **)&mark, n_nodes));
+    QK_TRY(cudaMemset(mark, 0, n_nodes));
+    QK_TRY(cudaMemset(mark + n_split, 1, 1));    // the head
 
-    qk_count_occupied<<<ctx->sm_count * 8, 256>>>(ctx->raw_keys, H, info);
     qk_walk_kernel<<<(unsigned)((n_nodes + 127) / 128), 128>>>(ctx->raw_keys, ctx->raw_next, n_split, stride_log2, first,
                                                                succ[0], dist[0], seg_len, info);
     QK_TRY(cudaGetLastError());
     for (uint64_t span = 1; span < n_nodes; span <<= 1) {
         qk_jump_kernel<<<(unsigned)((n_nodes + 255) / 256), 256>>>(succ[cur], dist[cur], succ[cur ^ 1], dist[cur ^ 1],
-                                                                   n_nodes);
+                                                                   n_nodes, mark);
         cur ^= 1;
     }
+    qk_check_caps_kernel<<<(unsigned)((n_nodes + 255) / 256), 256>>>(seg_len, mark, n_nodes, info);
     QK_TRY(cudaGetLastError());
     QK_TRY(cudaMemcpy(&total, dist[cur] + n_split, sizeof total, cudaMemcpyDeviceToHost));
     QK_TRY(cudaMemcpy(&hinfo, info, sizeof hinfo, cudaMemcpyDeviceToHost));
@@ -474,10 +493,12 @@ extern "C" int qk_dict_build(qk_ctx *ctx, uint64_t *n_kmers_out)
         rc = qk_fail(ctx, QK_ERR_FORMAT, "chain walk did not reach a splitter within %u steps: corrupt chain", QK_WALK_CAP);
         goto done;
     }
-    if (total != hinfo.occupied || total == 0) {
-        rc = qk_fail(ctx, QK_ERR_FORMAT,
-                     "chain from first_idx has %llu entries but the table holds %llu keys: not a QM11 chain", total,
-                     hinfo.occupied);
+    QK_TRY(cudaMemcpy(&head_succ, succ[cur] + n_split, sizeof head_succ, cudaMemcpyDeviceToHost));
+    // (after >= n_nodes jumps the head either points at END or sits on a cycle that never
+    //  comes back to first_idx; a path that does come back is a simple cycle, so it cannot
+    //  be longer than the table)
+    if (head_succ != (uint32_t)(n_split + 1) || total == 0 || total > H) {
+        rc = qk_fail(ctx, QK_ERR_FORMAT, "the chain from first_idx does not come back to it: not a QM11 chain");
         goto done;
     }
 
@@ -486,13 +507,9 @@ extern "C" int qk_dict_build(qk_ctx *ctx, uint64_t *n_kmers_out)
     QK_TRY(cudaMalloc((void **)&kbo, (total + 1) * sizeof(unsigned long long)));
     QK_TRY(cudaMemset(info, 0, sizeof(qk_build_info)));
     qk_scatter_kernel<<<(unsigned)((n_split + 1 + 127) / 128), 128>>>(ctx->raw_keys, ctx->raw_next, H, n_split, stride_log2, first,
-                                                                      dist[cur], seg_len, total, kbo, info);
+                                                                      dist[cur], seg_len, mark, total, kbo, info);
     QK_TRY(cudaGetLastError());
     QK_TRY(cudaMemcpy(&hinfo, info, sizeof hinfo, cudaMemcpyDeviceToHost));
-    if (hinfo.flags & QK_FLAG_EMPTY_ON_CHAIN) {
-        rc = qk_fail(ctx, QK_ERR_FORMAT, "the chain passes through an empty slot: not a QM11 chain");
-        goto done;
-    }
     skipped = hinfo.skipped;
     tm2 = qk_now(); // keys scattered by ordinal
     cudaFree(ctx->raw_keys);
@@ -543,6 +560,7 @@ done:
     cudaFree(succ[0]); cudaFree(succ[1]);
     cudaFree(dist[0]); cudaFree(dist[1]);
     cudaFree(seg_len);
+    cudaFree(mark);
     cudaFree(ctx->raw_keys);
     cudaFree(ctx->raw_next);
     ctx->raw_keys = NULL;

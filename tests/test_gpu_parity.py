@@ -9,6 +9,7 @@ Three anchors:
 """
 import os
 import subprocess
+from pathlib import Path
 
 import numpy as np
 import pytest
@@ -326,10 +327,82 @@ def test_corrupt_chain_is_rejected(qk, oracle, gpu_ctx):
         gpu_ctx.load_dictionary_arrays(30, keys, bad, first)
     assert e.value.code == 5                            # QK_ERR_FORMAT
     bad = nxt.copy()
-    bad[first] = np.flatnonzero(keys == 0)[0]           # chain runs into an empty slot
+    bad[first] = np.flatnonzero(keys == 0)[0]           # chain runs into an empty slot and from there to slot 0, for ever
+    bad[0] = 0
+    with pytest.raises(qk.QkError) as e:
+        gpu_ctx.load_dictionary_arrays(30, keys, bad, first)
+    assert e.value.code == 5
+    bad = nxt.copy()
+    chain = chain_slots(nxt, first)
+    bad[chain[20]] = chain[3]                           # a cycle that does not contain first
     with pytest.raises(qk.QkError):
         gpu_ctx.load_dictionary_arrays(30, keys, bad, first)
     assert gpu_ctx.load_dictionary_arrays(30, keys, nxt, first) == order.size   # and the intact one loads
+
+
+def read_qm(path):
+    raw = Path(path).read_bytes()
+    H = int.from_bytes(raw[8:16], "little")
+    keys = np.frombuffer(raw, dtype="<u8", count=H, offset=24).copy()
+    nxt = np.frombuffer(raw, dtype="<u4", count=H, offset=24 + 8 * H).copy()
+    return raw[4], keys, nxt, int.from_bytes(raw[16:24], "little")
+
+
+def chain_slots(nxt, first):
+    out, c = [], first
+    while True:
+        out.append(c)
+        c = int(nxt[c])
+        if c == first:
+            return out
+
+
+def test_occupied_slots_off_the_chain(mid_dict, qk, oracle, synth, gpu_ctx, tmp_path):
+    """`sparse` thins the chain and, when enough k-mers are left, keeps the table as it is (Q.c:1443-1461): the
+    dropped keys stay in their slots.  `count` still finds them (Q.c:90-99) but never prints them -- and a key that
+    sits behind a dropped copy of itself is never reached."""
+    k, keys, nxt, first = read_qm(mid_dict / "ref.fa.qm")
+    slots = chain_slots(nxt, first)
+    keep = [s for i, s in enumerate(slots) if i % 3 != 1 or i == 0]           # every third entry leaves the chain
+    assert keep[0] == first
+    for a, b in zip(keep, keep[1:] + keep[:1]):
+        nxt[a] = b
+    oracle_binding.write_qm(tmp_path / "thin.qm", k, keys, nxt, first)
+    synth("reads", "--ref", mid_dict / "ref.fa", "--out", tmp_path / "r.fa", "--n", 60000, "--len", 150, "--seed", 8)
+    want, ost = oracle.count_bin(tmp_path / "thin.qm", tmp_path / "r.fa")
+    got, st = gpu_bin(gpu_ctx, tmp_path / "thin.qm", tmp_path / "r.fa")
+    assert want.size == len(keep) < len(slots) and np.count_nonzero(keys) == len(slots)
+    assert np.array_equal(got, want) and want.sum() > 0
+    assert st["total_kmers"] == ost["total_kmers"]
+
+
+def test_empty_slot_on_the_chain(mid_dict, qk, oracle, synth, gpu_ctx, tmp_path):
+    """An `index` input holding the poly-A k-mer puts key 0 -- an empty slot -- on the chain.  Find_hash(0) stops at
+    the first empty slot of its probe path and "finds" it (Q.c:98), so that slot, if it is the one on the chain,
+    collects the poly-A/poly-T k-mers; any other empty slot on the chain is an entry that stays 0."""
+    k, keys, nxt, first = read_qm(mid_dict / "ref.fa.qm")
+    H = keys.size
+    c = oracle.djb(0) & (H - 1)
+    step = -1 if c & (H >> 1) else 1
+    while keys[c] != 0:
+        c += step
+    found, other = c, int(np.flatnonzero(keys == 0)[-1])
+    assert found != other
+    slots = chain_slots(nxt, first)
+    at = {found: 1000, other: 5}
+    for e, i in at.items():                                     # splice e in after the i-th entry
+        nxt[e] = nxt[slots[i]]
+        nxt[slots[i]] = e
+    oracle_binding.write_qm(tmp_path / "a.qm", k, keys, nxt, first)
+    synth("reads", "--ref", mid_dict / "ref.fa", "--out", tmp_path / "r.fa", "--n", 20000, "--len", 150, "--seed", 9)
+    with open(tmp_path / "r.fa", "a") as f:
+        f.write(">polyA\n" + "A" * 70 + "\n>polyT\n" + "T" * 45 + "\n>mixed\n" + "A" * 29 + "C" + "A" * 40 + "\n")
+    want, ost = oracle.count_bin(tmp_path / "a.qm", tmp_path / "r.fa")
+    got, st = gpu_bin(gpu_ctx, tmp_path / "a.qm", tmp_path / "r.fa")
+    assert want.size == len(slots) + 2 and np.array_equal(got, want)
+    order = chain_slots(nxt, first)
+    assert want[order.index(found)] == 41 + 16 + 11 and want[order.index(other)] == 0
+    assert st["total_kmers"] == ost["total_kmers"]
 
 
 # ------------------------------------------------------------------ dictionary-order extension
