@@ -179,6 +179,12 @@ int qk_reset_counters(qk_ctx *ctx);
 int qk_counters_select(qk_ctx *ctx, uint32_t which);
 /* The same, stream-ordered (no host synchronisation): for jobs run back to back. */
 int qk_reset_counters_async(qk_ctx *ctx);
+/* n more occurrences of the canonical key `key`, as if the reads had held them (nothing happens if
+ * the dictionary does not hold it).  Replaces Q.c:458-466 + 284-291: with -t N the reference pads its
+ * last batch of 4,096 keys with zeros and looks them up like any key, which is observable when the
+ * empty slot Find_hash(0) stops at is on the chain (Q.c:98) -- the command calls this with key 0 and
+ * 4,096 - total_kmers % 4,096 when it is given -t N, N > 0.  Syncs. */
+int qk_add_depth(qk_ctx *ctx, uint64_t key, uint32_t n);
 /* Copy `count` raw uint32 counters starting at ordinal `offset` to host memory (syncs). */
 int qk_counters_download(qk_ctx *ctx, uint64_t offset, uint32_t *out, uint64_t count);
 

@@ -314,8 +314,26 @@ int qko_gc_write(qko_gc *g, const char *txt_path)
     return 0;
 }
 
+/* ---- Q.c:458-466, 284-291: `count -t N`, N > 0.  K-mers travel to the workers in batches of FIFO_size = 4,096
+ * (Q.c:12); the last batch is filled up with zeros -- a whole batch of them when the total is a multiple of
+ * 4,096 -- and the workers look every entry up.  Find_hash(0) "finds" the first empty slot on key 0's path, so
+ * that slot's depth grows by the padding.  Returns the padding. */
+uint64_t qko_fifo_padding(const qko_dict *d, uint64_t total_kmers, uint16_t *depth)
+{
+    uint64_t pad = 4096 - total_kmers % 4096, slot;
+    qko_find(d, 0, &slot);
+    depth[slot] = (uint16_t)(depth[slot] + pad);
+    return pad;
+}
+
 /* ---- whole command: Q.c:304-545 ---------------------------------------------------- */
+int qko_count_t(const char *ref_prefix, const char *reads_path, const char *out_prefix, unsigned threads, qko_stats *st);
 int qko_count(const char *ref_prefix, const char *reads_path, const char *out_prefix, qko_stats *st)
+{
+    return qko_count_t(ref_prefix, reads_path, out_prefix, 0, st);
+}
+
+int qko_count_t(const char *ref_prefix, const char *reads_path, const char *out_prefix, unsigned threads, qko_stats *st)
 {
     char path[4096];
     qko_dict d;
@@ -328,6 +346,7 @@ int qko_count(const char *ref_prefix, const char *reads_path, const char *out_pr
     if (!depth) return 3;
     qko_count_stream(&d, reads, depth, st);
     fclose(reads);
+    if (threads & 0xFF) qko_fifo_padding(&d, st->total_kmers, depth);   /* uint8_t thread_count, Q.c:306 */
 
     uint64_t n = qko_chain_length(&d);
     uint16_t *ordered = malloc(n * sizeof(uint16_t));

@@ -123,6 +123,7 @@ SIGNATURES = {
     "qk_counters_device_ptr": (C.c_int, [_P, C.POINTER(_P), _U64P]),
     "qk_reset_counters": (C.c_int, [_P]),
     "qk_reset_counters_async": (C.c_int, [_P]),
+    "qk_add_depth": (C.c_int, [_P, C.c_uint64, C.c_uint32]),
     "qk_counters_select": (C.c_int, [_P, C.c_uint32]),
     "qk_slot_stream": (_P, [_P, C.c_uint32]),
     "qk_counters_download": (C.c_int, [_P, C.c_uint64, _P, C.c_uint64]),
@@ -364,6 +365,10 @@ class Context:
 
     def reset(self):
         self._check(self._lib.qk_reset_counters(self._h))
+
+    def add_depth(self, key: int, n: int):
+        """n more occurrences of a canonical key (the reference's -t N batch padding: key 0, Q.c:458-466)."""
+        self._check(self._lib.qk_add_depth(self._h, key, n))
 
     def select_counters(self, which: int):
         """Use counter buffer 0 or 1 for what is issued from now on."""
@@ -624,6 +629,8 @@ def count(ref_prefix, reads_path, out_prefix, threads: int = 0, device: int = 0,
         n = ctx.load_dictionary(f"{ref_prefix}.qm")
         st = ctx.count_file(reads_path, host_framer=host_framer)
         st.update(ctx.stats())
+        if threads & 0xFF:      # the reference's batch padding with -t N (Q.c:458-466; uint8_t thread_count, Q.c:306)
+            ctx.add_depth(0, 4096 - st["total_kmers"] % 4096)
         counts = ctx.finish()
         counts.tofile(f"{out_prefix}.bin")
         qgc_path = Path(f"{ref_prefix}.qgc")

@@ -45,7 +45,7 @@ struct qk_table_view {
     uint32_t rem_bits;        // 60 - bucket_bits
     uint32_t ord_bits;
     uint32_t has_stash;       // stash_used != 0
-    const uint32_t *ext;      // dictionary-order extension array (12 bytes per 16 ordinals), NULL unless k = 30
+    const uint32_t *ext;      // dictionary-order extension array (12 bytes per 16 ordinals), NULL when has_ext == 0 (k < 3, k = 32)
     uint64_t n_kmers;
 };
 
@@ -78,7 +78,7 @@ struct qk_ctx {
 
     qk_bucket *buckets;
     qk_stash_entry *stash;
-    uint32_t *ext;            // dictionary-order extension array (k = 30), else NULL: per 16 ordinals three words --
+    uint32_t *ext;            // dictionary-order extension array (3 <= k <= 31), else NULL: per 16 ordinals three words --
                               // last base (2 bits each), first base (2 bits each), continuation bits (low 16)
     qk_table_desc desc;
 

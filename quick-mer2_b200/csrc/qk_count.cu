@@ -1156,6 +1156,36 @@ extern "C" int qk_reset_counters(qk_ctx *ctx)
     return QK_OK;
 }
 
+// n more occurrences of one canonical key, as if the reads had held them.  What the command needs it for:
+// with -t N the reference pads its last, partly filled batch of 4,096 keys with zeros and its workers
+// look those up like any key (Q.c:458-466, 284-291); Find_hash(0) "finds" the first empty slot on its
+// path (Q.c:98), so an empty slot that is ON the chain -- key 0 of an `index` list -- receives the padding.
+__global__ void qk_add_depth_kernel(const qk_table_view tv, uint32_t *counters, uint64_t key, uint32_t n)
+{
+    const qk_probe p = qk_probe_prepare(tv, key);
+    const qk_bucket bk = qk_ld_bucket(p.bp);
+    const uint32_t ord_mask = tv.ord_bits >= 32 ? 0xFFFFFFFFu : (1u << tv.ord_bits) - 1;
+    uint32_t strand;
+    const uint32_t ord1 = qk_probe_resolve(tv, p, bk, ord_mask, &strand);
+    if (ord1) atomicAdd(counters + (ord1 - 1), n);
+}
+
+extern "C" int qk_add_depth(qk_ctx *ctx, uint64_t key, uint32_t n)
+{
+    if (!ctx) return QK_ERR_ARG;
+    qk_table_view tv;
+    int rc = qk_table_view_of(ctx, &tv);
+    if (rc) return rc;
+    if (key >> QK_KEY_BITS) return QK_OK; // no read produces it: never in the table
+    rc = qk_sync(ctx);
+    if (rc) return rc;
+    QK_CUDA(ctx, cudaSetDevice(ctx->device));
+    qk_add_depth_kernel<<<1, 1, 0, ctx->slots[0].stream>>>(tv, ctx->counters, key, n);
+    QK_CUDA(ctx, cudaGetLastError());
+    QK_CUDA(ctx, cudaStreamSynchronize(ctx->slots[0].stream));
+    return QK_OK;
+}
+
 // Two counter buffers, so that the reduce / download of one job overlaps the counting of the
 // next (samples run back to back against one dictionary).  Selecting a buffer affects the
 // launches, resets and downloads issued AFTER the call; work already enqueued keeps its buffer.

@@ -143,6 +143,10 @@ int qk_count_main(int argc, char **argv)
         total += t;
         hits += h;
     }
+    /* Q.c:458-466: with -t N the reference fills up its last batch of 4,096 keys with zeros, and its workers look
+     * them up like any other key (Q.c:284-291) -- seen in the .bin iff the empty slot Find_hash(0) stops at is on the
+     * chain (a dictionary made by `index` from a list that holds the poly-A k-mer). */
+    if (!rc && threads) rc = qk_add_depth(ctx, 0, (uint32_t)(4096 - total % 4096));
     if (!rc) rc = qk_multi_reduce(m);                    /* ncclReduce of the counters into GPU 0 */
     if (rc) {
         printf("Counting failed: %s / %s\n", qk_last_error(ctx), qk_multi_last_error(m));

@@ -46,7 +46,9 @@ class Oracle:
         L.qko_count_file.argtypes = [C.POINTER(Dict), C.c_char_p, C.c_void_p, C.POINTER(Stats)]
         L.qko_chain_gather.restype = C.c_uint64
         L.qko_chain_gather.argtypes = [C.POINTER(Dict), C.c_void_p, C.c_void_p, C.c_uint64]
-        L.qko_count.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(Stats)]
+        L.qko_count_t.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint, C.POINTER(Stats)]
+        L.qko_fifo_padding.restype = C.c_uint64
+        L.qko_fifo_padding.argtypes = [C.POINTER(Dict), C.c_uint64, C.c_void_p]
         self.L = L
 
     def djb(self, key: int) -> int:
@@ -69,16 +71,17 @@ class Oracle:
         assert n != C.c_size_t(-1).value and n <= size
         return out[:n].tobytes(), st.as_dict()
 
-    def count(self, ref_prefix, reads, out_prefix) -> dict:
-        """The whole command: writes <out_prefix>.bin (and .txt when <ref_prefix>.qgc exists)."""
+    def count(self, ref_prefix, reads, out_prefix, threads: int = 0) -> dict:
+        """The whole command: writes <out_prefix>.bin (and .txt when <ref_prefix>.qgc exists).  threads = the
+        reference's -t: only whether it is 0 matters (the batch padding of Q.c:458-466)."""
         st = Stats()
-        rc = self.L.qko_count(os.fsencode(str(ref_prefix)), os.fsencode(str(reads)), os.fsencode(str(out_prefix)),
-                              C.byref(st))
+        rc = self.L.qko_count_t(os.fsencode(str(ref_prefix)), os.fsencode(str(reads)), os.fsencode(str(out_prefix)),
+                                threads, C.byref(st))
         assert rc == 0, f"oracle count failed: {rc}"
         return st.as_dict()
 
-    def count_bin(self, qm_path, reads) -> tuple[np.ndarray, dict]:
-        """Depths in chain order (= .bin contents) for a dictionary file and a reads file."""
+    def count_bin(self, qm_path, reads, threads: int = 0) -> tuple[np.ndarray, dict]:
+        """Depths in chain order (= .bin contents) for a dictionary file and a reads file (threads: see count)."""
         d = Dict()
         rc = self.L.qko_dict_load(os.fsencode(str(qm_path)), C.byref(d))
         assert rc == 0, f"oracle dict load failed: {rc}"
@@ -86,6 +89,8 @@ class Oracle:
             depth = np.zeros(d.n_slots, dtype=np.uint16)
             st = Stats()
             assert self.L.qko_count_file(C.byref(d), os.fsencode(str(reads)), depth.ctypes.data, C.byref(st)) == 0
+            if threads:
+                self.L.qko_fifo_padding(C.byref(d), st.total_kmers, depth.ctypes.data)
             n = self.L.qko_chain_length(C.byref(d))
             out = np.zeros(n, dtype=np.uint16)
             self.L.qko_chain_gather(C.byref(d), depth.ctypes.data, out.ctypes.data, n)

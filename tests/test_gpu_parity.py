@@ -403,6 +403,17 @@ def test_empty_slot_on_the_chain(mid_dict, qk, oracle, synth, gpu_ctx, tmp_path)
     order = chain_slots(nxt, first)
     assert want[order.index(found)] == 41 + 16 + 11 and want[order.index(other)] == 0
     assert st["total_kmers"] == ost["total_kmers"]
+    # -t N: the reference fills its last batch of 4,096 keys up with zeros and looks those up too (Q.c:458-466;
+    # pinned against the live reference in tests/test_oracle.py) -- the command and qk.count(threads=) do the same
+    padded, _ = oracle.count_bin(tmp_path / "a.qm", tmp_path / "r.fa", threads=3)
+    assert padded[order.index(found)] == (68 + 4096 - ost["total_kmers"] % 4096) & 0xFFFF
+    (tmp_path / "p.fa.qm").write_bytes((tmp_path / "a.qm").read_bytes())
+    qk.count(tmp_path / "p.fa", tmp_path / "r.fa", tmp_path / "lib", threads=3)
+    assert (tmp_path / "lib.bin").read_bytes() == padded.tobytes()
+    for t, expect in (("3", padded), ("0", want)):
+        res = qk.run_cli(["count", "-t", t, tmp_path / "p.fa", tmp_path / "r.fa", tmp_path / "cli"])
+        assert res.returncode == 0, res.stdout + res.stderr
+        assert (tmp_path / "cli.bin").read_bytes() == expect.tobytes(), t
 
 
 # ------------------------------------------------------------------ dictionary-order extension

@@ -191,6 +191,64 @@ def test_synthetic_dictionary_equals_search(k, oracle, ref_binary, synth, tmp_pa
     assert np.array_equal(bin_a, bin_b) and sa["hits"] == sb["hits"] > 0
 
 
+def test_chain_is_all_that_count_reads_of_a_dictionary(oracle, ref_binary, synth, tmp_path):
+    """Two dictionaries `search` never writes but `count` accepts: occupied slots that are not on the chain (what `sparse`
+    leaves when it does not resize), and empty slots ON the chain (key 0, the poly-A k-mer of an `index` list) -- Find_hash(0)
+    "finds" the first empty slot on its path (Q.c:98), so that one collects the poly-A / poly-T k-mers.  The live
+    reference and the restatement must agree on both; the CUDA path is held to the same files in
+    tests/test_gpu_parity.py::test_occupied_slots_off_the_chain / test_empty_slot_on_the_chain."""
+    if ref_binary is None:
+        pytest.skip("oracle/_ref/quicKmer2 not built here")
+    synth("ref", "--out", tmp_path / "ref.fa", "--bases", 150000, "--contigs", 2, "--seed", 21, "--segdups", 3, "--segdup-len", 2000)
+    res = subprocess.run([str(ref_binary), "search", "-k", "30", "-e", "0", "-s", "1M", "ref.fa"], cwd=tmp_path, capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    raw = (tmp_path / "ref.fa.qm").read_bytes()
+    H, first = int.from_bytes(raw[8:16], "little"), int.from_bytes(raw[16:24], "little")
+    keys = np.frombuffer(raw, dtype="<u8", count=H, offset=24).copy()
+    nxt = np.frombuffer(raw, dtype="<u4", count=H, offset=24 + 8 * H).copy()
+    slots, c = [], first
+    while True:
+        slots.append(c)
+        c = int(nxt[c])
+        if c == first:
+            break
+    keep = [s for i, s in enumerate(slots) if i % 3 != 1 or i == 0]
+    for x, y in zip(keep, keep[1:] + keep[:1]):
+        nxt[x] = y
+    c = oracle.djb(0) & (H - 1)
+    step = -1 if c & (H >> 1) else 1
+    while keys[c] != 0:
+        c += step
+    found, other = c, int(np.flatnonzero(keys == 0)[-1])
+    for e, i in ((found, 700), (other, 3)):
+        nxt[e] = nxt[keep[i]]
+        nxt[keep[i]] = e
+    synth("reads", "--ref", tmp_path / "ref.fa", "--out", tmp_path / "r.fa", "--n", 8000, "--len", 150, "--seed", 4)
+    with open(tmp_path / "r.fa", "a") as f:
+        f.write(">polyA\n" + "A" * 70 + "\n>polyT\n" + "T" * 45 + "\n")
+    (tmp_path / "ref.fa.qm").write_bytes(raw[:24] + keys.tobytes() + nxt.tobytes())
+    want, st = oracle.count_bin(tmp_path / "ref.fa.qm", tmp_path / "r.fa")
+    assert want.size == len(keep) + 2 < len(slots)
+    order, c = [], first
+    for _ in range(want.size):
+        order.append(c)
+        c = int(nxt[c])
+    assert want[order.index(found)] == 41 + 16 and want[order.index(other)] == 0 and want.sum() > 100000
+    res = subprocess.run([str(ref_binary), "count", "ref.fa", "r.fa", "live"], cwd=tmp_path, capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert (tmp_path / "live.bin").read_bytes() == want.tobytes()
+    # -t N: the last batch of 4,096 keys is filled up with zeros, and those are looked up too (Q.c:458-466)
+    padded, _ = oracle.count_bin(tmp_path / "ref.fa.qm", tmp_path / "r.fa", threads=3)
+    pad = 4096 - st["total_kmers"] % 4096
+    assert padded[order.index(found)] == 41 + 16 + pad and (padded != want).sum() == 1
+    for t in ("1", "3"):
+        res = subprocess.run([str(ref_binary), "count", "-t", t, "ref.fa", "r.fa", "live"], cwd=tmp_path, capture_output=True, text=True)
+        assert res.returncode == 0, res.stdout + res.stderr
+        assert (tmp_path / "live.bin").read_bytes() == padded.tobytes(), t
+    st2 = oracle.count(tmp_path / "ref.fa", tmp_path / "r.fa", tmp_path / "port", threads=3)
+    assert (tmp_path / "port.bin").read_bytes() == padded.tobytes() and st2["total_kmers"] == st["total_kmers"]
+
+
 SMOOTH_STUB = """#!/usr/bin/env python3
 # stand-in for the reference's smooth_GC_mrsfast.py (LOWESS; needs numpy.float and matplotlib, absent here):
 # 401 float32 on stdout, a deterministic curve with the same range the real one has (clamped to [1/3, 3])
