@@ -31,6 +31,58 @@ def same_file(a: Path, b: Path, piece=64 << 20):
                 return True
 
 
+SMOOTH_STUB = """#!/usr/bin/env python3
+# stand-in for the reference's smooth_GC_mrsfast.py (LOWESS; needs numpy.float and matplotlib, absent in this image):
+# 401 float32 on stdout, a fixed curve in the range the real one is clamped to
+import math, struct, sys
+vals = [min(3.0, max(1 / 3, 1.0 + 0.8 * math.sin(i / 37.0) + (i % 11) * 0.013)) for i in range(401)]
+sys.stdout.buffer.write(struct.pack("<401f", *vals))
+"""
+
+
+def est_leg(d: Path, ref: Path, sample: Path, out: dict, args) -> bool:
+    """`est ref sample output.bed` (Q.c:555-685) on the .bin / .txt our count just wrote: <ref>.bed with one window per
+    --est-window dictionary entries, the Python smoother replaced by a fixed curve on the PATH, our command and the
+    reference's on the same files."""
+    n = out["bin_entries"]
+    w = args.est_window
+    t0 = time.time()
+    with open(str(ref) + ".bed", "w") as f:
+        for a in range(0, n - w, w * 4096):
+            f.write("".join(f"chrS\t{x}\t{x + w}\t{x}\t{x + w}\n" for x in range(a, min(n - w, a + w * 4096), w)))
+    stub = d / f"stubbin_{os.getpid()}"
+    stub.mkdir(exist_ok=True)
+    (stub / "smooth_GC_mrsfast.py").write_text(SMOOTH_STUB)
+    (stub / "smooth_GC_mrsfast.py").chmod(0o755)
+    env = dict(os.environ, PATH=f"{stub}:{os.environ['PATH']}", QK_TIMING="1")
+    e = {"windows": (n - w + w - 1) // w, "window_kmers": w, "bed_s": time.time() - t0}
+    ok = True
+    outs = {}
+    for who, exe in (("ours", CLI), ("reference", REF)):
+        if who == "reference" and not REF.exists():
+            continue
+        bed = Path(f"{sample}.{who}.bed")
+        t0 = time.time()
+        res = subprocess.run([str(exe), "est", str(ref), str(sample), str(bed)], capture_output=True, text=True, env=env)
+        e[f"{who}_wall_s"] = time.time() - t0
+        e[f"{who}_stdout"] = res.stdout.splitlines()[-3:]
+        if res.returncode:
+            e[f"{who}_failed"] = (res.stdout + res.stderr)[-1000:]
+            ok = False
+            continue
+        e[f"{who}_lines"] = sum(1 for _ in open(bed))
+        outs[who] = bed
+    if len(outs) == 2:
+        e["bed_identical"] = same_file(outs["ours"], outs["reference"])
+        ok = ok and e["bed_identical"]
+    for p in outs.values():
+        p.unlink(missing_ok=True)
+    (stub / "smooth_GC_mrsfast.py").unlink()
+    stub.rmdir()
+    out["est"] = e
+    return ok
+
+
 def main():
     import bench
     ap = argparse.ArgumentParser()
@@ -39,6 +91,8 @@ def main():
     ap.add_argument("--ref-threads", type=int, default=15)
     ap.add_argument("--gpus", default="0", help="device list for our command (-g)")
     ap.add_argument("--skip-reference", action="store_true", help="only our command (timing); no comparison")
+    ap.add_argument("--est", action="store_true", help="then `est` on our .bin/.txt: our command against the reference's, output.bed compared")
+    ap.add_argument("--est-window", type=int, default=1000, help="k-mers per window of the generated <ref>.bed")
     args = ap.parse_args()
     cdir = bench.cache_dir(args.cache_dir)
     subprocess.run(["make", "-s", "-C", str(ROOT / "quick-mer2_b200"), "all"], check=True)
@@ -72,6 +126,8 @@ def main():
         out["stdout_lines_identical"] = [l for l in out["ours_stdout"] if "elapse" not in l] == [l for l in out["reference_stdout"] if "elapse" not in l]
         ok = out["bin_identical"] and out["txt_identical"]
     out["bin_entries"] = Path(str(ours) + ".bin").stat().st_size // 2
+    if args.est:
+        ok = est_leg(d, ref, ours, out, args) and ok
     for p in (ours, theirs):
         for ext in (".bin", ".txt"):
             Path(str(p) + ext).unlink(missing_ok=True)
