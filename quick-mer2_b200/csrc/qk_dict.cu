@@ -129,7 +129,7 @@ __device__ __forceinline__ bool qk_node_slot(uint64_t id, uint64_t n_split, uint
     return s != first;
 }
 
-__global__ void qk_walk_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ next, uint64_t n_split,
+__global__ void qk_walk_kernel(const uint32_t *__restrict__ next, uint64_t hash_size, uint64_t n_split,
                                uint32_t stride_log2, uint64_t first, uint32_t *succ, unsigned long long *dist,
                                uint32_t *seg_len, qk_build_info *info)
 {
@@ -137,7 +137,6 @@ __global__ void qk_walk_kernel(const uint64_t *__restrict__ keys, const uint32_t
     if (id > n_split + 1) return;
     const uint32_t END = (uint32_t)(n_split + 1);
     uint64_t slot;
-    (void)keys;
     if (id == n_split + 1 || !qk_node_slot(id, n_split, stride_log2, first, &slot)) {
         succ[id] = END; dist[id] = 0; seg_len[id] = 0;
         return;
@@ -148,6 +147,10 @@ __global__ void qk_walk_kernel(const uint64_t *__restrict__ keys, const uint32_t
     do {
         c = next[c];
         ++len;
+        if (c >= hash_size) {       // a pointer out of the table (off the chain next[] may hold anything): this walk never ends
+            c = 0;
+            len = QK_WALK_CAP;
+        }
     } while (c != first && (c & smask) != 0 && len < QK_WALK_CAP);
     (void)info;
     succ[id] = (c == first) ? END : (uint32_t)(c >> stride_log2);
@@ -477,7 +480,7 @@ extern "C" int qk_dict_build(qk_ctx *ctx, uint64_t *n_kmers_out)
     QK_TRY(cudaMemset(mark, 0, n_nodes));
     QK_TRY(cudaMemset(mark + n_split, 1, 1));    // the head
 
-    qk_walk_kernel<<<(unsigned)((n_nodes + 127) / 128), 128>>>(ctx->raw_keys, ctx->raw_next, n_split, stride_log2, first,
+    qk_walk_kernel<<<(unsigned)((n_nodes + 127) / 128), 128>>>(ctx->raw_next, H, n_split, stride_log2, first,
                                                                succ[0], dist[0], seg_len, info);
     QK_TRY(cudaGetLastError());
     for (uint64_t span = 1; span < n_nodes; span <<= 1) {

@@ -367,6 +367,11 @@ def test_occupied_slots_off_the_chain(mid_dict, qk, oracle, synth, gpu_ctx, tmp_
     assert keep[0] == first
     for a, b in zip(keep, keep[1:] + keep[:1]):
         nxt[a] = b
+    # ... and what next[] holds in the empty slots is nobody's business (`index` and `sparse` malloc it, Q.c:189, 1365)
+    rng = np.random.default_rng(5)
+    empty = np.flatnonzero(keys == 0)
+    nxt[empty] = rng.integers(0, 1 << 32, size=empty.size, dtype=np.uint64).astype(np.uint32)
+    nxt[empty[::7]] = empty[::7]                                              # self-loops among them
     oracle_binding.write_qm(tmp_path / "thin.qm", k, keys, nxt, first)
     synth("reads", "--ref", mid_dict / "ref.fa", "--out", tmp_path / "r.fa", "--n", 60000, "--len", 150, "--seed", 8)
     want, ost = oracle.count_bin(tmp_path / "thin.qm", tmp_path / "r.fa")
