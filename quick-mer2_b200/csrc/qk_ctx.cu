@@ -10,15 +10,24 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "qk_common.cuh"
+
+// Reader and framer threads report into the same context: the message is formatted aside and
+// copied in under a lock, so that two failures at once leave one whole message, not a blend.
+static std::mutex g_err_lock;
 
 int qk_fail(qk_ctx *ctx, int code, const char *fmt, ...)
 {
     if (ctx) {
+        char msg[sizeof ctx->err];
         va_list ap;
         va_start(ap, fmt);
-        vsnprintf(ctx->err, sizeof ctx->err, fmt, ap);
+        vsnprintf(msg, sizeof msg, fmt, ap);
         va_end(ap);
+        std::lock_guard<std::mutex> hold(g_err_lock);
+        memcpy(ctx->err, msg, sizeof msg);
     }
     return code;
 }
