@@ -794,9 +794,11 @@ def gpu_arm(args):
         ctx.reset_async()
         ctx.count_mem(data.raw_ptr, data.raw_bytes)
 
+    shipped = {"bytes": 0}                      # what the host framer handed to the GPU in its last job (text lines, or packed chunks)
+
     def job_raw_host():
         ctx.reset_async()
-        ctx.count_mem_mt(data.raw_ptr, data.raw_bytes, threads=framer_threads)
+        shipped["bytes"] = ctx.count_mem_mt(data.raw_ptr, data.raw_bytes, threads=framer_threads)["sink_bytes"]
 
     job_raw = job_raw_host if host_framing else job_raw_device
 
@@ -938,9 +940,10 @@ def gpu_arm(args):
         if rank == 0:
             log(f"{job.__name__}: per step [count ms, hand the result to the read-back ms] = "
                 + str([round(1e3 * (b - a), 1) for a, b in zip([t0] + marks[:-1], marks)]) + f"; total {1e3 * dt:.1f} ms")
-        (k,) = all_sum([ctx.stats()["total_kmers"]])
+        st = ctx.stats()
+        (k, h) = all_sum([st["total_kmers"], st["hits"]])
         ctx.select_counters(0)
-        return dt / steps, k
+        return dt / steps, (k, h)               # k-mers and dictionary hits of the last job: every leg must agree on both
 
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     h_kmers = None
@@ -949,15 +952,34 @@ def gpu_arm(args):
         h2d_ms_step = None
     else:
         h2d_before = ctx.timing()["h2d_ms"]
-        pre_s, h_kmers = timed_host(job_preframed, e2e_steps, 1)
+        pre_s, h_seen = timed_host(job_preframed, e2e_steps, 1)
+        h_kmers = h_seen[0]
         h2d_ms_step = (ctx.timing()["h2d_ms"] - h2d_before) / (e2e_steps + 1)
-        raw_s, h_kmers_raw = timed_host(job_raw, e2e_steps, 1)
-        assert h_kmers_raw == h_kmers, (h_kmers_raw, h_kmers)
+        raw_s, h_seen_raw = timed_host(job_raw, e2e_steps, 1)
+        assert h_seen_raw == h_seen, (h_seen_raw, h_seen)
         other_s = None
         if world == 1:                              # the other framing policy, for comparison
             other_s, k2 = timed_host(job_raw_device if host_framing else job_raw_host, e2e_steps, 1)
-            assert k2 == h_kmers, (k2, h_kmers)
-    (h_raw_bytes, h_framed_bytes, h_bases) = all_sum([data.raw_bytes, data.h_framed_bytes, data.h_bases])
+            assert k2 == h_seen, (k2, h_seen)
+        main_shipped = shipped["bytes"] if host_framing else 0
+        unpacked_s = None
+        if host_framing and main_shipped and main_shipped < 0.9 * data.h_framed_bytes:
+            # ... and what the same path does when the host ships the sequence lines as text (QK_PACKED=0)
+            keep = os.environ.get("QK_PACKED")
+            os.environ["QK_PACKED"] = "0"
+            try:
+                unpacked_s, k3 = timed_host(job_raw_host, e2e_steps, 1)
+            finally:
+                if keep is None:
+                    del os.environ["QK_PACKED"]
+                else:
+                    os.environ["QK_PACKED"] = keep
+            assert k3 == h_seen, (k3, h_seen)
+            shipped["bytes"] = main_shipped
+    (h_raw_bytes, h_framed_bytes, h_bases, h_shipped) = all_sum([data.raw_bytes, data.h_framed_bytes, data.h_bases, shipped["bytes"]])
+    if not h_shipped:
+        h_shipped = h_framed_bytes
+    packed = h_shipped < 0.9 * h_framed_bytes       # the host framer packs to 0.375 bytes per position when the kernel can read that
 
     # ---- e2e from a FILE (page cache): reader threads pread() into the pinned slots ---------
     file_s = None
@@ -971,7 +993,7 @@ def gpu_arm(args):
                 ctx.count_file_mt(file_reads, threads=framer_threads)
             else:
                 ctx.count_file(file_reads, threads=args.reader_threads)
-        file_s, file_kmers = timed_host(job_file, 2, 1)
+        file_s, (file_kmers, _) = timed_host(job_file, 2, 1)
         file_bytes = os.path.getsize(file_reads)
 
     framer_gbs = None
@@ -1059,18 +1081,21 @@ def gpu_arm(args):
                          if data.n_framed + int(desc.table_bytes) > (256 << 20) else "working set fits L2: HBM term does not bind",
                    "note": data.note},
         "bases_per_s": job_bases / (ms_per_step * 1e-3),
-        "e2e": {"value": hk / raw_s, "unit": "k-mers/s", "h2d_bytes_per_step": h_framed_bytes if host_framing else h_raw_bytes,
+        "e2e": {"value": hk / raw_s, "unit": "k-mers/s", "h2d_bytes_per_step": h_shipped if host_framing else h_raw_bytes,
                 "d2h_bytes_per_step": 2 * n_kmers + 64,
-                "h2d_gbs": (h_framed_bytes if host_framing else h_raw_bytes) / raw_s / 1e9,
-                "frac_of_h2d_peak": ((h_framed_bytes if host_framing else h_raw_bytes) / world / raw_s / 1e9) / h2d if h2d == h2d else None,
+                "h2d_gbs": (h_shipped if host_framing else h_raw_bytes) / raw_s / 1e9,
+                "frac_of_h2d_peak": ((h_shipped if host_framing else h_raw_bytes) / world / raw_s / 1e9) / h2d if h2d == h2d else None,
                 "bases_per_s": h_bases / raw_s,
-                "framing": f"host, {framer_threads} threads per GPU" if host_framing else "device",
+                "framing": (f"host, {framer_threads} threads per GPU" + (", packed chunks (2-bit codes + reset flags, 24 bytes per 64 positions)" if packed else "")) if host_framing else "device",
                 "host_raw_gbs": h_raw_bytes / raw_s / 1e9,
                 "host_framer_alone_gbs": None if framer_gbs is None else {"raw_in": framer_gbs[0], "framed_out": framer_gbs[1], "threads": framer_threads},
+                "text_chunks": None if args.kernel_only or unpacked_s is None else {
+                    "framing": "host, sequence lines shipped as text (QK_PACKED=0)", "value": hk / unpacked_s, "h2d_bytes_per_step": h_framed_bytes},
                 "other_framing": None if args.kernel_only or other_s is None else {
                     "framing": "device" if host_framing else f"host, {framer_threads} threads", "value": hk / other_s,
-                    "h2d_bytes_per_step": h_raw_bytes if host_framing else h_framed_bytes},
-                "path": ("raw FASTA/FASTQ bytes in host memory -> qk_count_mem_mt (host threads frame blocks in parallel, sequence lines only into the pinned slots, H2D, count kernels) -> qk_finish (uint16 depths D2H)"
+                    "h2d_bytes_per_step": h_raw_bytes if host_framing else h_shipped},
+                "path": ("raw FASTA/FASTQ bytes in host memory -> qk_count_mem_mt (host threads frame blocks in parallel, sequence lines only"
+                         + (", packed," if packed else "") + " into the pinned slots, H2D, count kernels) -> qk_finish (uint16 depths D2H)"
                          if host_framing else
                          "raw FASTA/FASTQ bytes in pinned host memory -> qk_count_raw_mem (cut at line ends, H2D, device framing, count kernels) -> qk_finish (uint16 depths D2H)"),
                 "steps": e2e_steps, "raw_bytes_per_step": h_raw_bytes, "reads_per_step": data.h_lines * world, "kmers_per_step": hk,

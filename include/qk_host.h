@@ -54,6 +54,8 @@ typedef struct qk_framer_stats {
     uint64_t long_lines;    /* > QK_MAX_LINE_BYTES (T8)          */
     uint64_t unterminated;  /* final line without '\n' (T9)      */
     int fastq;
+    uint64_t sink_bytes;    /* qk_frame_mem_mt / qk_count_{mem,file}_mt: bytes handed to the chunk consumer, i.e. shipped to
+                             * the GPUs -- the sequence lines, or 0.375 bytes per position when the chunks are packed */
 } qk_framer_stats;
 
 qk_framer *qk_framer_open(const char *path);        /* NULL if the file cannot be opened */
@@ -142,6 +144,12 @@ typedef struct qk_chunk_sink {
     int (*ready)(void *user, uint32_t c, uint32_t s);
     int (*wait)(void *user, uint32_t c, uint32_t s);
     int (*submit)(void *user, uint32_t c, uint32_t s, uint64_t seq, size_t n_bytes, uint32_t n_lines);
+    /* != 0: the consumer takes PACKED chunks -- per 64 positions of the framed stream 24 bytes: four little-endian 32-bit
+     * words of 2-bit codes ((c >> 1) & 3, Q.c:411; 16 positions per word, the first in the top pair) and 64 flags
+     * (bit p: position p is 'N' or '\n', Q.c:403-404), which is all the count kernels keep of a byte.  `cap` and
+     * submit's n_bytes then count POSITIONS (multiples of 64; a block's lines are followed by '\n' positions up to
+     * the next multiple), the buffer holds n_bytes / 64 * 24 bytes. */
+    int packed;
 } qk_chunk_sink;
 int qk_frame_mem_mt(const qk_chunk_sink *sink, const uint8_t *data, size_t n, int seekable, uint32_t threads, qk_framer_stats *st);
 /* Measurement: the framer alone over `data`, chunks discarded; GB/s of raw input consumed and of

@@ -128,6 +128,14 @@ int qk_submit(qk_ctx *ctx, uint32_t slot, const uint8_t *bytes, size_t n_bytes,
               const uint32_t *line_off, uint32_t n_lines);
 /* Same, for a chunk already resident in device memory (16-byte aligned). */
 int qk_submit_device(qk_ctx *ctx, uint32_t slot, const uint8_t *dev_bytes, size_t n_bytes);
+/* A PACKED chunk from the slot's pinned buffer (or any host memory): per 64 positions of a framed stream 24 bytes --
+ * four little-endian 32-bit words of 2-bit codes ((c >> 1) & 3, Q.c:411; 16 positions per word, the first in the
+ * top pair) and 64 reset flags (bit p: position p is 'N' or '\n', Q.c:403-404).  That is all the count kernels
+ * keep of a byte, so the result is the one qk_submit gives for the text; the link carries 0.375 bytes per position.
+ * n_positions is a multiple of 64 (fill up with '\n' positions) and at most the slot capacity.  Needs the
+ * dictionary-order kernel (table_desc.has_ext != 0, i.e. 3 <= k <= 31), QK_ERR_STATE otherwise.  The host framer
+ * makes such chunks (host/qk_framer_mt.c). */
+int qk_submit_packed(qk_ctx *ctx, uint32_t slot, const uint8_t *packed, size_t n_positions, uint32_t n_lines);
 /* Raw streams: the record framing of Q.c:393-398,451-455 done ON THE DEVICE.  qk_raw_begin
  * starts a stream: `fastq` = its first byte is '@' (Q.c:395); `skip_first_line` = the first line
  * is consumed without being examined (always for FASTQ, and for FASTA on a pipe where the

@@ -78,6 +78,7 @@ class FramerStats(C.Structure):
         ("long_lines", C.c_uint64),
         ("unterminated", C.c_uint64),
         ("fastq", C.c_int),
+        ("sink_bytes", C.c_uint64),
     ]
 
     def as_dict(self):
@@ -124,6 +125,7 @@ SIGNATURES = {
     "qk_reset_counters": (C.c_int, [_P]),
     "qk_reset_counters_async": (C.c_int, [_P]),
     "qk_add_depth": (C.c_int, [_P, C.c_uint64, C.c_uint32]),
+    "qk_submit_packed": (C.c_int, [_P, C.c_uint32, C.c_void_p, C.c_size_t, C.c_uint32]),
     "qk_counters_select": (C.c_int, [_P, C.c_uint32]),
     "qk_slot_stream": (_P, [_P, C.c_uint32]),
     "qk_counters_download": (C.c_int, [_P, C.c_uint64, _P, C.c_uint64]),
@@ -443,6 +445,14 @@ class Context:
         """Count a framed chunk straight from (ideally pinned) host memory: async H2D + kernel."""
         self._check(self._lib.qk_submit(self._h, slot, host_ptr, n_bytes, None, n_lines))
 
+    def submit_packed(self, packed: np.ndarray, n_positions: int, slot: int = 0, n_lines: int = 0):
+        """Count a packed chunk (24 bytes per 64 positions: qk_submit_packed) held in a uint8 array; waits for the copy."""
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        if packed.size < n_positions // 64 * 24:
+            raise ValueError("packed chunk shorter than n_positions / 64 * 24 bytes")
+        self._check(self._lib.qk_submit_packed(self._h, slot, _np_ptr(packed), n_positions, n_lines))
+        self._check(self._lib.qk_wait_slot(self._h, slot))
+
     def count_mem(self, host_ptr: int, n_bytes: int, seekable: bool = True, host_framer: bool = False) -> dict:
         """Count raw FASTA/FASTQ bytes at a host address (the whole reads stream).  Pinned
         memory is DMA'd from directly; the device does the record framing unless host_framer."""
@@ -566,14 +576,25 @@ class ChunkSink(C.Structure):
     READY = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_uint32)
     SUBMIT = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_size_t, C.c_uint32)
     _fields_ = [("user", C.c_void_p), ("n_ctx", C.c_uint32), ("n_slots", C.c_uint32), ("cap", C.c_size_t),
-                ("buffer", BUFFER), ("ready", READY), ("wait", READY), ("submit", SUBMIT)]
+                ("buffer", BUFFER), ("ready", READY), ("wait", READY), ("submit", SUBMIT), ("packed", C.c_int)]
+
+
+def unpack_chunk(packed: bytes) -> tuple[np.ndarray, np.ndarray]:
+    """A packed chunk (struct qk_chunk_sink: 24 bytes per 64 positions) -> (2-bit code, reset flag) per position."""
+    g = np.frombuffer(packed, dtype=np.uint8).reshape(-1, 24)
+    words = g[:, :16].copy().view("<u4")                                    # (groups, 4): 16 positions each, the first in the top pair
+    shifts = (2 * (15 - np.arange(16))).astype(np.uint32)
+    codes = ((words[:, :, None] >> shifts[None, None, :]) & 3).astype(np.uint8).reshape(-1)
+    flags = np.unpackbits(g[:, 16:24].copy(), axis=1, bitorder="little").reshape(-1)
+    return codes, flags
 
 
 def frame_mt(data: bytes, seekable: bool = True, threads: int = 4, n_ctx: int = 1, n_slots: int = 3, cap: int = 1 << 20,
-             busy_every: int = 0):
+             busy_every: int = 0, packed: bool = False):
     """Host-only: the multi-threaded framer (qk_frame_mem_mt) into Python-owned buffers.  Returns
     (chunks in stream order, per-chunk (consumer, lines), stats).  busy_every > 0 makes ready()
-    answer "busy" now and then, as a GPU whose copy is still in flight would."""
+    answer "busy" now and then, as a GPU whose copy is still in flight would.  packed: the chunks are
+    packed ones (cap and their sizes in positions; see unpack_chunk)."""
     import threading
     L = lib()
     buf = np.frombuffer(data, dtype=np.uint8) if len(data) else np.zeros(0, dtype=np.uint8)
@@ -587,11 +608,11 @@ def frame_mt(data: bytes, seekable: bool = True, threads: int = 4, n_ctx: int = 
 
     def submit(_u, c, s, seq, n_bytes, n_lines):
         with lock:
-            got[seq] = (bufs[c][s][:n_bytes].tobytes(), c, n_lines)
+            got[seq] = (bufs[c][s][:n_bytes // 64 * 24 if packed else n_bytes].tobytes(), c, n_lines)
         return 0
 
     sink = ChunkSink(None, n_ctx, n_slots, cap, ChunkSink.BUFFER(lambda _u, c, s: bufs[c][s].ctypes.data), ChunkSink.READY(ready),
-                     ChunkSink.READY(lambda _u, c, s: 0), ChunkSink.SUBMIT(submit))
+                     ChunkSink.READY(lambda _u, c, s: 0), ChunkSink.SUBMIT(submit), int(packed))
     st = FramerStats()
     rc = L.qk_frame_mem_mt(C.byref(sink), _np_ptr(buf), buf.size, int(seekable), threads, C.byref(st))
     if rc:

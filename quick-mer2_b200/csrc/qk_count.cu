@@ -94,6 +94,44 @@ __device__ __forceinline__ uint4 qk_load16(const uint8_t *__restrict__ bytes, ui
     return v;
 }
 
+// What a lane holds of 16 positions between its load and its use.  ASCII chunks: the 16 bytes, turned into codes and
+// reset flags when they are needed (the conversion then overlaps the next load).  PACKED chunks (host/qk_framer_mt.c:
+// per 64 positions four 32-bit code words and 64 flags, 24 bytes) hold the two already.
+template <bool PACKED> struct qk_in16;
+template <> struct qk_in16<false> {
+    uint4 v;
+    __device__ __forceinline__ uint32_t codes() const { return qk_codes16(v); }
+    __device__ __forceinline__ uint32_t resets() const { return qk_resets16(v); }
+};
+template <> struct qk_in16<true> {
+    uint32_t c, r;
+    __device__ __forceinline__ uint32_t codes() const { return c; }
+    __device__ __forceinline__ uint32_t resets() const { return r; }
+};
+// the 16 positions at chunk position pos (a multiple of 16); positions at or beyond n read as '\n'
+template <bool PACKED> __device__ __forceinline__ qk_in16<PACKED> qk_fetch16(const uint8_t *__restrict__ bytes, uint32_t pos, uint32_t n);
+template <> __device__ __forceinline__ qk_in16<false> qk_fetch16<false>(const uint8_t *__restrict__ bytes, uint32_t pos, uint32_t n)
+{
+    qk_in16<false> x;
+    x.v = qk_load16(bytes, pos, n);
+    return x;
+}
+template <> __device__ __forceinline__ qk_in16<true> qk_fetch16<true>(const uint8_t *__restrict__ bytes, uint32_t pos, uint32_t n)
+{
+    qk_in16<true> x;
+    x.c = 0;
+    x.r = 0xFFFFu;
+    if (pos < n) {   // (n is a multiple of 64: a group is there whole or not at all)
+        const uint8_t *g = bytes + (size_t)(pos >> 6) * 24;
+        const uint32_t w = (pos >> 4) & 3u;
+        unsigned short r16;
+        asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(x.c) : "l"(g + 4 * w));
+        asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(r16) : "l"(g + 16 + 2 * w));
+        x.r = r16;
+    }
+    return x;
+}
+
 // the same load with an L2 fetch-size hint of 64 B: a missing sector then costs 64 B of DRAM
 // traffic instead of the default 128 B (measured, profiles/r1_gather_probe_ncu.txt)
 __device__ __forceinline__ qk_bucket qk_ld_bucket64(const qk_bucket *p)
@@ -739,7 +777,7 @@ __device__ __forceinline__ uint32_t qk_walk16(const qk_table_view &tv, uint64_t 
     return ((1u << len) - 1) << sh;
 }
 
-template <int MINB, bool L64, int MODE>
+template <int MINB, bool L64, int MODE, bool PACKED>
 __global__ void __launch_bounds__(QK_THREADS, MINB) qk_count_ext32_kernel(const qk_count_args a)
 {
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -766,15 +804,15 @@ __global__ void __launch_bounds__(QK_THREADS, MINB) qk_count_ext32_kernel(const 
         while (pos > 0 && found == QK_NONE) {
             pos -= 512;
             const uint32_t at = pos + lane * 16;
-            const uint32_t m = qk_resets16(qk_load16(bytes, at, n));
+            const uint32_t m = qk_fetch16<PACKED>(bytes, at, n).resets();
             found = __reduce_max_sync(FULL, m ? (int)(at + 31 - __clz(m)) : QK_NONE);
         }
         carry_last = (found == QK_NONE) ? -1 : found;
         const uint32_t base = sub0 * QK_SUB2;
         if (base >= 32) {
-            const uint4 h0 = qk_load16(bytes, base - 32, n), h1 = qk_load16(bytes, base - 16, n);
-            halo_c = ((uint64_t)qk_codes16(h0) << 32) | qk_codes16(h1);
-            halo_m = qk_resets16(h0) | (qk_resets16(h1) << 16);
+            const qk_in16<PACKED> h0 = qk_fetch16<PACKED>(bytes, base - 32, n), h1 = qk_fetch16<PACKED>(bytes, base - 16, n);
+            halo_c = ((uint64_t)h0.codes() << 32) | h1.codes();
+            halo_m = h0.resets() | (h1.resets() << 16);
         }
     }
 
@@ -806,16 +844,16 @@ __global__ void __launch_bounds__(QK_THREADS, MINB) qk_count_ext32_kernel(const 
 
     // the warp loads 1 KiB as two fully coalesced 512-byte rows; ownership (32 contiguous positions per lane)
     // is taken from shared memory afterwards
-    uint4 cur0 = qk_load16(bytes, sub0 * QK_SUB2 + lane * 16, n), cur1 = qk_load16(bytes, sub0 * QK_SUB2 + 512 + lane * 16, n);
+    qk_in16<PACKED> cur0 = qk_fetch16<PACKED>(bytes, sub0 * QK_SUB2 + lane * 16, n), cur1 = qk_fetch16<PACKED>(bytes, sub0 * QK_SUB2 + 512 + lane * 16, n);
     for (uint32_t sub = sub0; sub < sub_end; ++sub) {
         const uint32_t base = sub * QK_SUB2;
         __syncwarp(); // everybody is done reading the previous sub-tile
         {
             uint32_t *c32 = reinterpret_cast<uint32_t *>(sm.codes);
             uint16_t *m16 = reinterpret_cast<uint16_t *>(sm.mask);
-            const uint32_t r0 = qk_resets16(cur0), r1 = qk_resets16(cur1);
-            c32[2 + (lane ^ 1)] = qk_codes16(cur0);            // first base of a 32-base word in its top pair
-            c32[2 + 32 + (lane ^ 1)] = qk_codes16(cur1);
+            const uint32_t r0 = cur0.resets(), r1 = cur1.resets();
+            c32[2 + (lane ^ 1)] = cur0.codes();                // first base of a 32-base word in its top pair
+            c32[2 + 32 + (lane ^ 1)] = cur1.codes();
             m16[2 + lane] = (uint16_t)r0;
             m16[2 + 32 + lane] = (uint16_t)r1;
             if (lane == 0) {
@@ -827,8 +865,8 @@ __global__ void __launch_bounds__(QK_THREADS, MINB) qk_count_ext32_kernel(const 
             const int own1 = r1 ? (int)(base + 512 + 16 * lane + 31 - __clz(r1)) : QK_NONE;
             const int seen = __reduce_max_sync(FULL, max(own0, own1));
             if (sub + 1 < sub_end) {
-                cur0 = qk_load16(bytes, base + QK_SUB2 + lane * 16, n); // prefetch
-                cur1 = qk_load16(bytes, base + QK_SUB2 + 512 + lane * 16, n);
+                cur0 = qk_fetch16<PACKED>(bytes, base + QK_SUB2 + lane * 16, n); // prefetch
+                cur1 = qk_fetch16<PACKED>(bytes, base + QK_SUB2 + 512 + lane * 16, n);
             }
             __syncwarp();
             // ---- which of my 32 positions end a 30-mer: no reset among the 30 bytes ending there ----
@@ -1041,7 +1079,14 @@ static int qk_table_view_of(qk_ctx *ctx, qk_table_view *tv)
     return QK_OK;
 }
 
+static int qk_launch_count_as(qk_ctx *ctx, qk_slot *sl, const uint8_t *dev_bytes, size_t n_bytes, bool packed);
 int qk_launch_count(qk_ctx *ctx, qk_slot *sl, const uint8_t *dev_bytes, size_t n_bytes)
+{
+    return qk_launch_count_as(ctx, sl, dev_bytes, n_bytes, false);
+}
+
+// n_bytes = positions of the chunk; packed: dev_bytes holds them as 24 bytes per 64 (qk_fetch16<true>)
+static int qk_launch_count_as(qk_ctx *ctx, qk_slot *sl, const uint8_t *dev_bytes, size_t n_bytes, bool packed)
 {
     qk_count_args a;
     int rc = qk_table_view_of(ctx, &a.tv);
@@ -1075,20 +1120,29 @@ int qk_launch_count(qk_ctx *ctx, qk_slot *sl, const uint8_t *dev_bytes, size_t n
     if (plain_loads < 0) plain_loads = getenv("QK_EXT_PLAIN_LOADS") != NULL;
     static int run16 = -1;       // QK_EXT_RUN16=1: the 16-positions-per-lane walk (A/B knob)
     if (run16 < 0) run16 = getenv("QK_EXT_RUN16") != NULL;
-    if (a.tv.ext && !classic && (!run16 || ctx->desc.has_ext != 1)) {
+    if (packed && !(a.tv.ext && ctx->desc.has_ext))
+        return qk_fail(ctx, QK_ERR_STATE, "packed chunks are read by the dictionary-order kernel only (3 <= k <= 31)");
+    if (packed || (a.tv.ext && !classic && (!run16 || ctx->desc.has_ext != 1))) {
         const size_t smem = QK_WARPS * sizeof(qk_warp_smem2);
         static int attr_set[64];
         if (ctx->device < 64 && !attr_set[ctx->device]) {
-            QK_CUDA(ctx, cudaFuncSetAttribute(qk_count_ext32_kernel<4, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            QK_CUDA(ctx, cudaFuncSetAttribute(qk_count_ext32_kernel<4, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            QK_CUDA(ctx, cudaFuncSetAttribute(qk_count_ext32_kernel<4, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            QK_CUDA(ctx, cudaFuncSetAttribute(qk_count_ext32_kernel<4, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            QK_CUDA(ctx, cudaFuncSetAttribute(qk_count_ext32_kernel<4, true, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            QK_CUDA(ctx, cudaFuncSetAttribute(qk_count_ext32_kernel<4, false, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            QK_CUDA(ctx, cudaFuncSetAttribute(qk_count_ext32_kernel<4, true, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            QK_CUDA(ctx, cudaFuncSetAttribute(qk_count_ext32_kernel<4, true, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            QK_CUDA(ctx, cudaFuncSetAttribute(qk_count_ext32_kernel<4, true, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            QK_CUDA(ctx, cudaFuncSetAttribute(qk_count_ext32_kernel<4, true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            QK_CUDA(ctx, cudaFuncSetAttribute(qk_count_ext32_kernel<4, true, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_set[ctx->device] = 1;
         }
-        if (ctx->desc.has_ext == 2) qk_count_ext32_kernel<4, true, 1><<<grid, QK_THREADS, smem, sl->stream>>>(a);
-        else if (ctx->desc.has_ext == 3) qk_count_ext32_kernel<4, true, 2><<<grid, QK_THREADS, smem, sl->stream>>>(a);
-        else if (plain_loads) qk_count_ext32_kernel<4, false, 0><<<grid, QK_THREADS, smem, sl->stream>>>(a);
-        else qk_count_ext32_kernel<4, true, 0><<<grid, QK_THREADS, smem, sl->stream>>>(a);
+        if (packed) {
+            if (ctx->desc.has_ext == 2) qk_count_ext32_kernel<4, true, 1, true><<<grid, QK_THREADS, smem, sl->stream>>>(a);
+            else if (ctx->desc.has_ext == 3) qk_count_ext32_kernel<4, true, 2, true><<<grid, QK_THREADS, smem, sl->stream>>>(a);
+            else qk_count_ext32_kernel<4, true, 0, true><<<grid, QK_THREADS, smem, sl->stream>>>(a);
+        } else if (ctx->desc.has_ext == 2) qk_count_ext32_kernel<4, true, 1, false><<<grid, QK_THREADS, smem, sl->stream>>>(a);
+        else if (ctx->desc.has_ext == 3) qk_count_ext32_kernel<4, true, 2, false><<<grid, QK_THREADS, smem, sl->stream>>>(a);
+        else if (plain_loads) qk_count_ext32_kernel<4, false, 0, false><<<grid, QK_THREADS, smem, sl->stream>>>(a);
+        else qk_count_ext32_kernel<4, true, 0, false><<<grid, QK_THREADS, smem, sl->stream>>>(a);
     } else if (a.tv.ext && ctx->desc.has_ext == 1 && !classic) {
         // 4 CTAs/SM at 64 registers: 5 and 6 CTAs/SM spill and measured 2-5 % slower (profiles/README.md)
         if (plain_loads) qk_count_ext_kernel<4, false><<<grid, QK_THREADS, 0, sl->stream>>>(a);
@@ -1129,6 +1183,28 @@ extern "C" int qk_submit_device(qk_ctx *ctx, uint32_t slot, const uint8_t *dev_b
     if (n_bytes == 0) return QK_OK;
     QK_CUDA(ctx, cudaSetDevice(ctx->device));
     return qk_launch_count(ctx, &ctx->slots[slot], dev_bytes, n_bytes);
+}
+
+// A packed chunk (host/qk_framer_mt.c: per 64 positions of the framed stream four 32-bit words of 2-bit codes and 64
+// reset flags, 24 bytes): 0.375 bytes per position over the link instead of 1, and nothing for the kernel to convert.
+extern "C" int qk_submit_packed(qk_ctx *ctx, uint32_t slot, const uint8_t *packed, size_t n_positions, uint32_t n_lines)
+{
+    if (!ctx || slot >= ctx->n_slots || (!packed && n_positions) || (n_positions & 63)) return QK_ERR_ARG;
+    if (n_positions > ctx->chunk_capacity) return qk_fail(ctx, QK_ERR_ARG, "chunk of %zu positions exceeds the slot capacity", n_positions);
+    if (ctx->dict_state != 2) return qk_fail(ctx, QK_ERR_STATE, "no dictionary built on this context");
+    if (!ctx->desc.has_ext) return qk_fail(ctx, QK_ERR_STATE, "packed chunks are read by the dictionary-order kernel only (3 <= k <= 31)");
+    ctx->lines += n_lines;
+    if (n_positions == 0) return QK_OK;
+    QK_CUDA(ctx, cudaSetDevice(ctx->device));
+    qk_slot *sl = &ctx->slots[slot];
+    qk_timing_pair *tp;
+    int rc = qk_ring_push(ctx, sl, 0, &tp);
+    if (rc) return rc;
+    QK_CUDA(ctx, cudaEventRecord(tp->a, sl->stream));
+    QK_CUDA(ctx, cudaMemcpyAsync(sl->dev, packed, n_positions / 64 * 24, cudaMemcpyHostToDevice, sl->stream));
+    QK_CUDA(ctx, cudaEventRecord(tp->b, sl->stream));
+    QK_CUDA(ctx, cudaEventRecord(sl->h2d_done, sl->stream));
+    return qk_launch_count_as(ctx, sl, sl->dev, n_positions, true);
 }
 
 extern "C" int qk_counters_device_ptr(const qk_ctx *ctx, uint32_t **counters, uint64_t *n_kmers)

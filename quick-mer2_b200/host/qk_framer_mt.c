@@ -40,6 +40,7 @@
 
 #define QK_MT_MAX_CTX 16
 #define QK_MT_MAX_THREADS 128
+#define QK_PACKED_DEFAULT 0          /* qk_count_mem_mt / qk_count_file_mt ship packed chunks unless QK_PACKED=0 */
 
 enum { SLOT_FREE = 0, SLOT_FILLING = 1, SLOT_SUBMITTING = 2, SLOT_SUBMITTED = 3 };
 
@@ -71,12 +72,14 @@ typedef struct {
     uint32_t state;
     int cur_ctx, cur_slot, rr;           /* open chunk (-1 = none), round-robin start */
     uint64_t lines, bases, long_lines, unterminated;
+    uint64_t sink_bytes;                 /* bytes assigned to chunks so far (resolver only) */
     _Atomic int err;
     int avx512;
     uint16_t tab[2][256];                /* the line state machine from all four entry states at once */
     size_t stage_cap;                    /* bytes of a worker's staging buffer */
     int nt;                              /* staged non-temporal stores (QK_FRAMER_NT=0 turns them off) */
     int populate;                        /* the input is a file mapping: populate each block's pages in one call */
+    int packed;                          /* the sink takes packed chunks: 24 bytes per 64 positions (see qk_pack_positions) */
 } mt_job;
 
 /* ---- line scan + state machine ------------------------------------------------------------ */
@@ -228,11 +231,10 @@ static int scan_plain(const uint8_t *d, size_t from, size_t n, size_t stop_at, m
  * The lines are gathered in `stage` (thread-local, cache-resident, co-aligned with o modulo 64) and go to the pinned
  * chunk buffer with non-temporal 64-byte stores: the destination is written once and read by the DMA engine only, so
  * the read-for-ownership a normal store costs (as much DRAM traffic again as the write itself) is saved. */
-__attribute__((target("avx512f,avx512bw"))) static uint64_t copy_avx512(uint8_t *o, const uint8_t *d, size_t n, const mt_sim *S, uint32_t s_in,
-                                                                        uint8_t *stage)
+__attribute__((target("avx512f,avx512bw"))) static inline size_t gather_avx512(uint8_t *w, const uint8_t *d, size_t n, const mt_sim *S,
+                                                                                 uint32_t s_in, uint64_t *long_lines)
 {
     uint64_t longl = 0;
-    uint8_t *w = stage + ((uintptr_t)o & 63);
     uint8_t *const w0 = w;
     for (size_t k = 0; k < S->n_lines; ++k) {
         if (!((S->keep[k] >> s_in) & 1u)) continue;
@@ -252,14 +254,28 @@ __attribute__((target("avx512f,avx512bw"))) static uint64_t copy_avx512(uint8_t 
         w += len;
         longl += len > QK_MAX_LINE_BYTES;
     }
-    /* stage -> destination */
-    size_t total = (size_t)(w - w0), at = 0;
-    const uint8_t *r = w0;
+    *long_lines = longl;
+    return (size_t)(w - w0);
+}
+
+/* `total` staged bytes at r (co-aligned with o modulo 64) -> destination */
+__attribute__((target("avx512f,avx512bw"))) static inline void stream_out(uint8_t *o, const uint8_t *r, size_t total)
+{
+    size_t at = 0;
     const size_t head = (64 - ((uintptr_t)o & 63)) & 63;
     if (head && total >= head) { memcpy(o, r, head); at = head; }
     for (; at + 64 <= total; at += 64) _mm512_stream_si512((void *)(o + at), _mm512_load_si512((const void *)(r + at)));
     if (at < total) memcpy(o + at, r + at, total - at);
     _mm_sfence();                                                /* before the chunk is handed to the copy engine */
+}
+
+__attribute__((target("avx512f,avx512bw"))) static uint64_t copy_avx512(uint8_t *o, const uint8_t *d, size_t n, const mt_sim *S, uint32_t s_in,
+                                                                        uint8_t *stage)
+{
+    uint64_t longl = 0;
+    uint8_t *w = stage + ((uintptr_t)o & 63);
+    const size_t total = gather_avx512(w, d, n, S, s_in, &longl);
+    stream_out(o, w, total);
     return longl;
 }
 
@@ -276,6 +292,64 @@ static uint64_t copy_plain(uint8_t *o, const uint8_t *d, size_t n, const mt_sim 
         o += len;
         longl += len > QK_MAX_LINE_BYTES;
     }
+    return longl;
+}
+
+/* ---- packed chunks ----------------------------------------------------------------------------
+ * What the count kernels make of a framed chunk first is 2 bits per position ((c >> 1) & 3, Q.c:411) and a flag
+ * per position (c is 'N' or '\n': the k-mer register starts over, Q.c:403-404).  A PACKED chunk is exactly that,
+ * made here: per 64 positions, four little-endian 32-bit code words (16 positions each, the first in the top
+ * pair -- qk_codes16 in csrc/qk_count.cu) and the 64 flags (bit p = position p), 24 bytes for 64 -- 0.375 bytes
+ * per position over PCIe and out of the host's DRAM twice (written here, read by the copy engine) instead of 1.
+ * Every block's output starts on a multiple of 64 positions and is filled up with '\n' positions (empty lines:
+ * no k-mers), so that blocks pack independently. */
+static void pack_plain(uint8_t *o, const uint8_t *ascii, size_t n_pos)     /* n_pos % 64 == 0 */
+{
+    for (size_t g = 0; g < n_pos / 64; ++g, o += 24, ascii += 64) {
+        uint64_t flags = 0;
+        for (int w = 0; w < 4; ++w) {
+            uint32_t codes = 0;
+            for (int i = 0; i < 16; ++i) {
+                const uint8_t c = ascii[16 * w + i];
+                codes |= (uint32_t)((c >> 1) & 3u) << (2 * (15 - i));
+                flags |= (uint64_t)(c == 'N' || c == '\n') << (16 * w + i);
+            }
+            memcpy(o + 4 * w, &codes, 4);
+        }
+        memcpy(o + 16, &flags, 8);
+    }
+}
+
+__attribute__((target("avx512f,avx512bw,avx512vl"))) static void pack_avx512(uint8_t *o, const uint8_t *ascii, size_t n_pos)
+{
+    const __m512i three = _mm512_set1_epi8(3), weights = _mm512_set1_epi32(0x01041040), ones = _mm512_set1_epi16(1);
+    const __m512i nl = _mm512_set1_epi8('\n'), en = _mm512_set1_epi8('N');
+    const __m128i flip = _mm_set_epi8(12, 13, 14, 15, 8, 9, 10, 11, 4, 5, 6, 7, 0, 1, 2, 3);
+    for (size_t g = 0; g < n_pos / 64; ++g, o += 24, ascii += 64) {
+        const __m512i v = _mm512_loadu_si512((const void *)ascii);
+        const __m512i c = _mm512_and_si512(_mm512_srli_epi16(v, 1), three);
+        /* four codes -> one byte, the first in the top pair: bytes (c0, c1, c2, c3) . (64, 16, 4, 1) */
+        const __m512i quads = _mm512_madd_epi16(_mm512_maddubs_epi16(c, weights), ones);
+        const __m128i bytes = _mm_shuffle_epi8(_mm512_cvtepi32_epi8(quads), flip);   /* a code word is little-endian: its first quad last */
+        const uint64_t flags = _mm512_cmpeq_epi8_mask(v, nl) | _mm512_cmpeq_epi8_mask(v, en);
+        _mm_storeu_si128((__m128i *)o, bytes);
+        memcpy(o + 16, &flags, 8);
+    }
+}
+
+/* the kept lines of trajectory s_in as a piece of a packed chunk at o (pad_pos positions, a multiple of 64): gathered
+ * in `stage` as copy_avx512 does, filled up with '\n', packed into `pstage` (co-aligned with o modulo 64), streamed out */
+__attribute__((target("avx512f,avx512bw,avx512vl"))) static uint64_t copy_packed_avx512(uint8_t *o, const uint8_t *d, size_t n, const mt_sim *S,
+                                                                                       uint32_t s_in, size_t pad_pos, uint8_t *stage,
+                                                                                       uint8_t *pstage, int nt)
+{
+    uint64_t longl = 0;
+    const size_t out = gather_avx512(stage, d, n, S, s_in, &longl);
+    memset(stage + out, '\n', pad_pos - out);
+    uint8_t *r = pstage + ((uintptr_t)o & 63);
+    pack_avx512(r, stage, pad_pos);
+    if (nt) stream_out(o, r, pad_pos / 64 * 24);
+    else memcpy(o, r, pad_pos / 64 * 24);
     return longl;
 }
 
@@ -350,7 +424,7 @@ static int open_chunk(mt_job *j)
 }
 
 /* ---- worker ----------------------------------------------------------------------------------- */
-typedef struct { mt_job *j; uint64_t *starts; uint8_t *keep, *stage; size_t starts_cap; } mt_worker;
+typedef struct { mt_job *j; uint64_t *starts; uint8_t *keep, *stage, *pstage; size_t starts_cap; } mt_worker;
 
 static void *worker(void *arg)
 {
@@ -406,18 +480,20 @@ static void *worker(void *arg)
         int rc = atomic_load(&j->err);
         const uint32_t s_in = j->state;
         const size_t out = out_bytes[s_in];
+        /* what the block takes of its chunk: its bytes, or -- packed -- whole groups of 64 positions */
+        const size_t take = j->packed ? (out + 63) & ~(size_t)63 : out;
         uint8_t *dst = NULL;
         int c = -1, s = -1;
         if (!rc && out) {
-            if (out > j->cap) rc = QK_ERR_ARG;                      /* a line longer than a chunk */
-            if (!rc && j->cur_ctx >= 0 && j->chunk[j->cur_ctx][j->cur_slot].fill + out > j->cap) close_chunk(j);
+            if (take > j->cap) rc = QK_ERR_ARG;                     /* a line longer than a chunk */
+            if (!rc && j->cur_ctx >= 0 && j->chunk[j->cur_ctx][j->cur_slot].fill + take > j->cap) close_chunk(j);
             if (!rc && j->cur_ctx < 0) rc = open_chunk(j);
             if (!rc) {
                 c = j->cur_ctx;
                 s = j->cur_slot;
                 mt_chunk *ch = &j->chunk[c][s];
-                dst = j->sink->buffer(j->sink->user, (uint32_t)c, (uint32_t)s) + ch->fill;
-                ch->fill += out;
+                dst = j->sink->buffer(j->sink->user, (uint32_t)c, (uint32_t)s) + (j->packed ? ch->fill / 64 * 24 : ch->fill);
+                ch->fill += take;
                 ch->lines += out_lines[s_in];
                 atomic_fetch_add(&ch->pending, 1);
             }
@@ -427,13 +503,25 @@ static void *worker(void *arg)
             j->state = exit_state[s_in];
             j->lines += out_lines[s_in];
             j->bases += out - out_lines[s_in];
+            j->sink_bytes += j->packed ? take / 64 * 24 : take;
             j->unterminated += (uint64_t)(unterminated && last_kept[s_in]); /* counted when it is a read, as qk_framer_next does */
         }
         if (i + 1 == j->n_blocks) close_chunk(j);                   /* (its own copy below still holds it open through `pending`) */
         atomic_store_explicit(&j->resolved, i + 1, memory_order_release);
         /* 4. copy the sequence lines */
         if (dst) {
-            const uint64_t longl = j->avx512 && j->nt && out <= j->stage_cap ? copy_avx512(dst, d, n, &S, s_in, w->stage) : copy_plain(dst, d, n, &S, s_in);
+            uint64_t longl;
+            if (!j->packed) longl = j->avx512 && j->nt && out <= j->stage_cap ? copy_avx512(dst, d, n, &S, s_in, w->stage) : copy_plain(dst, d, n, &S, s_in);
+            else if (j->avx512 && take <= j->stage_cap) longl = copy_packed_avx512(dst, d, n, &S, s_in, take, w->stage, w->pstage, j->nt);
+            else {                                                  /* no AVX-512, or a block with a line of megabytes */
+                uint8_t *tmp = malloc(take);
+                if (tmp) {
+                    longl = copy_plain(tmp, d, n, &S, s_in);
+                    memset(tmp + out, '\n', take - out);
+                    pack_plain(dst, tmp, take);
+                    free(tmp);
+                } else { int z = 0; longl = 0; atomic_compare_exchange_strong(&j->err, &z, QK_ERR_NOMEM); }
+            }
             if (longl) { pthread_mutex_lock(&j->submit_mu[0]); j->long_lines += longl; pthread_mutex_unlock(&j->submit_mu[0]); }
             atomic_fetch_sub(&j->chunk[c][s].pending, 1);
             try_submit(j, c, s);
@@ -464,7 +552,8 @@ int qk_frame_mem_mt(const qk_chunk_sink *sink, const uint8_t *data, size_t n, in
     j->sink = sink;
     j->n_ctx = sink->n_ctx;
     j->n_slots = sink->n_slots;
-    j->cap = sink->cap;
+    j->packed = sink->packed != 0;
+    j->cap = j->packed ? sink->cap & ~(size_t)63 : sink->cap;        /* packed: positions, in whole groups of 64 */
     for (uint32_t c = 0; c < j->n_ctx; ++c) pthread_mutex_init(&j->submit_mu[c], NULL);
     j->data = data;
     j->n = n;
@@ -495,7 +584,12 @@ int qk_frame_mem_mt(const qk_chunk_sink *sink, const uint8_t *data, size_t n, in
         wk[t].starts = malloc(starts_cap * sizeof(uint64_t));
         wk[t].keep = malloc(starts_cap);
         wk[t].stage = j->avx512 ? aligned_alloc(64, (j->stage_cap + 128 + 63) / 64 * 64) : NULL;
-        if (!wk[t].starts || !wk[t].keep || (j->avx512 && !wk[t].stage)) { free(wk[t].starts); free(wk[t].keep); free(wk[t].stage); rc = QK_ERR_NOMEM; break; }
+        wk[t].pstage = j->avx512 && j->packed ? aligned_alloc(64, (j->stage_cap / 64 * 24 + 128 + 63) / 64 * 64) : NULL;
+        if (!wk[t].starts || !wk[t].keep || (j->avx512 && !wk[t].stage) || (j->avx512 && j->packed && !wk[t].pstage)) {
+            free(wk[t].starts); free(wk[t].keep); free(wk[t].stage); free(wk[t].pstage);
+            rc = QK_ERR_NOMEM;
+            break;
+        }
         ++allocated;
     }
     if (rc) { int z = 0; atomic_compare_exchange_strong(&j->err, &z, rc); }
@@ -505,7 +599,7 @@ int qk_frame_mem_mt(const qk_chunk_sink *sink, const uint8_t *data, size_t n, in
     }
     if (!rc && j->n_blocks) worker(&wk[threads - 1]);
     for (uint32_t t = 0; t < started; ++t) pthread_join(th[t], NULL);
-    for (uint32_t t = 0; t < allocated; ++t) { free(wk[t].starts); free(wk[t].keep); free(wk[t].stage); }
+    for (uint32_t t = 0; t < allocated; ++t) { free(wk[t].starts); free(wk[t].keep); free(wk[t].stage); free(wk[t].pstage); }
     if (!rc) rc = atomic_load(&j->err);
     for (uint32_t c = 0; c < j->n_ctx; ++c) pthread_mutex_destroy(&j->submit_mu[c]);
     if (st) {
@@ -516,13 +610,14 @@ int qk_frame_mem_mt(const qk_chunk_sink *sink, const uint8_t *data, size_t n, in
         st->long_lines = j->long_lines;
         st->unterminated = j->unterminated;
         st->fastq = j->fastq;
+        st->sink_bytes = j->sink_bytes;
     }
     free(j);
     return rc;
 }
 
 /* ---- the sink that counts: chunk slots of one context per GPU ------------------------------------ */
-typedef struct { qk_ctx *ctx[QK_MT_MAX_CTX]; } ctx_sink;
+typedef struct { qk_ctx *ctx[QK_MT_MAX_CTX]; int packed; } ctx_sink;
 static uint8_t *cs_buffer(void *u, uint32_t c, uint32_t s) { return qk_slot_host_buffer(((ctx_sink *)u)->ctx[c], s); }
 static int cs_ready(void *u, uint32_t c, uint32_t s) { return qk_slot_ready(((ctx_sink *)u)->ctx[c], s); }
 static int cs_wait(void *u, uint32_t c, uint32_t s) { return qk_wait_slot(((ctx_sink *)u)->ctx[c], s); }
@@ -530,6 +625,7 @@ static int cs_submit(void *u, uint32_t c, uint32_t s, uint64_t seq, size_t n_byt
 {
     (void)seq;                              /* counting is an integer sum: chunk order does not matter */
     qk_ctx *ctx = ((ctx_sink *)u)->ctx[c];
+    if (((ctx_sink *)u)->packed) return qk_submit_packed(ctx, s, qk_slot_host_buffer(ctx, s), n_bytes, n_lines);
     return qk_submit(ctx, s, qk_slot_host_buffer(ctx, s), n_bytes, NULL, n_lines); /* "sem_post", Q.c:431-432 */
 }
 
@@ -538,7 +634,11 @@ int qk_count_mem_mt(qk_ctx *const *ctxs, uint32_t n_ctx, const uint8_t *data, si
 {
     if (!ctxs || n_ctx < 1 || n_ctx > QK_MT_MAX_CTX || (!data && n)) return QK_ERR_ARG;
     ctx_sink cs;
-    qk_chunk_sink sink = {&cs, n_ctx, 0, 0, cs_buffer, cs_ready, cs_wait, cs_submit};
+    qk_chunk_sink sink = {&cs, n_ctx, 0, 0, cs_buffer, cs_ready, cs_wait, cs_submit, 0};
+    /* Packed chunks (2-bit codes + reset flags, 0.375 bytes per position: see qk_chunk_sink) when every context counts
+     * with the dictionary-order kernel, the only one that reads them (3 <= k <= 31).  QK_PACKED=0 ships the text. */
+    const char *pk = getenv("QK_PACKED");
+    cs.packed = pk ? atoi(pk) != 0 : QK_PACKED_DEFAULT;
     for (uint32_t c = 0; c < n_ctx; ++c) {
         uint32_t ns = 0;
         size_t cap = 0;
@@ -547,7 +647,10 @@ int qk_count_mem_mt(qk_ctx *const *ctxs, uint32_t n_ctx, const uint8_t *data, si
         if (c == 0) { sink.n_slots = ns; sink.cap = cap; }
         else if (ns != sink.n_slots || cap != sink.cap) return QK_ERR_ARG;   /* same slot geometry everywhere */
         cs.ctx[c] = ctxs[c];
+        qk_table_desc desc;
+        if (qk_dict_describe(ctxs[c], &desc) != QK_OK || !desc.has_ext) cs.packed = 0;
     }
+    sink.packed = cs.packed;
     int rc = qk_frame_mem_mt(&sink, data, n, seekable, threads, st);
     for (uint32_t c = 0; c < n_ctx; ++c) {
         int r2 = qk_sync(ctxs[c]);                                    /* drain + join, Q.c:458-479 */
@@ -580,7 +683,8 @@ int qk_bench_framer(const uint8_t *data, size_t n, uint32_t threads, int repeats
         if (!ns.buf[s]) { for (uint32_t t = 0; t < s; ++t) free(ns.buf[t]); return QK_ERR_NOMEM; }
         memset(ns.buf[s], 0, cap);
     }
-    qk_chunk_sink sink = {&ns, 1, n_slots, cap, ns_buffer, ns_ready, ns_wait, ns_submit};
+    const char *pk = getenv("QK_PACKED");
+    qk_chunk_sink sink = {&ns, 1, n_slots, cap, ns_buffer, ns_ready, ns_wait, ns_submit, pk ? atoi(pk) != 0 : QK_PACKED_DEFAULT};
     int rc = qk_frame_mem_mt(&sink, data, n, 1, threads, NULL);    /* warm-up */
     atomic_store(&ns.bytes, 0);
     struct timespec t0, t1;

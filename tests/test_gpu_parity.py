@@ -135,11 +135,14 @@ def test_gzip_input(qk, tmp_path):
     assert res.returncode == 1 and "Counting failed" in res.stdout                # a truncated file is an error, not a short count
 
 
+@pytest.mark.parametrize("packed", ["text", "packed"])
 @pytest.mark.parametrize("case", golden_cases())
-def test_golden_with_the_multithreaded_host_framer(case, qk, tmp_path):
+def test_golden_with_the_multithreaded_host_framer(case, packed, qk, tmp_path, monkeypatch):
     """qk_count_file_mt / qk_count_mem_mt: host threads frame blocks of the input in parallel and ship only
-    the sequence lines -- same .bin as the reference wrote, from a file (mapped), from memory, in pipe
-    mode, with small chunks and few slots."""
+    the sequence lines -- as text, or packed to 2-bit codes + reset flags (24 bytes per 64 positions, read by
+    qk_count_ext32_kernel<.., PACKED>) -- same .bin as the reference wrote, from a file (mapped), from memory,
+    with small chunks and few slots."""
+    monkeypatch.setenv("QK_PACKED", "1" if packed == "packed" else "0")
     meta = golden_meta(case)
     d = GOLDEN / case
     want = np.fromfile(d / "expect.bin", dtype=np.uint16)
@@ -151,6 +154,11 @@ def test_golden_with_the_multithreaded_host_framer(case, qk, tmp_path):
             st = ctx.count_file_mt(d / meta["reads"], threads=threads)
             assert np.array_equal(ctx.finish(), want)
             assert ctx.stats()["total_kmers"] == meta["total_kmers"]
+            framed = st["bases"] + st["lines"]
+            if packed == "packed":      # (every 512 KiB block is filled up to a multiple of 64 positions)
+                assert 0.375 * framed <= st["sink_bytes"] <= 0.375 * framed + 24 * (2 + len(raw) // (16 << 10)) and st["sink_bytes"] % 24 == 0
+            else:
+                assert st["sink_bytes"] == framed
             ctx.reset()
             st2 = ctx.count_mem_mt(buf.ctypes.data, buf.size, seekable=True, threads=threads)
             assert np.array_equal(ctx.finish(), want) and st2 == st
@@ -265,6 +273,52 @@ def test_against_oracle_seeded(kind, mid_dict, qk, oracle, synth, tmp_path):
     for key in ("total_kmers", "hits", "lines", "bases"):
         assert st[key] == ost[key], key
     assert st["hits"] > 0.4 * st["total_kmers"]
+
+
+@pytest.mark.parametrize("kind", ["fastq", "lower_crlf", "hifi"])
+def test_packed_chunks_against_oracle(kind, mid_dict, qk, oracle, synth, tmp_path, monkeypatch):
+    """Packed chunks from the host framer (2-bit codes + reset flags) give the oracle's depths: many reads, N blocks,
+    lower case and CR (bases like any other, Q.c:411), lines beyond the 65,536 run-counter wrap; one chunk or many."""
+    args = {
+        "fastq": ["--n", 150000, "--len", 150, "--fastq", "--rand-qual"],
+        "lower_crlf": ["--n", 50000, "--len", 101, "--lower-ppm", 300000, "--crlf"],
+        "hifi": ["--n", 300, "--len", 15000, "--hifi", "--max-len", 99998, "--err-ppm", 1000],
+    }[kind]
+    reads = tmp_path / ("reads.fq" if kind == "fastq" else "reads.fa")
+    synth("reads", "--ref", mid_dict / "ref.fa", "--out", reads, "--seed", 4321, *args)
+    want, ost = oracle.count_bin(mid_dict / "ref.fa.qm", reads)
+    monkeypatch.setenv("QK_PACKED", "1")
+    for n_slots, cap, threads in ((3, 1 << 20, 6), (8, 32 << 20, 3)):
+        with qk.Context(device=0, n_slots=n_slots, chunk_capacity=cap) as ctx:
+            ctx.load_dictionary(mid_dict / "ref.fa.qm")
+            st = ctx.count_file_mt(reads, threads=threads)
+            got, gst = ctx.finish(), ctx.stats()
+            assert np.array_equal(got, want)
+            assert (gst["total_kmers"], gst["hits"], st["lines"], st["bases"]) == (ost["total_kmers"], ost["hits"], ost["lines"], ost["bases"])
+            assert st["sink_bytes"] < 0.4 * (st["bases"] + st["lines"])       # it WAS packed
+
+
+def test_packed_chunk_api(qk, oracle, gpu_ctx, tmp_path):
+    """qk_submit_packed by hand: a chunk packed in numpy counts like its text; sizes must be whole groups of 64
+    positions; a dictionary without the dictionary-order kernel (k = 32) refuses packed chunks."""
+    d = GOLDEN / "k30_fasta_t0"
+    meta = golden_meta("k30_fasta_t0")
+    want = np.fromfile(d / "expect.bin", dtype=np.uint16)
+    framed, _ = oracle.frame_file(d / meta["reads"])
+    from test_host import pack_model                                           # the format, stated in numpy
+    packed = np.frombuffer(pack_model(framed), dtype=np.uint8)
+    n_pos = packed.size // 24 * 64
+    assert n_pos - 64 < len(framed) <= n_pos
+    gpu_ctx.load_dictionary(d / "ref.fa.qm")
+    gpu_ctx.submit_packed(packed, n_pos)
+    assert np.array_equal(gpu_ctx.finish(), want) and gpu_ctx.stats()["total_kmers"] == meta["total_kmers"]
+    with pytest.raises(qk.QkError):
+        gpu_ctx.submit_packed(packed, n_pos - 16)
+    keys, nxt, first = oracle_binding.build_qm_arrays(oracle, np.arange(1, 50, dtype=np.uint64) * 104729, 256)
+    gpu_ctx.load_dictionary_arrays(32, keys, nxt, first)
+    with pytest.raises(qk.QkError) as e:
+        gpu_ctx.submit_packed(packed, n_pos)
+    assert e.value.code == 4                                                   # QK_ERR_STATE
 
 
 @pytest.mark.parametrize("k", [3, 5, 12, 20, 25, 29, 30, 31])

@@ -416,6 +416,89 @@ def test_mt_framer_edges(qk):
         qk.frame_mt(b">x\n" + base(300000) + b"\n", threads=2, cap=200000)
 
 
+def canonical_text(framed: bytes) -> bytes:
+    """What the count kernels keep of a framed stream: per byte its 2-bit code (Q.c:411) and whether it resets the
+    register ('N', '\\n': Q.c:403-404) -- written back as text (A C T G for the codes 0..3), empty lines dropped."""
+    b = np.frombuffer(framed, dtype=np.uint8)
+    out = np.frombuffer(b"ACTG", dtype=np.uint8)[(b >> 1) & 3].copy()
+    out[b == ord("N")] = ord("N")
+    out[b == ord("\n")] = ord("\n")
+    return b"".join(l + b"\n" for l in out.tobytes().split(b"\n") if l)
+
+
+def packed_text(qk, chunks) -> bytes:
+    out = []
+    for c in chunks:
+        codes, flags = qk.unpack_chunk(c)
+        t = np.frombuffer(b"ACTG", dtype=np.uint8)[codes].copy()
+        assert set(np.unique(codes[flags == 1])) <= {1, 3}          # a flag sits on a '\n' (code 1) or an 'N' (code 3)
+        t[(flags == 1) & (codes == 3)] = ord("N")
+        t[(flags == 1) & (codes == 1)] = ord("\n")
+        assert t.size % 64 == 0 and t[-1] == ord("\n")
+        out.append(t.tobytes())
+    return b"".join(l + b"\n" for l in b"".join(out).split(b"\n") if l)
+
+
+@pytest.mark.parametrize("fastq_like", [False, True])
+def test_mt_framer_packed_chunks(fastq_like, qk, oracle, tmp_path):
+    """Packed chunks (24 bytes per 64 positions: 2-bit codes + reset flags) say exactly what the text chunks say to the
+    count kernels: same codes, same resets, in the same order; only empty lines are added (every block is filled up
+    to a multiple of 64 positions).  AVX-512 and scalar packers, any thread count, malformed streams."""
+    from conftest import weird_stream
+    rng = np.random.default_rng(4242 + fastq_like)
+    seq = "".join(rng.choice(list("ACGTacgtNn"), size=6000))
+    text = weird_stream(rng, seq, fastq_like, 9000).encode()
+    (tmp_path / "w.txt").write_bytes(text)
+    want, ost = oracle.frame_file(tmp_path / "w.txt")
+    for env in ({}, {"QK_NO_AVX512": "1"}, {"QK_FRAMER_NT": "0"}):
+        os.environ.update(env)
+        try:
+            for threads, n_ctx, n_slots, cap, busy in ((1, 1, 2, 200000, 0), (5, 2, 3, 300032, 3), (3, 1, 4, 1 << 20, 0)):
+                chunks, who, st = qk.frame_mt(text, threads=threads, n_ctx=n_ctx, n_slots=n_slots, cap=cap, busy_every=busy, packed=True)
+                assert packed_text(qk, chunks) == canonical_text(want), (env, threads)
+                assert (st["lines"], st["bases"], st["fastq"]) == (ost["lines"], ost["bases"], ost["fastq"])
+                assert all(len(c) % 24 == 0 and len(c) // 24 * 64 <= cap for c in chunks) and sum(l for _, l in who) == ost["lines"]
+        finally:
+            for k in env:
+                del os.environ[k]
+    # edges: nothing, a lone unterminated line, lines of every length around the group size, one of the maximum length
+    base = lambda n: bytes(rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), size=n))
+    for data in (b"", b"ACGT", b">h\nAC", b"".join(b">r\n" + base(n) + b"\n" for n in range(0, 200)), b">x\n" + base(99998) + b"\n" + base(63) + b"\n"):
+        ref_chunks, rst = qk.frame(data, seekable=True, chunk_capacity=400000)
+        for threads in (1, 4):
+            chunks, _, st = qk.frame_mt(data, threads=threads, cap=400000, packed=True)
+            assert packed_text(qk, chunks) == canonical_text(b"".join(ref_chunks))
+            assert (st["lines"], st["bases"], st["unterminated"]) == (rst["lines"], rst["bases"], rst["unterminated"])
+
+
+def pack_model(framed: bytes) -> bytes:
+    """The packed-chunk format stated in numpy (include/qk_host.h, struct qk_chunk_sink): the stream filled up with
+    '\\n' to a multiple of 64 positions; per 64 positions four little-endian 32-bit words of 2-bit codes (16 positions per
+    word, the first in the top pair) and 64 flags ('N' or '\\n'), bit p = position p."""
+    text = np.frombuffer(framed + b"\n" * (-len(framed) % 64), dtype=np.uint8)
+    codes = ((text >> 1) & 3).astype(np.uint32).reshape(-1, 4, 16)
+    words = (codes << (2 * (15 - np.arange(16, dtype=np.uint32)))[None, None, :]).sum(axis=2, dtype=np.uint64).astype("<u4")
+    flags = np.packbits(((text == ord("N")) | (text == ord("\n"))).reshape(-1, 64), axis=1, bitorder="little")
+    return np.concatenate([words.view(np.uint8).reshape(-1, 16), flags], axis=1).tobytes()
+
+
+def test_packed_chunk_bytes_are_the_documented_format(qk):
+    """One block in, one packed chunk out: byte for byte what the format says (AVX-512 and scalar packers); this is
+    the layout qk_fetch16<true> (csrc/qk_count.cu) reads, held to the same model in tests/test_gpu_parity.py."""
+    rng = np.random.default_rng(0)
+    framed = b"".join(bytes(rng.choice(np.frombuffer(b"ACGTNacgtn\r", dtype=np.uint8), size=int(rng.integers(0, 300)))) + b"\n" for _ in range(500))
+    raw = b">h\n" + framed.replace(b"\n", b"\n>h\n")[:-3]
+    for env in ({}, {"QK_NO_AVX512": "1"}):
+        os.environ.update(env)
+        try:
+            chunks, _, st = qk.frame_mt(raw, threads=1, cap=4 << 20, packed=True)
+            assert len(chunks) == 1 and chunks[0] == pack_model(framed), env
+            assert st["sink_bytes"] == len(chunks[0])
+        finally:
+            for k in env:
+                del os.environ[k]
+
+
 # ---------------------------------------------------------------------------- BAM input
 def make_bam(reads, refs=(("chr1", 1000000),), text="@HD\tVN:1.6\n"):
     """A minimal BAM (SAM spec 4.2), uncompressed bytes: reads = [(name, flag, sequence)]."""
