@@ -40,7 +40,7 @@
 
 #define QK_MT_MAX_CTX 16
 #define QK_MT_MAX_THREADS 128
-#define QK_PACKED_DEFAULT 0          /* qk_count_mem_mt / qk_count_file_mt ship packed chunks unless QK_PACKED=0 */
+#define QK_PACKED_DEFAULT 1          /* qk_count_mem_mt / qk_count_file_mt ship packed chunks unless QK_PACKED=0 */
 
 enum { SLOT_FREE = 0, SLOT_FILLING = 1, SLOT_SUBMITTING = 2, SLOT_SUBMITTED = 3 };
 
