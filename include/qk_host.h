@@ -124,8 +124,10 @@ int qk_count_raw_file_mt(qk_ctx *ctx, const char *reads_path, uint32_t threads, 
 /* ---- all host cores frame, any GPU counts (host/qk_framer_mt.c) ---------------------------------
  * The framing rules above applied by `threads` workers (0 = QK_FRAMER_THREADS or every online
  * CPU) to blocks of the input in parallel; only the sequence lines are copied into the pinned
- * slot buffers, so FASTQ crosses the host link at ~1.25 instead of ~2.6 bytes per k-mer.  The
- * framed chunks go to whichever of the n_ctx contexts (same slot count and capacity; one per
+ * slot buffers, so FASTQ crosses the host link at ~1.25 instead of ~2.6 bytes per k-mer -- and at
+ * ~0.47 when they go as PACKED chunks (2-bit codes + reset flags, see qk_chunk_sink.packed and
+ * qk_submit_packed), which they do when every context counts with the dictionary-order kernel
+ * (3 <= k <= 31) unless QK_PACKED=0 is set.  The framed chunks go to whichever of the n_ctx contexts (same slot count and capacity; one per
  * GPU; same dictionary) has a slot free first.  Same result, byte for byte, as qk_count_framer /
  * qk_count_raw_mem.  qk_count_file_mt maps a regular file (the page cache is the input buffer);
  * pipes and gzip files are counted by ctxs[0] through the sequential stream path. */
