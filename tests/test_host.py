@@ -499,6 +499,29 @@ def test_packed_chunk_bytes_are_the_documented_format(qk):
                 del os.environ[k]
 
 
+def test_mt_framer_on_arbitrary_bytes(qk):
+    """Any byte soup -- NULs, high bytes, '>' and '@' anywhere, CR, runs of newlines -- frames like the single-threaded
+    statement of the rules, as text and packed; the packed chunk says of every byte what Q.c:403-411 would."""
+    from hypothesis import given, settings, strategies as st_
+
+    alphabet = st_.sampled_from([b"A", b"C", b"G", b"T", b"N", b"n", b"a", b"\n", b"\n", b">", b"@", b"+", b"\r", b"\x00", b"\xff", b"I", b" "])
+
+    @settings(max_examples=60, deadline=None)
+    @given(st_.lists(alphabet, min_size=0, max_size=3000), st_.integers(1, 5), st_.booleans())
+    def check(parts, threads, seekable):
+        data = b"".join(parts) * 40            # long enough for several 16 KiB blocks at this chunk capacity
+        ref_chunks, rst = qk.frame(data, seekable=seekable, chunk_capacity=200000)
+        want = b"".join(ref_chunks)
+        chunks, _, st = qk.frame_mt(data, seekable=seekable, threads=threads, cap=200000)
+        assert b"".join(chunks) == want
+        assert (st["lines"], st["bases"], st["unterminated"], st["fastq"]) == (rst["lines"], rst["bases"], rst["unterminated"], rst["fastq"])
+        pchunks, _, pst = qk.frame_mt(data, seekable=seekable, threads=threads, cap=200000, packed=True)
+        assert packed_text(qk, pchunks) == canonical_text(want)
+        assert (pst["lines"], pst["bases"]) == (rst["lines"], rst["bases"])
+
+    check()
+
+
 # ---------------------------------------------------------------------------- BAM input
 def make_bam(reads, refs=(("chr1", 1000000),), text="@HD\tVN:1.6\n"):
     """A minimal BAM (SAM spec 4.2), uncompressed bytes: reads = [(name, flag, sequence)]."""
