@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Host-side measurements for the end-to-end roofline: memory bandwidth of the box (read, memcpy) and the
 multi-threaded framer alone (raw GB/s in, framed GB/s out) by thread count, with and without the staged
-non-temporal stores.  No GPU needed.  usage: tools/framer_probe.py [reads=2000000]"""
+non-temporal stores, packed chunks or text.  No GPU needed.  usage: tools/framer_probe.py [reads=2000000]"""
 import json
 import os
 import sys
@@ -27,10 +27,11 @@ for t in sorted({1, 4, 8, cpus}):
     if t <= cpus:
         r, c = qk.bench_host_memory(256 << 20, t)
         out["host_memory"][t] = {"read_gbs": r, "memcpy_gbs": c}
-for nt in ("1", "0"):
+for packed, nt in (("1", "1"), ("0", "1"), ("0", "0")):       # packed chunks (the default); text; text without the staged non-temporal stores
+    os.environ["QK_PACKED"] = packed
     os.environ["QK_FRAMER_NT"] = nt
     for t in sorted({1, 4, 8, 12, cpus}):
         if t <= cpus:
             a, b = qk.bench_framer(data.ctypes.data, data.size, threads=t, repeats=3)
-            out["framer"].append({"nt_stores": nt == "1", "threads": t, "raw_gbs": a, "framed_gbs": b})
+            out["framer"].append({"packed": packed == "1", "nt_stores": nt == "1", "threads": t, "raw_gbs": a, "out_gbs": b})   # out: bytes of text, or positions (0.375 bytes each) when packed
 print(json.dumps(out))
