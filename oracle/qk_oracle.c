@@ -14,8 +14,9 @@
  * and, when oracle/_ref/quicKmer2 is present, against live runs of it.
  *
  * Every function cites the lines of QuicKmer.c ("Q.c") it restates.  It is a
- * restatement, not a copy: serial, single-threaded (the reference's result does not
- * depend on -t, Q.c:291 vs Q.c:443), with explicit handling of the two inputs on which
+ * restatement, not a copy: serial, single-threaded (the reference's result depends on
+ * -t in one way only, the zero padding of its last worker batch: qko_fifo_padding), with
+ * explicit handling of the two inputs on which
  * the reference has undefined behaviour (flagged in qko_stats.undefined_lines).
  */
 #define _FILE_OFFSET_BITS 64
@@ -376,6 +377,102 @@ int qko_count_t(const char *ref_prefix, const char *reads_path, const char *out_
     qko_dict_free(&d);
     return 0;
 }
+
+/* ---- `search` pass 1: Q.c:824-923 (hash_from_fasta) with the table growth of Q.c:738-822 ------------------------
+ * SURVEY 8(f) rank 4, the oracle half: which canonical k-mers the reference genome holds and how often.  Differences
+ * from `count`'s codec (qko_count_line) that a device version has to reproduce:
+ *   - the FASTA is read 199 bytes at a time (fgets(buf, 200)); the register is NOT reset at a line end, only at a
+ *     line that starts with '>' and at 'N' -- a sequence continues over its lines (and a header line longer than
+ *     199 bytes continues as sequence); reading stops at a piece that starts with a NUL byte;
+ *   - the run counter saturates at k (no 16-bit wrap); the key 0 (poly-A / poly-T) is never stored;
+ *   - occurrences saturate at 255;
+ *   - when more than 0.8 of the slots are taken -- checked after every piece -- the table doubles and is re-probed IN
+ *     PLACE (upper half of the old range downwards, then the lower half upwards).  Which slot a key ends up in
+ *     depends on that order, so it is restated as it is; the totals the reference prints came out the same for
+ *     every starting size tried (tests/test_oracle.py), i.e. the sweep loses no key.
+ * Returns 0 and fills *out (keys/occ are malloc'd, hash_size slots each). */
+typedef struct {
+    uint64_t hash_size;   /* final Hash_size                                     */
+    uint64_t distinct;    /* `count`: keys entered (Q.c:877), re-entries included */
+    uint64_t unique;      /* slots with occurrence 1 (Q.c:916-921)               */
+    uint64_t resizes;
+    uint64_t *keys;
+    uint8_t *occ;
+} qko_pass1;
+
+static uint64_t qko_p1_find(const uint64_t *keys, uint64_t n_slots, uint64_t key)   /* Q.c:90-99 on a bare array */
+{
+    uint64_t s = qko_djb(key) & (n_slots - 1);
+    const int64_t step = (s & (n_slots >> 1)) ? -1 : 1;
+    while (keys[s] != 0 && keys[s] != key) s = (uint64_t)((int64_t)s + step);
+    return s;
+}
+
+static void qko_p1_rehome(uint64_t *keys, uint8_t *occ, uint64_t n_slots, uint64_t at)   /* one step of Q.c:760-790 */
+{
+    if (!keys[at]) return;
+    const uint64_t to = qko_p1_find(keys, n_slots, keys[at]);
+    if (to == at) return;
+    keys[to] = keys[at]; keys[at] = 0;
+    occ[to] = occ[at];   occ[at] = 0;
+}
+
+int qko_search_pass1(const char *fasta_path, uint8_t k, uint64_t hash_size, qko_pass1 *out)
+{
+    memset(out, 0, sizeof *out);
+    FILE *f = fopen(fasta_path, "r");
+    if (!f || k < 1 || k > 32 || hash_size < 2 || (hash_size & (hash_size - 1))) { if (f) fclose(f); return 1; }
+    uint64_t *keys = calloc(hash_size, sizeof *keys);
+    uint8_t *occ = calloc(hash_size, 1);
+    if (!keys || !occ) { fclose(f); return 2; }
+    const uint64_t mask = k < 32 ? (((uint64_t)1 << (2 * k)) - 1) : 0;       /* Q.c:860 on x86-64: 1 << 64 == 1 << 0 */
+    char buf[200];
+    uint8_t charge = 0;
+    uint64_t fwd = 0, rc = 0, distinct = 0, resizes = 0;
+    while (fgets(buf, 200, f) && buf[0]) {                                   /* Q.c:835 */
+        if (buf[0] == '>') { charge = 0; fwd = rc = 0; continue; }           /* Q.c:838-845 */
+        for (const char *p = buf; *p && *p != '\n'; ++p) {
+            if (*p == 'N') { charge = 0; fwd = rc = 0; continue; }           /* Q.c:848-854 */
+            const uint64_t code = ((uint8_t)*p >> 1) & 3;                    /* Q.c:855-861 */
+            fwd = (fwd << 2) | code;
+            rc = (rc | (((code - 2) & 3) << 60)) >> 2;
+            uint64_t key = fwd & mask;
+            if (key > rc) key = rc;
+            if (charge < k) ++charge;
+            if (!key || charge != k) continue;                               /* Q.c:864 */
+            const uint64_t s = qko_p1_find(keys, hash_size, key);            /* Q.c:866-875 */
+            if (!keys[s]) { keys[s] = key; ++distinct; }
+            if (occ[s] < 255) ++occ[s];                                      /* Q.c:888 */
+        }
+        if ((double)distinct > 0.8 * (double)hash_size) {                    /* Q.c:891-895 */
+            const uint64_t old = hash_size, grown = hash_size << 1;
+            uint64_t *k2 = realloc(keys, grown * sizeof *keys);
+            uint8_t *o2 = k2 ? realloc(occ, grown) : NULL;
+            if (!k2 || !o2) { free(k2 ? k2 : keys); free(occ); fclose(f); return 2; }
+            keys = k2; occ = o2;
+            memset(keys + old, 0, (grown - old) * sizeof *keys);
+            memset(occ + old, 0, grown - old);     /* (the reference leaves realloc's bytes; glibc hands back zero pages
+                                                    *  for tables of this size -- slots of empty keys, never read before
+                                                    *  they are written, Q.c:766) */
+            hash_size = grown;
+            for (uint64_t i = old - 1; i >= (old >> 1); --i) qko_p1_rehome(keys, occ, hash_size, i);   /* Q.c:758-772 */
+            for (uint64_t i = 0; i < (old >> 1); ++i) qko_p1_rehome(keys, occ, hash_size, i);         /* Q.c:773-788 */
+            ++resizes;
+        }
+    }
+    fclose(f);
+    uint64_t unique = 0;
+    for (uint64_t i = 0; i < hash_size; ++i) unique += occ[i] == 1;          /* Q.c:916-921 */
+    out->hash_size = hash_size;
+    out->distinct = distinct;
+    out->unique = unique;
+    out->resizes = resizes;
+    out->keys = keys;
+    out->occ = occ;
+    return 0;
+}
+
+void qko_pass1_free(qko_pass1 *p) { free(p->keys); free(p->occ); memset(p, 0, sizeof *p); }
 
 /* ---- est: window depths (Q.c:555-685), given the correction curve ----------------------------------
  * The reference gets its 401-float correction curve from `popen("smooth_GC_mrsfast.py <sample>.txt")`

@@ -28,6 +28,12 @@ class Stats(C.Structure):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
 
+class Pass1(C.Structure):
+    """qko_pass1 (oracle/qk_oracle.c)."""
+    _fields_ = [("hash_size", C.c_uint64), ("distinct", C.c_uint64), ("unique", C.c_uint64), ("resizes", C.c_uint64),
+                ("keys", C.POINTER(C.c_uint64)), ("occ", C.POINTER(C.c_uint8))]
+
+
 class Oracle:
     def __init__(self):
         if not LIB.exists():
@@ -49,7 +55,23 @@ class Oracle:
         L.qko_count_t.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint, C.POINTER(Stats)]
         L.qko_fifo_padding.restype = C.c_uint64
         L.qko_fifo_padding.argtypes = [C.POINTER(Dict), C.c_uint64, C.c_void_p]
+        L.qko_search_pass1.argtypes = [C.c_char_p, C.c_uint8, C.c_uint64, C.POINTER(Pass1)]
+        L.qko_pass1_free.argtypes = [C.POINTER(Pass1)]
         self.L = L
+
+    def search_pass1(self, fasta, k: int, hash_size: int) -> dict:
+        """`search` pass 1 (Q.c:824-923): the k-mer occurrence table of a reference FASTA.  Returns the figures the
+        reference prints (distinct = its `total`, unique) and the table as {key: occurrences}."""
+        p = Pass1()
+        rc = self.L.qko_search_pass1(os.fsencode(str(fasta)), k, hash_size, C.byref(p))
+        assert rc == 0, f"oracle search pass 1 failed: {rc}"
+        try:
+            keys = np.ctypeslib.as_array(p.keys, shape=(p.hash_size,)).copy()
+            occ = np.ctypeslib.as_array(p.occ, shape=(p.hash_size,)).copy()
+            return {"hash_size": int(p.hash_size), "distinct": int(p.distinct), "unique": int(p.unique), "resizes": int(p.resizes),
+                    "keys": keys, "occ": occ}
+        finally:
+            self.L.qko_pass1_free(C.byref(p))
 
     def djb(self, key: int) -> int:
         return self.L.qko_djb(key)

@@ -249,6 +249,41 @@ def test_chain_is_all_that_count_reads_of_a_dictionary(oracle, ref_binary, synth
     assert (tmp_path / "port.bin").read_bytes() == padded.tobytes() and st2["total_kmers"] == st["total_kmers"]
 
 
+@pytest.mark.parametrize("k,size", [(30, "4M"), (30, "256K"), (20, "256K"), (12, "1M"), (31, "512K")])
+def test_search_pass1_restatement_against_live_reference(k, size, oracle, ref_binary, synth, tmp_path):
+    """SURVEY 8(f) rank 4, oracle first: `search` pass 1 (hash_from_fasta, Q.c:824-923) restated -- sequences that run
+    over their lines, no 16-bit wrap, key 0 left out, occurrences capped at 255, and the in-place re-probing when the
+    table doubles -- against the two figures the reference prints after it ("Uniq count U, total T"), with the table
+    large enough from the start and with two or three doublings on the way."""
+    import re
+    if ref_binary is None:
+        pytest.skip("oracle/_ref/quicKmer2 not built here")
+    synth("ref", "--out", tmp_path / "ref.fa", "--bases", 900000, "--contigs", 4, "--seed", 100 + k, "--segdups", 12, "--segdup-len", 6000,
+          "--nblock", 1500)
+    with open(tmp_path / "ref.fa", "a") as f:
+        f.write(">polyA_and_a_long_header " + "x" * 300 + "\n" + "A" * 150 + "\n" + "ACGT" * 40 + "\n")
+    res = subprocess.run([str(ref_binary), "search", "-k", str(k), "-e", "0", "-s", size, "ref.fa"], cwd=tmp_path, capture_output=True, text=True,
+                         errors="replace")
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr
+    m = re.search(r"Uniq count (\d+), total (\d+)", res.stdout)
+    assert m, res.stdout[-2000:]
+    slots = int(size[:-1]) << (20 if size.endswith("M") else 10)
+    p1 = oracle.search_pass1(tmp_path / "ref.fa", k, slots)
+    assert (p1["unique"], p1["distinct"]) == (int(m.group(1)), int(m.group(2)))
+    assert (p1["resizes"] > 0) == (size == "256K" or (size, k) == ("512K", 31))
+    grown = oracle.search_pass1(tmp_path / "ref.fa", k, 4096)           # eight or nine doublings: the sweep loses no key
+    assert (grown["unique"], grown["distinct"]) == (p1["unique"], p1["distinct"]) and grown["resizes"] >= 8
+    occupied = p1["keys"] != 0
+    assert occupied.sum() == p1["distinct"] and (p1["occ"][~occupied] == 0).all() and p1["occ"][occupied].min() >= 1
+    if k >= 20:                                   # duplicated stretches: some k-mers occur more than once
+        assert 0.5 * p1["distinct"] < p1["unique"] < p1["distinct"]
+    # the dictionary `search -e 0` goes on to write holds exactly the k-mers that occur once
+    raw = (tmp_path / "ref.fa.qm").read_bytes()
+    H = int.from_bytes(raw[8:16], "little")
+    written = np.frombuffer(raw, dtype="<u8", count=H, offset=24)
+    assert np.array_equal(np.sort(written[written != 0]), np.sort(p1["keys"][p1["occ"] == 1]))
+
+
 SMOOTH_STUB = """#!/usr/bin/env python3
 # stand-in for the reference's smooth_GC_mrsfast.py (LOWESS; needs numpy.float and matplotlib, absent here):
 # 401 float32 on stdout, a deterministic curve with the same range the real one has (clamped to [1/3, 3])
